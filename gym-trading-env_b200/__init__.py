@@ -1,0 +1,27 @@
+"""B200-native batched implementation of Gym-Trading-Env's per-step simulation hot path.
+
+Scope: `TradingEnv.step` + `Portfolio` math + log-return reward + done/truncated
+flags + windowed `_get_obs` + in-place auto-reset, for N independent envs in lockstep, as
+hand-written sm_100a CUDA kernels behind a C-ABI library (`include/gte_b200.h`).
+
+    import gym_trading_env_b200 as gte
+    env = gte.TradingVectorEnv(df, positions=[-1, 0, 1], windows=64, num_envs=65536, ...)
+    obs, infos = env.reset()
+    obs, reward, terminated, truncated, infos = env.step(actions)     # CUDA tensors
+"""
+from .data import SeriesArrays, frame_to_arrays, make_gbm_arrays, make_gbm_ohlcv  # noqa: F401
+
+__version__ = "0.1.0"
+
+_LAZY = {"TradingVectorEnv", "MultiDatasetTradingVectorEnv", "basic_reward_function",
+         "dynamic_feature_last_position_taken", "dynamic_feature_real_position", "shard_envs", "LazyInfos"}
+
+
+def __getattr__(name):          # torch / the CUDA library are only imported when an env class is used
+    if name in _LAZY:
+        from . import vector_env
+        return getattr(vector_env, name)
+    if name == "build":
+        from ._cabi import build
+        return build
+    raise AttributeError(name)

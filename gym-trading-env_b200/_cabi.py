@@ -1,0 +1,143 @@
+"""ctypes binding of ``libgte_b200.so`` — the only way Python reaches the GPU in this package.
+
+The structures mirror ``include/gte_b200.h`` field for field.  There is NO fallback: if the CUDA
+library is missing or fails to load, :func:`load` raises and every env constructor fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_PKG, "csrc")
+LIB_PATH = os.path.join(_CSRC, "libgte_b200.so")
+INCLUDE_DIR = os.path.join(os.path.dirname(_PKG), "include")
+SOURCES = ["gte_step.cu", "gte_obs.cu", "gte_cabi.cu"]
+HEADERS = ["gte_device.cuh", "gte_launch.h", os.path.join(INCLUDE_DIR, "gte_b200.h")]
+
+GTE_MAX_POSITIONS = 64
+GTE_MAX_DATASETS = 64
+GTE_N_METRICS = 8
+GTE_STEP_THREADS = 256
+GTE_MAX_PARTIAL_ROWS = 4096
+OBS_AUTO, OBS_GENERIC, OBS_VEC, OBS_TMA = 0, 1, 2, 3
+OBS_VARIANTS = {"auto": OBS_AUTO, "generic": OBS_GENERIC, "vec": OBS_VEC, "tma": OBS_TMA}
+METRIC_NAMES = ["episodes", "terminated", "truncated", "sum_portfolio_return", "sum_market_return",
+                "sum_episode_length", "sum_reward", "reserved"]
+
+
+class GteParams(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int32), ("n_positions", C.c_int32), ("windows", C.c_int32),
+        ("n_static", C.c_int32), ("n_dyn", C.c_int32), ("max_episode_duration", C.c_int32),
+        ("n_datasets", C.c_int32), ("initial_position_idx", C.c_int32),
+        ("episodes_between_switch", C.c_int32), ("plan_episodes", C.c_int32),
+        ("multi_dataset", C.c_int32), ("reserved0", C.c_int32),
+        ("t_stride", C.c_int64), ("env_id_offset", C.c_int64), ("seed", C.c_uint64),
+        ("fee", C.c_double), ("rate", C.c_double), ("v0", C.c_double), ("done_ratio", C.c_double),
+        ("positions", C.c_double * GTE_MAX_POSITIONS),
+    ]
+
+
+class GteData(C.Structure):
+    _fields_ = [
+        ("features", C.c_void_p), ("price", C.c_void_p), ("lengths", C.c_void_p),
+        ("window_table", C.c_void_p * 4), ("window_table_ds_stride", C.c_int64),
+    ]
+
+
+class GteState(C.Structure):
+    _fields_ = [
+        ("asset", C.c_void_p), ("fiat", C.c_void_p), ("interest_asset", C.c_void_p),
+        ("interest_fiat", C.c_void_p), ("pos_idx", C.c_void_p), ("step", C.c_void_p),
+        ("ep_start", C.c_void_p), ("dataset_idx", C.c_void_p), ("dyn_ring", C.c_void_p),
+        ("plan_cursor", C.c_void_p), ("ds_used", C.c_void_p), ("ds_episodes", C.c_void_p),
+        ("reset_plan", C.c_void_p), ("error_flag", C.c_void_p),
+    ]
+
+
+class GteStepOut(C.Structure):
+    _fields_ = [
+        ("reward", C.c_void_p), ("terminated", C.c_void_p), ("truncated", C.c_void_p),
+        ("valuation", C.c_void_p), ("real_position", C.c_void_p), ("info_idx", C.c_void_p),
+        ("info_step", C.c_void_p), ("pre_reset_portfolio", C.c_void_p),
+        ("metric_partials", C.c_void_p), ("metrics_step", C.c_void_p),
+        ("metrics_total", C.c_void_p), ("block_counter", C.c_void_p),
+    ]
+
+
+class GteInfo(C.Structure):
+    _fields_ = [
+        ("idx", C.c_void_p), ("step", C.c_void_p), ("position_index", C.c_void_p),
+        ("dataset_idx", C.c_void_p), ("position", C.c_void_p), ("real_position", C.c_void_p),
+        ("portfolio_valuation", C.c_void_p), ("data_close", C.c_void_p), ("distribution", C.c_void_p),
+    ]
+
+
+EXPORTS = ["gte_version", "gte_last_error", "gte_reset", "gte_step", "gte_gather_obs", "gte_info",
+           "gte_obs_variant_for"]
+
+
+def nvcc_command(out_path: str = LIB_PATH):
+    """The exact build line (sm_100a only; -fmad=false keeps fp64 math FMA-free, -lineinfo for ncu)."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+            "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-o", out_path] + \
+           [os.path.join(_CSRC, s) for s in SOURCES]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(_CSRC, s) for s in SOURCES] + \
+           [h if os.path.isabs(h) else os.path.join(_CSRC, h) for h in HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu into csrc/libgte_b200.so with nvcc (cross-compiles without a GPU)."""
+    if force or needs_build():
+        cmd = nvcc_command()
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library or raise — there is deliberately no CPU / PyTorch fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  gym_trading_env_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.gte_version.restype = C.c_int
+    lib.gte_last_error.restype = C.c_char_p
+    P = C.POINTER
+    lib.gte_reset.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+    lib.gte_step.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, P(GteStepOut), C.c_uint64,
+                             C.c_int, C.c_void_p]
+    lib.gte_gather_obs.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, C.c_int, C.c_void_p]
+    lib.gte_info.argtypes = [P(GteParams), P(GteData), P(GteState), P(GteInfo), C.c_void_p]
+    lib.gte_obs_variant_for.argtypes = [P(GteParams), P(GteData)]
+    for name in ("gte_reset", "gte_step", "gte_gather_obs", "gte_info", "gte_obs_variant_for"):
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    msg = load().gte_last_error().decode("utf-8", "replace")
+    if rc == -1:
+        raise ValueError(f"{what}: {msg}")
+    raise RuntimeError(f"{what}: {msg}")

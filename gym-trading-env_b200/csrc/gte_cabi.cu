@@ -1,0 +1,102 @@
+// gte_cabi.cu — the extern "C" boundary of libgte_b200.so (see include/gte_b200.h).
+// Argument validation + kernel enqueue; no allocation, no synchronisation, no hidden state except
+// the thread-local last-error string.
+#include <cstdio>
+#include <cstring>
+
+#include "gte_launch.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail_arg(const char* fn, const char* what) {
+    std::snprintf(g_err, sizeof(g_err), "%s: bad argument: %s", fn, what);
+    return GTE_ERR_ARG;
+}
+
+int check_cuda(const char* fn, cudaError_t e) {
+    if (e == cudaSuccess) return GTE_OK;
+    std::snprintf(g_err, sizeof(g_err), "%s: CUDA error %d (%s): %s", fn, (int)e, cudaGetErrorName(e),
+                  cudaGetErrorString(e));
+    return GTE_ERR_CUDA;
+}
+
+#define GTE_REQUIRE(fn, cond) do { if (!(cond)) return fail_arg(fn, #cond); } while (0)
+
+int check_common(const char* fn, const GteParams* p, const GteData* d, const GteState* s) {
+    GTE_REQUIRE(fn, p != nullptr && d != nullptr && s != nullptr);
+    GTE_REQUIRE(fn, p->n_envs > 0);
+    GTE_REQUIRE(fn, p->n_positions > 0 && p->n_positions <= GTE_MAX_POSITIONS);
+    GTE_REQUIRE(fn, p->windows >= 0);
+    GTE_REQUIRE(fn, p->n_static >= 0 && (p->n_dyn == 0 || p->n_dyn == 2) && p->n_static + p->n_dyn > 0);
+    GTE_REQUIRE(fn, p->n_datasets >= 1 && p->n_datasets <= GTE_MAX_DATASETS);
+    GTE_REQUIRE(fn, p->initial_position_idx >= -1 && p->initial_position_idx < p->n_positions);
+    GTE_REQUIRE(fn, p->episodes_between_switch >= 1);
+    GTE_REQUIRE(fn, p->plan_episodes >= 0);
+    GTE_REQUIRE(fn, p->t_stride >= 2);
+    GTE_REQUIRE(fn, p->v0 > 0.0);
+    GTE_REQUIRE(fn, d->price != nullptr && d->lengths != nullptr);
+    GTE_REQUIRE(fn, p->n_static == 0 || d->features != nullptr);
+    GTE_REQUIRE(fn, s->asset && s->fiat && s->interest_asset && s->interest_fiat);
+    GTE_REQUIRE(fn, s->pos_idx && s->step && s->ep_start && s->dataset_idx);
+    GTE_REQUIRE(fn, p->n_dyn == 0 || s->dyn_ring != nullptr);
+    GTE_REQUIRE(fn, s->plan_cursor && s->ds_used && s->ds_episodes && s->error_flag);
+    GTE_REQUIRE(fn, p->plan_episodes == 0 || s->reset_plan != nullptr);
+    return GTE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gte_version(void) { return GTE_VERSION; }
+
+const char* gte_last_error(void) { return g_err; }
+
+int gte_reset(const GteParams* params, const GteData* data, const GteState* state, const uint8_t* mask,
+              uint64_t tick, int first, void* stream) {
+    if (int rc = check_common("gte_reset", params, data, state)) return rc;
+    return check_cuda("gte_reset", gte::launch_reset(*params, *data, *state, mask, tick, first,
+                                                     static_cast<cudaStream_t>(stream)));
+}
+
+int gte_step(const GteParams* params, const GteData* data, const GteState* state, const int64_t* actions,
+             const GteStepOut* out, uint64_t tick, int autoreset, void* stream) {
+    if (int rc = check_common("gte_step", params, data, state)) return rc;
+    GTE_REQUIRE("gte_step", actions != nullptr && out != nullptr);
+    GTE_REQUIRE("gte_step", out->reward && out->terminated && out->truncated);
+    GTE_REQUIRE("gte_step", out->metric_partials && out->metrics_step && out->block_counter);
+    return check_cuda("gte_step", gte::launch_step(*params, *data, *state, actions, *out, tick, autoreset,
+                                                   static_cast<cudaStream_t>(stream)));
+}
+
+int gte_gather_obs(const GteParams* params, const GteData* data, const GteState* state, float* obs,
+                   int variant, void* stream) {
+    if (int rc = check_common("gte_gather_obs", params, data, state)) return rc;
+    GTE_REQUIRE("gte_gather_obs", obs != nullptr);
+    GTE_REQUIRE("gte_gather_obs", variant >= GTE_OBS_AUTO && variant <= GTE_OBS_TMA);
+    if (variant == GTE_OBS_VEC && !gte::obs_vec_supported(*params, *data))
+        return fail_arg("gte_gather_obs", "GTE_OBS_VEC needs windows>0, 16-byte-multiple windows and window tables");
+    if (variant == GTE_OBS_TMA && !gte::obs_tma_supported(*params, *data))
+        return fail_arg("gte_gather_obs", "GTE_OBS_TMA needs the GTE_OBS_VEC conditions and windows<=128");
+    return check_cuda("gte_gather_obs", gte::launch_obs(*params, *data, *state, obs, variant,
+                                                        static_cast<cudaStream_t>(stream)));
+}
+
+int gte_info(const GteParams* params, const GteData* data, const GteState* state, const GteInfo* info,
+             void* stream) {
+    if (int rc = check_common("gte_info", params, data, state)) return rc;
+    GTE_REQUIRE("gte_info", info != nullptr);
+    return check_cuda("gte_info", gte::launch_info(*params, *data, *state, *info,
+                                                   static_cast<cudaStream_t>(stream)));
+}
+
+int gte_obs_variant_for(const GteParams* params, const GteData* data) {
+    if (params == nullptr || data == nullptr) return GTE_ERR_ARG;
+    if (gte::obs_tma_supported(*params, *data)) return GTE_OBS_TMA;
+    if (gte::obs_vec_supported(*params, *data)) return GTE_OBS_VEC;
+    return GTE_OBS_GENERIC;
+}
+
+}  // extern "C"

@@ -1,0 +1,27 @@
+// gte_launch.h — host-side launchers shared between the kernel translation units and the C-ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gte_b200.h"
+
+namespace gte {
+
+int num_sms();
+int step_grid(int n_envs);
+
+cudaError_t launch_step(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
+                        const GteStepOut& O, uint64_t tick, int autoreset, cudaStream_t stream);
+cudaError_t launch_reset(const GteParams& P, const GteData& D, const GteState& S, const uint8_t* mask,
+                         uint64_t tick, int first, cudaStream_t stream);
+cudaError_t launch_info(const GteParams& P, const GteData& D, const GteState& S, const GteInfo& I,
+                        cudaStream_t stream);
+
+// Which gather variants the shape allows (vector/TMA need 16-byte-multiple windows + window tables).
+bool obs_vec_supported(const GteParams& P, const GteData& D);
+bool obs_tma_supported(const GteParams& P, const GteData& D);
+cudaError_t launch_obs(const GteParams& P, const GteData& D, const GteState& S, float* obs, int variant,
+                       cudaStream_t stream);
+
+}  // namespace gte

@@ -1,0 +1,359 @@
+// gte_obs.cu — observation-window gather kernels (sm_100a).  Replaces TradingEnv._get_obs
+// (environments.py:152-160): obs[env] = rows idx-W+1..idx of [static features | dynamic features].
+//
+// Three variants:
+//   generic : scalar gather, any shape (windows=None, odd row sizes); a power-of-two lane group per env.
+//   vec     : one warp per env; 128-bit ld.global.nc from the 16-byte-aligned window table (rows in the
+//             reference's own [t, F] layout, dynamic columns zero), dynamic columns patched in
+//             registers from the per-env ring, 128-bit coalesced st.global.  No shared memory.
+//   tma     : one warp per env per pipeline stage; cp.async.bulk (TMA, 1-D) pulls the whole window
+//             global->shared, lanes patch the dynamic columns in shared memory, cp.async.bulk pushes
+//             the finished window shared->global.  The LSU only touches the 8-byte ring entries.
+#include "gte_device.cuh"
+#include "gte_launch.h"
+
+namespace gte {
+
+// floor(e / d) for e*d < 2^32 via one umulhi; magic = ceil(2^32 / d)
+__device__ __forceinline__ uint32_t fast_div(uint32_t e, uint32_t magic) { return __umulhi(e, magic); }
+static inline uint32_t div_magic(uint32_t d) { return (uint32_t)(((1ull << 32) + d - 1) / d); }
+
+struct ObsShape {
+    int W, F, ns, nd;            // window rows, row floats, static cols, dynamic cols
+    uint32_t magicF;             // ceil(2^32 / F)
+    int row_bytes, win_bytes, n_vec;
+};
+
+static ObsShape make_shape(const GteParams& P) {
+    ObsShape s;
+    s.W = P.windows > 0 ? P.windows : 1;
+    s.ns = P.n_static;
+    s.nd = P.n_dyn;
+    s.F = s.ns + s.nd;
+    s.magicF = div_magic((uint32_t)s.F);
+    s.row_bytes = s.F * 4;
+    s.win_bytes = s.W * s.row_bytes;
+    s.n_vec = s.win_bytes / 16;
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------ generic
+template <int G>
+__global__ void __launch_bounds__(256)
+obs_generic_kernel(const GteParams P, const GteData D, const GteState S, float* __restrict__ obs,
+                   const ObsShape sh) {
+    const int groups_per_block = 256 / G;
+    const int lane = threadIdx.x % G;
+    const int64_t n_groups = (int64_t)gridDim.x * groups_per_block;
+    const int per_env = sh.W * sh.F;
+    for (int64_t env = (int64_t)blockIdx.x * groups_per_block + threadIdx.x / G; env < P.n_envs;
+         env += n_groups) {
+        const int ep_start = S.ep_start[env];
+        const int idx = ep_start + S.step[env];
+        const int ds = S.dataset_idx[env];
+        const int r0 = idx + 1 - sh.W;
+        const float* __restrict__ feat = D.features + ((int64_t)ds * P.t_stride + r0) * sh.ns;
+        const float* __restrict__ ring = S.dyn_ring + env * sh.W * 2;
+        float* __restrict__ out = obs + env * per_env;
+        for (int e = lane; e < per_env; e += G) {
+            const int w = e / sh.F, c = e - w * sh.F;
+            float v;
+            if (c < sh.ns) {
+                v = __ldg(feat + (int64_t)w * sh.ns + c);
+            } else {
+                const int r = r0 + w;
+                v = (r >= ep_start) ? ring[(r % sh.W) * 2 + (c - sh.ns)] : 0.0f;
+            }
+            out[e] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ float4 ld_nc_v4(const void* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_cs_v4(void* p, const float4& v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// byte address of the 16B-aligned copy of the window that starts at row r0 of dataset ds
+__device__ __forceinline__ const char* window_src(const GteData& D, const ObsShape& sh, int ds, int r0) {
+    const int64_t off = (int64_t)r0 * sh.row_bytes;
+    const int c = (int)((off >> 2) & 3);
+    // select without dynamic indexing (keeps the kernel parameters in the constant bank)
+    const float* t = (c == 0) ? D.window_table[0] : (c == 1) ? D.window_table[1]
+                   : (c == 2) ? D.window_table[2] : D.window_table[3];
+    return reinterpret_cast<const char*>(t) + (int64_t)ds * D.window_table_ds_stride + off;
+}
+
+// ------------------------------------------------------------------------------------------ vec
+template <bool PAIR>     // PAIR: n_dyn == 2 and F even -> the dynamic pair is an aligned float2
+__global__ void __launch_bounds__(256)
+obs_vec_kernel(const GteParams P, const GteData D, const GteState S, float* __restrict__ obs,
+               const ObsShape sh) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); env < P.n_envs;
+         env += n_warps) {
+        const int ep_start = S.ep_start[env];
+        const int idx = ep_start + S.step[env];
+        const int ds = S.dataset_idx[env];
+        const int r0 = idx + 1 - sh.W;
+        const int s0 = ((r0 % sh.W) + sh.W) % sh.W;            // ring slot of window row 0
+        const char* __restrict__ src = window_src(D, sh, ds, r0);
+        const float2* __restrict__ ring = reinterpret_cast<const float2*>(S.dyn_ring) + env * sh.W;
+        char* __restrict__ dst = reinterpret_cast<char*>(obs) + env * (int64_t)sh.win_bytes;
+        for (int j = lane; j < sh.n_vec; j += 32) {
+            float4 v = ld_nc_v4(src + 16 * j);
+            if (sh.nd > 0) {
+                float* pv = reinterpret_cast<float*>(&v);
+#pragma unroll
+                for (int k = 0; k < 4; k += (PAIR ? 2 : 1)) {
+                    const uint32_t e = 4u * j + k;
+                    const int w = (int)fast_div(e, sh.magicF);
+                    const int c = (int)e - w * sh.F;
+                    if (c >= sh.ns) {
+                        const int r = r0 + w;
+                        int slot = s0 + w;
+                        if (slot >= sh.W) slot -= sh.W;
+                        if (PAIR) {
+                            const float2 d = (r >= ep_start) ? __ldg(ring + slot) : make_float2(0.f, 0.f);
+                            pv[k] = d.x;
+                            pv[k + 1] = d.y;
+                        } else {
+                            const float* rf = reinterpret_cast<const float*>(ring + slot);
+                            pv[k] = (r >= ep_start) ? __ldg(rf + (c - sh.ns)) : 0.0f;
+                        }
+                    }
+                }
+            }
+            st_cs_v4(dst + 16 * j, v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ tma
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// TMA 1-D bulk copy shared -> global, tracked by the per-thread bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int kTmaWarps = 8;          // warps per CTA
+constexpr int kTmaStages = 4;         // window buffers per warp: current + kTmaDepth loading + 1 draining store
+constexpr int kTmaDepth = kTmaStages - 2;
+
+struct EnvMeta { int ep_start, idx, ds; };
+
+__device__ __forceinline__ EnvMeta load_meta(const GteState& S, int64_t env, int n_envs) {
+    EnvMeta m;
+    m.ep_start = 0; m.idx = 0; m.ds = 0;
+    if (env < n_envs) {
+        m.ep_start = S.ep_start[env];
+        m.idx = m.ep_start + S.step[env];
+        m.ds = S.dataset_idx[env];
+    }
+    return m;
+}
+
+// RPL = ring entries per lane = ceil(W / 32): the ring of the NEXT env is prefetched into registers
+// while the current window is in flight, so no HBM latency sits between "window landed" and "store".
+template <int RPL>
+__global__ void __launch_bounds__(kTmaWarps * 32)
+obs_tma_kernel(const GteParams P, const GteData D, const GteState S, float* __restrict__ obs,
+               const ObsShape sh) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bars[kTmaWarps][kTmaStages];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wbuf = smem_raw + (size_t)warp * kTmaStages * sh.win_bytes;
+    const int N = P.n_envs;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kTmaStages; ++s) mbar_init(&bars[warp][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const int64_t n_warps = (int64_t)gridDim.x * kTmaWarps;
+    const int64_t env0 = (int64_t)blockIdx.x * kTmaWarps + warp;
+
+    auto issue_load = [&](int64_t env, const EnvMeta& m, int stage) {   // lane 0 only
+        if (env < N) {
+            mbar_expect_tx(&bars[warp][stage], (uint32_t)sh.win_bytes);
+            bulk_g2s(wbuf + (size_t)stage * sh.win_bytes, window_src(D, sh, m.ds, m.idx + 1 - sh.W),
+                     (uint32_t)sh.win_bytes, &bars[warp][stage]);
+        }
+    };
+    auto load_ring = [&](int64_t env, float2 (&d)[RPL]) {
+        const float2* __restrict__ ring = reinterpret_cast<const float2*>(S.dyn_ring) + env * sh.W;
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) {
+            const int s = lane + 32 * q;
+            d[q] = (sh.nd > 0 && env < N && s < sh.W) ? __ldg(ring + s) : make_float2(0.f, 0.f);
+        }
+    };
+
+    // meta queue: mq[k] belongs to env + k*n_warps; mq[0..kTmaDepth] have their window load issued
+    EnvMeta mq[kTmaDepth + 2];
+#pragma unroll
+    for (int k = 0; k < kTmaDepth + 2; ++k) mq[k] = load_meta(S, env0 + (int64_t)k * n_warps, N);
+    float2 d_cur[RPL], d_nxt[RPL];
+    load_ring(env0, d_cur);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k <= kTmaDepth; ++k) issue_load(env0 + (int64_t)k * n_warps, mq[k], k);
+    }
+
+    int it = 0;
+    for (int64_t env = env0; env < N; env += n_warps, ++it) {
+        const int stage = it % kTmaStages;
+        const uint32_t parity = (uint32_t)(it / kTmaStages) & 1u;
+        unsigned char* buf = wbuf + (size_t)stage * sh.win_bytes;
+        const EnvMeta m = mq[0];
+        const int r0 = m.idx + 1 - sh.W;
+        const int s0 = ((r0 % sh.W) + sh.W) % sh.W;
+
+        // prefetch for later iterations (no use of the results in this iteration)
+        load_ring(env + n_warps, d_nxt);
+        const EnvMeta m_far = load_meta(S, env + (int64_t)(kTmaDepth + 2) * n_warps, N);
+
+        mbar_wait(&bars[warp][stage], parity);           // window (static cols + zero dyn cols) has landed
+
+        if (sh.nd > 0) {
+            float* fbuf = reinterpret_cast<float*>(buf);
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) {
+                const int s = lane + 32 * q;
+                int w = s - s0;
+                if (w < 0) w += sh.W;
+                if (s < sh.W && r0 + w >= m.ep_start) {
+                    float* qd = fbuf + w * sh.F + sh.ns;
+                    qd[0] = d_cur[q].x;
+                    if (sh.nd > 1) qd[1] = d_cur[q].y;
+                }
+            }
+            fence_proxy_async();                          // generic-proxy smem writes -> visible to TMA
+        }
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g(reinterpret_cast<char*>(obs) + env * (int64_t)sh.win_bytes, buf, (uint32_t)sh.win_bytes);
+            bulk_commit();
+            // refill the buffer whose store was committed in the PREVIOUS iteration: allow only the
+            // store just committed to be still reading shared memory.
+            bulk_wait_read<1>();
+            issue_load(env + (int64_t)(kTmaDepth + 1) * n_warps, mq[kTmaDepth + 1], (it + kTmaDepth + 1) % kTmaStages);
+        }
+        // rotate the queues
+#pragma unroll
+        for (int k = 0; k < kTmaDepth + 1; ++k) mq[k] = mq[k + 1];
+        mq[kTmaDepth + 1] = m_far;
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) d_cur[q] = d_nxt[q];
+    }
+    if (lane == 0) bulk_wait_read<0>();                   // smem must outlive the last store's reads
+}
+
+// ------------------------------------------------------------------------------------------ launch
+bool obs_vec_supported(const GteParams& P, const GteData& D) {
+    const ObsShape sh = make_shape(P);
+    if (P.windows <= 0 || sh.win_bytes % 16 != 0) return false;
+    if ((int64_t)sh.W * sh.F * (int64_t)sh.F >= (1ll << 31)) return false;     // fast_div range
+    for (int r = 0; r < 4; ++r) {                       // every residue class a window start can have
+        const int c = (int)((((int64_t)r * sh.row_bytes) >> 2) & 3);
+        if (D.window_table[c] == nullptr) return false;
+    }
+    return D.window_table_ds_stride % 16 == 0;
+}
+
+static size_t tma_smem_bytes(const ObsShape& sh) { return (size_t)kTmaWarps * kTmaStages * sh.win_bytes; }
+
+bool obs_tma_supported(const GteParams& P, const GteData& D) {
+    if (!obs_vec_supported(P, D)) return false;
+    const ObsShape sh = make_shape(P);
+    return sh.W <= 128 && tma_smem_bytes(sh) <= 200 * 1024;
+}
+
+cudaError_t launch_obs(const GteParams& P, const GteData& D, const GteState& S, float* obs, int variant,
+                       cudaStream_t stream) {
+    const ObsShape sh = make_shape(P);
+    if (variant == GTE_OBS_AUTO)
+        variant = obs_tma_supported(P, D) ? GTE_OBS_TMA : (obs_vec_supported(P, D) ? GTE_OBS_VEC : GTE_OBS_GENERIC);
+    const int sms = num_sms();
+    if (variant == GTE_OBS_GENERIC) {
+        const int per_env = sh.W * sh.F;
+        int G = 32;
+        while (G > 1 && G / 2 >= per_env) G /= 2;
+        const int64_t need = ((int64_t)P.n_envs * G + 255) / 256;
+        const int grid = (int)(need < (int64_t)sms * 16 ? need : (int64_t)sms * 16);
+        switch (G) {
+            case 32: obs_generic_kernel<32><<<grid, 256, 0, stream>>>(P, D, S, obs, sh); break;
+            case 16: obs_generic_kernel<16><<<grid, 256, 0, stream>>>(P, D, S, obs, sh); break;
+            case 8: obs_generic_kernel<8><<<grid, 256, 0, stream>>>(P, D, S, obs, sh); break;
+            case 4: obs_generic_kernel<4><<<grid, 256, 0, stream>>>(P, D, S, obs, sh); break;
+            case 2: obs_generic_kernel<2><<<grid, 256, 0, stream>>>(P, D, S, obs, sh); break;
+            default: obs_generic_kernel<1><<<grid, 256, 0, stream>>>(P, D, S, obs, sh); break;
+        }
+        return cudaGetLastError();
+    }
+    if (variant == GTE_OBS_VEC) {
+        if (!obs_vec_supported(P, D)) return cudaErrorInvalidValue;
+        const int64_t need = ((int64_t)P.n_envs + 7) / 8;
+        const int grid = (int)(need < (int64_t)sms * 8 ? need : (int64_t)sms * 8);
+        if (sh.nd == 2 && sh.F % 2 == 0) obs_vec_kernel<true><<<grid, 256, 0, stream>>>(P, D, S, obs, sh);
+        else obs_vec_kernel<false><<<grid, 256, 0, stream>>>(P, D, S, obs, sh);
+        return cudaGetLastError();
+    }
+    if (variant == GTE_OBS_TMA) {
+        if (!obs_tma_supported(P, D)) return cudaErrorInvalidValue;
+        const size_t smem = tma_smem_bytes(sh);
+        const int rpl = (sh.W + 31) / 32;
+        void (*kern)(const GteParams, const GteData, const GteState, float*, const ObsShape) =
+            rpl <= 1 ? obs_tma_kernel<1> : (rpl <= 2 ? obs_tma_kernel<2> : obs_tma_kernel<4>);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = (int)((220 * 1024) / (smem + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+        const int64_t need = ((int64_t)P.n_envs + kTmaWarps - 1) / kTmaWarps;
+        const int grid = (int)(need < (int64_t)sms * per_sm ? need : (int64_t)sms * per_sm);
+        kern<<<grid, kTmaWarps * 32, smem, stream>>>(P, D, S, obs, sh);
+        return cudaGetLastError();
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace gte

@@ -1,0 +1,105 @@
+"""Host-side data staging for the batched trading env (numpy / pandas only, runs once).
+
+Mirrors what the reference does once per DataFrame in ``TradingEnv._set_df``
+(`/root/reference/src/gym_trading_env/environments.py:128-143`):
+
+* feature columns  = every column whose name contains ``"feature"``, in DataFrame order (`:130`);
+* the float32 feature matrix is produced by *numpy's own* float64→float32 cast (`:141`), so the
+  device copy is bit-identical to the reference's ``_obs_array`` by construction;
+* the price vector is the float64 ``close`` column (`:143`).
+
+Also holds the synthetic GBM OHLCV generator every BASELINE.json config is quoted on
+(SURVEY.md §8(d)).  Nothing here touches the GPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import pandas as pd
+
+
+@dataclass
+class SeriesArrays:
+    """One market series, staged the way `_set_df` stages it (environments.py:128-143)."""
+
+    features: np.ndarray      # float32 [T, F_static]  (static "feature*" columns, df order)
+    price: np.ndarray         # float64 [T]            ("close")
+    feature_names: list
+    info: dict                # name -> float64 [T] for numeric non-feature columns (open/high/low/close/volume…)
+    index: np.ndarray | None  # datetime64 index values (infos["date"]); may be None
+
+    @property
+    def length(self) -> int:
+        return int(self.price.shape[0])
+
+
+def frame_to_arrays(df: pd.DataFrame) -> SeriesArrays:
+    """DataFrame -> arrays with the reference's column rules (environments.py:130-143)."""
+    if "close" not in df.columns:
+        raise ValueError("the DataFrame must contain a 'close' column (environments.py:143)")
+    feature_names = [c for c in df.columns if "feature" in c]                      # :130
+    feats = np.array(df[feature_names], dtype=np.float32) if feature_names else \
+        np.zeros((len(df), 0), dtype=np.float32)                                   # :141
+    feats = np.ascontiguousarray(feats.reshape(len(df), len(feature_names)))
+    price = np.ascontiguousarray(np.array(df["close"], dtype=np.float64))          # :143
+    info = {}
+    for c in df.columns:
+        if c in feature_names:
+            continue
+        col = df[c]
+        if pd.api.types.is_numeric_dtype(col.dtype):
+            info[c] = np.ascontiguousarray(np.array(col, dtype=np.float64))
+    index = df.index.values if isinstance(df.index, pd.DatetimeIndex) else None
+    return SeriesArrays(feats, price, feature_names, info, index)
+
+
+def make_gbm_ohlcv(T: int = 100_000, seed: int = 0, sigma: float = 0.002) -> pd.DataFrame:
+    """Synthetic GBM OHLCV frame with 8 static ``feature_*`` columns.
+
+    log-returns r_t ~ N(0, sigma); close = 100*exp(cumsum r); open/high/low jittered around it;
+    volume ~ U(1,2); hourly DatetimeIndex from 2000-01-01.  T+168 rows are generated, NaN rows
+    from the rolling/pct_change features are dropped, and exactly the last T rows are kept.
+    Feature recipe = `/root/reference/examples/example_environnement.py:18-22` plus three
+    longer-horizon columns so that F_static = 8 as BASELINE.json's configs state.
+    """
+    rng = np.random.default_rng(seed)
+    n = T + 168
+    r = rng.normal(0.0, sigma, size=n)
+    close = 100.0 * np.exp(np.cumsum(r))
+    open_ = close * (1.0 + rng.normal(0.0, 1e-3, size=n))
+    high = np.maximum(open_, close) * (1.0 + np.abs(rng.normal(0.0, 1e-3, size=n)))
+    low = np.minimum(open_, close) * (1.0 - np.abs(rng.normal(0.0, 1e-3, size=n)))
+    volume = rng.uniform(1.0, 2.0, size=n)
+    idx = pd.date_range("2000-01-01", periods=n, freq="h")
+    df = pd.DataFrame({"open": open_, "high": high, "low": low, "close": close, "volume": volume}, index=idx)
+    df["feature_close"] = df["close"].pct_change()
+    df["feature_open"] = df["open"] / df["close"]
+    df["feature_high"] = df["high"] / df["close"]
+    df["feature_low"] = df["low"] / df["close"]
+    df["feature_volume"] = df["volume"] / df["volume"].rolling(7 * 24).max()
+    df["feature_ret_8"] = df["close"].pct_change(8)
+    df["feature_ret_64"] = df["close"].pct_change(64)
+    df["feature_vol_64"] = df["close"].pct_change().rolling(64).std()
+    df = df.dropna()
+    df = df.iloc[-T:].copy()
+    assert len(df) == T, (len(df), T)
+    return df
+
+
+def make_gbm_arrays(T: int, seed: int = 0, sigma: float = 0.002, n_features: int = 8):
+    """Fast array-only GBM series for large benchmark tables (no pandas; C4 uses 32 x 1M rows).
+
+    Same price process as :func:`make_gbm_ohlcv`; features are cheap functions of the same
+    series (returns over several horizons), float32-cast by numpy as `_set_df` does (:141).
+    Used only where building a DataFrame per series would dominate set-up time.
+    """
+    rng = np.random.default_rng(seed)
+    r = rng.normal(0.0, sigma, size=T + 64)
+    close = 100.0 * np.exp(np.cumsum(r))
+    feats = np.empty((T, n_features), dtype=np.float64)
+    horizons = [1, 2, 4, 8, 16, 32, 64]
+    for j in range(n_features):
+        h = horizons[j % len(horizons)]
+        feats[:, j] = close[64:] / close[64 - h:T + 64 - h] - 1.0
+    return np.ascontiguousarray(feats.astype(np.float32)), np.ascontiguousarray(close[64:])

@@ -1,0 +1,557 @@
+"""gymnasium-VectorEnv-shaped host classes over the CUDA library (the drop-in boundary).
+
+``TradingVectorEnv`` keeps the constructor surface of the reference ``TradingEnv``
+(`/root/reference/src/gym_trading_env/environments.py:79-93`) and ``MultiDatasetTradingVectorEnv``
+that of ``MultiDatasetTradingEnv`` (`:365-371`), plus ``num_envs`` / ``device`` / ``seed``.
+``reset(seed, options) -> (obs, infos)`` and ``step(actions) -> (obs, rewards, terminations,
+truncations, infos)`` follow gymnasium's vector API with SAME-STEP in-place auto-reset: where an
+episode ended, reward/flags are the terminal step's and obs/state are those of the fresh episode.
+
+Everything numeric happens in ``libgte_b200.so`` (hand-written sm_100a kernels) through ctypes on raw
+``tensor.data_ptr()`` pointers; PyTorch only owns device memory and streams.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob as _glob
+from collections.abc import Mapping
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .data import SeriesArrays, frame_to_arrays
+
+
+# ---- names the reference exports and callers pass back in (identity-compared, never called) -------
+def basic_reward_function(history=None):
+    """Sentinel for the reference's ``basic_reward_function`` (environments.py:17-18):
+    ``log(valuation[-1] / valuation[-2])``.  Selects the fused device log-return reward."""
+    raise NotImplementedError("basic_reward_function is evaluated inside the CUDA step kernel")
+
+
+def dynamic_feature_last_position_taken(history=None):
+    """Sentinel for environments.py:20-21 (position taken at the last step)."""
+    raise NotImplementedError("evaluated inside the CUDA step kernel")
+
+
+def dynamic_feature_real_position(history=None):
+    """Sentinel for environments.py:23-24 (real position of the portfolio)."""
+    raise NotImplementedError("evaluated inside the CUDA step kernel")
+
+
+_DEFAULT_DYNAMIC = [dynamic_feature_last_position_taken, dynamic_feature_real_position]
+
+
+def _fn_name(f):
+    return getattr(f, "__name__", None)
+
+
+# ---- spaces: gymnasium's when importable, else shape/dtype stand-ins --------------------------------
+try:  # pragma: no cover - gymnasium is absent from the build image
+    from gymnasium import spaces as _spaces
+    _Discrete, _Box, _MultiDiscrete = _spaces.Discrete, _spaces.Box, _spaces.MultiDiscrete
+except Exception:  # noqa: BLE001
+    class _Discrete:
+        def __init__(self, n):
+            self.n, self.shape, self.dtype = int(n), (), np.dtype(np.int64)
+
+        def __repr__(self):
+            return f"Discrete({self.n})"
+
+    class _MultiDiscrete:
+        def __init__(self, nvec):
+            self.nvec = np.asarray(nvec, dtype=np.int64)
+            self.shape, self.dtype = self.nvec.shape, np.dtype(np.int64)
+
+        def __repr__(self):
+            return f"MultiDiscrete({self.nvec.tolist()})"
+
+    class _Box:
+        def __init__(self, low, high, shape, dtype=np.float32):
+            self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), np.dtype(dtype)
+
+        def __repr__(self):
+            return f"Box({self.low}, {self.high}, {self.shape}, {self.dtype})"
+
+
+def shard_envs(total_envs: int, rank: int, world_size: int):
+    """Env-index range owned by `rank`: [offset, offset+count) — contiguous, sizes differ by <= 1."""
+    base, rem = divmod(int(total_envs), int(world_size))
+    count = base + (1 if rank < rem else 0)
+    offset = rank * base + min(rank, rem)
+    return offset, count
+
+
+class LazyInfos(Mapping):
+    """History's last row (environments.py:253-264) as a dict of [N] device tensors, computed by
+    one `gte_info` launch on first access after each step/reset."""
+
+    KEYS = ["idx", "step", "position_index", "position", "real_position", "portfolio_valuation",
+            "data_close", "dataset_idx", "portfolio_distribution_asset", "portfolio_distribution_fiat",
+            "portfolio_distribution_borrowed_asset", "portfolio_distribution_borrowed_fiat",
+            "portfolio_distribution_interest_asset", "portfolio_distribution_interest_fiat",
+            "reward", "episode_metrics"]
+
+    def __init__(self, env):
+        self._env = env
+        self._version = -1
+
+    def _materialise(self):
+        if self._version != self._env._tick:
+            self._env._launch_info()
+            self._version = self._env._tick
+
+    def __getitem__(self, key):
+        e = self._env
+        if key == "reward":
+            return e._reward
+        if key == "episode_metrics":
+            return e.get_metrics()
+        if key not in self.KEYS:
+            raise KeyError(key)
+        self._materialise()
+        if key.startswith("portfolio_distribution_"):
+            names = ["asset", "fiat", "borrowed_asset", "borrowed_fiat", "interest_asset", "interest_fiat"]
+            return e._info_dist[names.index(key[len("portfolio_distribution_"):])]
+        return e._info_t[key]
+
+    def __iter__(self):
+        return iter(self.KEYS)
+
+    def __len__(self):
+        return len(self.KEYS)
+
+
+class TradingVectorEnv:
+    """N independent reference-semantics ``TradingEnv`` instances advanced in lockstep on one B200.
+
+    Reference parameters (same names, defaults and meaning as environments.py:79-93): ``df, positions,
+    dynamic_feature_functions, reward_function, windows, trading_fees, borrow_interest_rate,
+    portfolio_initial_value, initial_position, max_episode_duration, verbose, name, render_mode``.
+
+    Extra keyword-only parameters: ``num_envs``; ``device``; ``seed`` (keys the Philox stream that
+    replaces the reference's global ``np.random`` draws at reset, hazard H2); ``env_id_offset``
+    (global id of env 0 when sharded over GPUs); ``done_valuation_ratio`` (0.7 = this fork's stop
+    rule, environments.py:246; 0.0 = upstream "valuation <= 0"); ``reset_plan`` — int32
+    ``[N, E, 3]`` of (start row, position index, dataset index) consumed by successive resets
+    instead of the RNG (record-and-replay for parity tests); ``obs_variant`` in
+    {"auto","generic","vec","tma"}; ``output`` "torch" (CUDA tensors, default) or "numpy"
+    (pinned host buffers, host<->device copies inside `step`); ``autoreset`` (True = in-place).
+
+    ``reward_function`` must be :func:`basic_reward_function` and ``dynamic_feature_functions`` the two
+    defaults or ``[]``: arbitrary Python callbacks over a History cannot run inside the kernel and
+    there is deliberately no CPU fallback (NotImplementedError).
+
+    Returned tensors are persistent buffers overwritten by the next call: copy what you keep.
+    """
+
+    metadata = {"render_modes": ["logs"]}
+
+    def __init__(self, df, positions=[0, 1], dynamic_feature_functions=_DEFAULT_DYNAMIC,
+                 reward_function=basic_reward_function, windows=None, trading_fees=0,
+                 borrow_interest_rate=0, portfolio_initial_value=1000, initial_position="random",
+                 max_episode_duration="max", verbose=1, name="Stock", render_mode="logs", *,
+                 num_envs=1, device=None, seed=0, env_id_offset=0, done_valuation_ratio=0.7,
+                 reset_plan=None, obs_variant="auto", output="torch", autoreset=True,
+                 _multi_dataset=False, _episodes_between_dataset_switch=1):
+        self._lib = _cabi.load()                      # fails loudly when the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise RuntimeError("gym_trading_env_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+
+        # --- reference constructor checks (environments.py:94-110) ---
+        self.max_episode_duration = max_episode_duration
+        self.name, self.verbose = name, verbose
+        self.positions = list(positions)
+        self.windows = windows
+        self.trading_fees = trading_fees
+        self.borrow_interest_rate = borrow_interest_rate
+        self.portfolio_initial_value = float(portfolio_initial_value)
+        self.initial_position = initial_position
+        assert self.initial_position in self.positions or self.initial_position == "random", \
+            "The 'initial_position' parameter must be 'random' or a position mentionned in the 'position' (default is [0, 1]) parameter."
+        assert render_mode is None or render_mode in self.metadata["render_modes"]
+        self.render_mode = render_mode
+        if reward_function is not basic_reward_function and _fn_name(reward_function) != "basic_reward_function":
+            raise NotImplementedError(
+                "only basic_reward_function (log-return, environments.py:17-18) is fused into the CUDA step "
+                "kernel; arbitrary Python reward callbacks are not supported (no CPU fallback)")
+        self.reward_function = reward_function
+        dyn = list(dynamic_feature_functions)
+        if len(dyn) == 0:
+            self._n_dyn = 0
+        elif [_fn_name(f) for f in dyn] == ["dynamic_feature_last_position_taken", "dynamic_feature_real_position"]:
+            self._n_dyn = 2
+        else:
+            raise NotImplementedError(
+                "dynamic_feature_functions must be the two defaults (environments.py:20-24, :82) or []")
+        self.dynamic_feature_functions = dyn
+        if not (1 <= len(self.positions) <= _cabi.GTE_MAX_POSITIONS):
+            raise ValueError(f"between 1 and {_cabi.GTE_MAX_POSITIONS} positions are supported")
+        if windows is not None and (int(windows) != windows or windows < 1):
+            raise ValueError("windows must be None or a positive int")
+        if max_episode_duration != "max" and (not isinstance(max_episode_duration, (int, np.integer))
+                                              or max_episode_duration < 2):
+            raise ValueError("max_episode_duration must be 'max' or an int >= 2")
+        if output not in ("torch", "numpy"):
+            raise ValueError("output must be 'torch' or 'numpy'")
+        if obs_variant not in _cabi.OBS_VARIANTS:
+            raise ValueError(f"obs_variant must be one of {list(_cabi.OBS_VARIANTS)}")
+
+        self.num_envs = int(num_envs)
+        if self.num_envs < 1:
+            raise ValueError("num_envs must be >= 1")
+        self.seed = int(seed)
+        self.env_id_offset = int(env_id_offset)
+        self.done_valuation_ratio = float(done_valuation_ratio)
+        self.output = output
+        self.autoreset = bool(autoreset)
+        self._obs_variant = _cabi.OBS_VARIANTS[obs_variant]
+        self._multi = bool(_multi_dataset)
+        self._k_switch = int(_episodes_between_dataset_switch)
+        self._tick = 0
+        self._needs_first = True
+        self.log_metrics = []
+
+        series = df if isinstance(df, (list, tuple)) else [df]
+        series = [s if isinstance(s, SeriesArrays) else frame_to_arrays(s) for s in series]
+        self._set_series(series)
+        self._alloc_state(reset_plan)
+        self._build_structs()
+
+        F = self._n_static + self._n_dyn
+        shape = (F,) if windows is None else (int(windows), F)
+        self.single_observation_space = _Box(-np.inf, np.inf, shape=shape, dtype=np.float32)
+        self.observation_space = _Box(-np.inf, np.inf, shape=(self.num_envs,) + shape, dtype=np.float32)
+        self.single_action_space = _Discrete(len(self.positions))
+        self.action_space = _MultiDiscrete([len(self.positions)] * self.num_envs)
+
+    # ------------------------------------------------------------------ data staging (_set_df, :128-143)
+    def _set_series(self, series):
+        n_ds = len(series)
+        if not (1 <= n_ds <= _cabi.GTE_MAX_DATASETS):
+            raise ValueError(f"between 1 and {_cabi.GTE_MAX_DATASETS} datasets are supported")
+        ns = series[0].features.shape[1]
+        for s in series:
+            if s.features.shape[1] != ns:
+                raise ValueError("every dataset must have the same number of feature columns")
+        self._n_static = ns
+        if ns + self._n_dyn == 0:
+            raise ValueError("no feature column (name containing 'feature') and no dynamic feature")
+        self._series = series
+        self._feature_names = list(series[0].feature_names) + [f"dynamic_feature__{i}" for i in range(self._n_dyn)]
+        lengths = np.array([s.length for s in series], dtype=np.int32)
+        W0 = 0 if self.windows is None else int(self.windows) - 1
+        for T in lengths:
+            if self.max_episode_duration != "max":
+                if int(T) - int(self.max_episode_duration) - W0 <= W0:     # np.random.randint(low, high) needs low < high (:174)
+                    raise ValueError(f"dataset of {T} rows is too short for windows={self.windows}, "
+                                     f"max_episode_duration={self.max_episode_duration}")
+            elif int(T) < W0 + 2:
+                raise ValueError(f"dataset of {T} rows is too short for windows={self.windows}")
+        t_stride = int(lengths.max())
+        self._t_stride, self._lengths_np, self._n_ds = t_stride, lengths, n_ds
+        feats = np.zeros((n_ds, t_stride, ns), dtype=np.float32)
+        price = np.ones((n_ds, t_stride), dtype=np.float64)
+        for k, s in enumerate(series):
+            feats[k, :s.length] = s.features
+            price[k, :s.length] = s.price
+        dev = self.device
+        self._features = torch.from_numpy(feats).to(dev)
+        self._price = torch.from_numpy(price).to(dev)
+        self._lengths = torch.from_numpy(lengths).to(dev)
+        self._build_window_tables(feats)
+
+    def _build_window_tables(self, feats):
+        """16-byte-aligned copies of the reference's own `_obs_array` layout [t, F] (dynamic columns
+        zero, environments.py:135-141), one per alignment class a window start can fall in."""
+        self._window_tables = [None] * 4
+        self._window_ptrs = [0] * 4
+        self._window_ds_stride = 0
+        if self.windows is None:
+            return
+        F = self._n_static + self._n_dyn
+        row_bytes = 4 * F
+        if (int(self.windows) * row_bytes) % 16 != 0:
+            return
+        n_ds, t_stride, ns = feats.shape
+        rows = np.zeros((n_ds, t_stride, F), dtype=np.float32)
+        rows[:, :, :ns] = feats
+        ds_stride = ((t_stride * row_bytes + 15) // 16) * 16
+        raw = rows.reshape(n_ds, -1).view(np.uint8)
+        classes = sorted({((r * row_bytes) >> 2) & 3 for r in range(4)})
+        for c in classes:
+            shift = (16 - 4 * c) % 16
+            host = np.zeros(n_ds * ds_stride + 16, dtype=np.uint8)
+            for k in range(n_ds):
+                o = shift + k * ds_stride
+                host[o:o + raw.shape[1]] = raw[k]
+            t = torch.from_numpy(host).to(self.device)
+            assert t.data_ptr() % 16 == 0
+            self._window_tables[c] = t
+            self._window_ptrs[c] = t.data_ptr() + shift
+        self._window_ds_stride = ds_stride
+
+    # ------------------------------------------------------------------ device state
+    def _alloc_state(self, reset_plan):
+        N, dev = self.num_envs, self.device
+        f64 = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)   # noqa: E731
+        i32 = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)     # noqa: E731
+        W = 1 if self.windows is None else int(self.windows)
+        F = self._n_static + self._n_dyn
+        self._asset, self._fiat, self._interest_asset, self._interest_fiat = f64(N), f64(N), f64(N), f64(N)
+        self._pos_idx, self._step, self._ep_start, self._dataset_idx = i32(N), i32(N), i32(N), i32(N)
+        self._plan_cursor, self._ds_episodes = i32(N), i32(N)
+        self._ds_used = torch.zeros(N, dtype=torch.int64, device=dev)
+        self._dyn_ring = torch.zeros(N, W, 2, dtype=torch.float32, device=dev)
+        self._error_flag = i32(1)
+        self._reset_plan = None
+        if reset_plan is not None:
+            plan = torch.as_tensor(np.ascontiguousarray(reset_plan), dtype=torch.int32)
+            if plan.dim() != 3 or plan.shape[0] != N or plan.shape[2] != 3:
+                raise ValueError("reset_plan must be int32 [num_envs, E, 3]")
+            self._reset_plan = plan.to(dev).contiguous()
+        obs_shape = (N, F) if self.windows is None else (N, W, F)
+        self._obs = torch.zeros(obs_shape, dtype=torch.float32, device=dev)
+        self._reward, self._valuation, self._real_position = f64(N), f64(N), f64(N)
+        self._terminated = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._truncated = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._info_idx, self._info_step = i32(N), i32(N)
+        self._pre_reset_portfolio = f64(4, N)
+        self._metric_partials = f64(_cabi.GTE_MAX_PARTIAL_ROWS, _cabi.GTE_N_METRICS)
+        self._metrics_step, self._metrics_total = f64(_cabi.GTE_N_METRICS), f64(_cabi.GTE_N_METRICS)
+        self._block_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._actions_dev = torch.zeros(N, dtype=torch.int64, device=dev)
+        # lazily computed info columns
+        self._info_t = {"idx": i32(N), "step": i32(N), "position_index": i32(N), "dataset_idx": i32(N),
+                        "position": f64(N), "real_position": f64(N), "portfolio_valuation": f64(N),
+                        "data_close": f64(N)}
+        self._info_dist = f64(6, N)
+        self._host = None
+        self.infos = LazyInfos(self)
+
+    def _build_structs(self):
+        p = _cabi.GteParams()
+        p.n_envs, p.n_positions = self.num_envs, len(self.positions)
+        p.windows = 0 if self.windows is None else int(self.windows)
+        p.n_static, p.n_dyn = self._n_static, self._n_dyn
+        p.max_episode_duration = -1 if self.max_episode_duration == "max" else int(self.max_episode_duration)
+        p.n_datasets = self._n_ds
+        p.initial_position_idx = -1 if self.initial_position == "random" else self.positions.index(self.initial_position)
+        p.episodes_between_switch = self._k_switch
+        p.plan_episodes = 0 if self._reset_plan is None else int(self._reset_plan.shape[1])
+        p.multi_dataset = int(self._multi)
+        p.t_stride, p.env_id_offset, p.seed = self._t_stride, self.env_id_offset, self.seed & (2**64 - 1)
+        p.fee, p.rate = float(self.trading_fees), float(self.borrow_interest_rate)
+        p.v0, p.done_ratio = self.portfolio_initial_value, self.done_valuation_ratio
+        for i, x in enumerate(self.positions):
+            p.positions[i] = float(x)
+        d = _cabi.GteData()
+        d.features = self._features.data_ptr() if self._n_static else None
+        d.price, d.lengths = self._price.data_ptr(), self._lengths.data_ptr()
+        for c in range(4):
+            d.window_table[c] = self._window_ptrs[c] or None
+        d.window_table_ds_stride = self._window_ds_stride
+        s = _cabi.GteState()
+        s.asset, s.fiat = self._asset.data_ptr(), self._fiat.data_ptr()
+        s.interest_asset, s.interest_fiat = self._interest_asset.data_ptr(), self._interest_fiat.data_ptr()
+        s.pos_idx, s.step, s.ep_start = self._pos_idx.data_ptr(), self._step.data_ptr(), self._ep_start.data_ptr()
+        s.dataset_idx, s.dyn_ring = self._dataset_idx.data_ptr(), self._dyn_ring.data_ptr()
+        s.plan_cursor, s.ds_used, s.ds_episodes = self._plan_cursor.data_ptr(), self._ds_used.data_ptr(), self._ds_episodes.data_ptr()
+        s.reset_plan = None if self._reset_plan is None else self._reset_plan.data_ptr()
+        s.error_flag = self._error_flag.data_ptr()
+        o = _cabi.GteStepOut()
+        o.reward, o.terminated, o.truncated = self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr()
+        o.valuation, o.real_position = self._valuation.data_ptr(), self._real_position.data_ptr()
+        o.info_idx, o.info_step = self._info_idx.data_ptr(), self._info_step.data_ptr()
+        o.pre_reset_portfolio = self._pre_reset_portfolio.data_ptr()
+        o.metric_partials, o.metrics_step = self._metric_partials.data_ptr(), self._metrics_step.data_ptr()
+        o.metrics_total, o.block_counter = self._metrics_total.data_ptr(), self._block_counter.data_ptr()
+        i = _cabi.GteInfo()
+        t = self._info_t
+        i.idx, i.step, i.position_index, i.dataset_idx = (t["idx"].data_ptr(), t["step"].data_ptr(),
+                                                          t["position_index"].data_ptr(), t["dataset_idx"].data_ptr())
+        i.position, i.real_position = t["position"].data_ptr(), t["real_position"].data_ptr()
+        i.portfolio_valuation, i.data_close = t["portfolio_valuation"].data_ptr(), t["data_close"].data_ptr()
+        i.distribution = self._info_dist.data_ptr()
+        self._P, self._D, self._S, self._O, self._I = p, d, s, o, i
+        self._resolved_variant = self._lib.gte_obs_variant_for(C.byref(p), C.byref(d))
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _next_tick(self):
+        t = self._tick
+        self._tick += 1
+        return t
+
+    def _launch_reset(self, mask_ptr, first):
+        _cabi.check(self._lib.gte_reset(C.byref(self._P), C.byref(self._D), C.byref(self._S), mask_ptr,
+                                        self._next_tick(), int(first), self._stream()), "gte_reset")
+
+    def _launch_obs(self, variant=None):
+        v = self._obs_variant if variant is None else variant
+        _cabi.check(self._lib.gte_gather_obs(C.byref(self._P), C.byref(self._D), C.byref(self._S),
+                                             C.c_void_p(self._obs.data_ptr()), v, self._stream()), "gte_gather_obs")
+
+    def _launch_info(self):
+        _cabi.check(self._lib.gte_info(C.byref(self._P), C.byref(self._D), C.byref(self._S), C.byref(self._I),
+                                       self._stream()), "gte_info")
+
+    def _launch_step(self, actions_ptr, autoreset=None):
+        ar = self.autoreset if autoreset is None else autoreset
+        _cabi.check(self._lib.gte_step(C.byref(self._P), C.byref(self._D), C.byref(self._S), actions_ptr,
+                                       C.byref(self._O), self._next_tick(), int(ar), self._stream()), "gte_step")
+
+    def _host_buffers(self):
+        if self._host is None:
+            pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)   # noqa: E731
+            self._host = {"actions": pin(self._actions_dev), "obs": pin(self._obs), "reward": pin(self._reward),
+                          "terminated": pin(self._terminated), "truncated": pin(self._truncated)}
+        return self._host
+
+    # ------------------------------------------------------------------ gymnasium vector API
+    def reset(self, seed=None, options=None):
+        """Reset every env (environments.py:163-199); ``options={"mask": bool[N]}`` resets a subset.
+        ``seed`` re-keys the Philox stream (the reference ignores gymnasium's seed, hazard H2)."""
+        with torch.cuda.device(self.device):
+            if seed is not None:
+                self.seed = int(seed)
+                self._P.seed = self.seed & (2**64 - 1)
+            if self._needs_first:                                  # MultiDatasetTradingEnv.__init__ draw (:378)
+                self._launch_reset(None, first=True)
+                self._needs_first = False
+            mask_ptr, keep = None, None
+            if options is not None and options.get("mask") is not None:
+                keep = torch.as_tensor(options["mask"]).to(self.device).to(torch.uint8).contiguous()
+                if keep.shape != (self.num_envs,):
+                    raise ValueError("options['mask'] must have shape [num_envs]")
+                mask_ptr = C.c_void_p(keep.data_ptr())
+            self._launch_reset(mask_ptr, first=False)
+            self._launch_obs()
+            return self._emit_obs(), self.infos
+
+    def step(self, actions):
+        """One lockstep iteration (environments.py:233-272) with in-place auto-reset."""
+        with torch.cuda.device(self.device):
+            host_in = not (isinstance(actions, torch.Tensor) and actions.is_cuda)
+            if host_in:
+                a = np.asarray(actions)
+                if a.shape != (self.num_envs,):
+                    raise ValueError(f"actions must have shape ({self.num_envs},), got {a.shape}")
+                if a.size and (a.max() >= len(self.positions)):
+                    raise IndexError("list index out of range")      # what positions[position_index] raises (:234)
+                h = self._host_buffers()["actions"]
+                h.numpy()[...] = a
+                self._actions_dev.copy_(h, non_blocking=True)
+                act = self._actions_dev
+            else:
+                act = actions
+                if act.dtype != torch.int64 or not act.is_contiguous() or act.shape != (self.num_envs,) \
+                        or act.device != self.device:
+                    act = act.to(device=self.device, dtype=torch.int64).contiguous().view(self.num_envs)
+            self._launch_step(C.c_void_p(act.data_ptr()))
+            self._launch_obs()
+            if self.output == "numpy":
+                h = self._host_buffers()
+                for k, t in (("obs", self._obs), ("reward", self._reward), ("terminated", self._terminated),
+                             ("truncated", self._truncated)):
+                    h[k].copy_(t, non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                return (h["obs"].numpy(), h["reward"].numpy(), h["terminated"].numpy().view(np.bool_),
+                        h["truncated"].numpy().view(np.bool_), self.infos)
+            return self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), self.infos
+
+    def _emit_obs(self):
+        if self.output == "numpy":
+            h = self._host_buffers()
+            h["obs"].copy_(self._obs, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            return h["obs"].numpy()
+        return self._obs
+
+    def close(self):
+        self._host = None
+
+    # ------------------------------------------------------------------ metrics / errors / state
+    def get_metrics(self, total=True):
+        """Numeric episode metrics (environments.py:279-283) as a name -> 0-d tensor dict."""
+        t = self._metrics_total if total else self._metrics_step
+        return {n: t[i] for i, n in enumerate(_cabi.METRIC_NAMES)}
+
+    def allreduce_metrics(self, total=False, async_op=False):
+        """Sum the metric vector over all ranks (NCCL over NVLink when torch.distributed is initialised).
+        The only cross-GPU exchange on this path: envs never interact."""
+        import torch.distributed as dist
+        t = self._metrics_total if total else self._metrics_step
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=async_op)
+        return None
+
+    def check_errors(self):
+        """Synchronising check of the in-kernel error flags (device-resident actions are not validated on the host)."""
+        flag = int(self._error_flag.item())
+        if flag & 1:
+            raise IndexError("an action >= len(positions) was passed to step() (treated as hold)")
+        if flag & 2:
+            raise IndexError("an env was stepped past the end of its data without a reset")
+
+    def state_dict(self):
+        """Env state as tensors (checkpoint/resume: SURVEY.md §5)."""
+        names = ["asset", "fiat", "interest_asset", "interest_fiat", "pos_idx", "step", "ep_start", "dataset_idx",
+                 "dyn_ring", "plan_cursor", "ds_used", "ds_episodes", "metrics_total"]
+        d = {n: getattr(self, "_" + n).clone() for n in names}
+        d["tick"] = self._tick
+        return d
+
+    def load_state_dict(self, d):
+        for n, v in d.items():
+            if n == "tick":
+                self._tick = int(v)
+            else:
+                getattr(self, "_" + n).copy_(v)
+        self._needs_first = False
+
+    @property
+    def idx(self):
+        return self._ep_start + self._step
+
+    @property
+    def obs_variant(self):
+        v = self._obs_variant or self._resolved_variant
+        return {v_: k for k, v_ in _cabi.OBS_VARIANTS.items()}[v]
+
+
+class MultiDatasetTradingVectorEnv(TradingVectorEnv):
+    """Batched ``MultiDatasetTradingEnv`` (environments.py:309-400): every dataset matched by
+    ``dataset_dir`` is loaded, preprocessed and kept device-resident; each env carries its own dataset
+    index and least-used rotation state (`next_dataset`, :380-391) and switches every
+    ``episodes_between_dataset_switch`` episodes inside the in-kernel auto-reset.
+
+    ``datasets=[DataFrame | SeriesArrays, ...]`` may be given instead of ``dataset_dir``.
+    """
+
+    def __init__(self, dataset_dir=None, *args, preprocess=lambda df: df, episodes_between_dataset_switch=1,
+                 datasets=None, **kwargs):
+        self.dataset_dir = dataset_dir
+        self.preprocess = preprocess
+        self.episodes_between_dataset_switch = int(episodes_between_dataset_switch)
+        if self.episodes_between_dataset_switch < 1:
+            raise ValueError("episodes_between_dataset_switch must be >= 1")
+        if datasets is None:
+            import pandas as pd
+            self.dataset_pathes = sorted(_glob.glob(self.dataset_dir))
+            if len(self.dataset_pathes) == 0:
+                raise FileNotFoundError(f"No dataset found with the path : {self.dataset_dir}")   # :376
+            datasets = [self.preprocess(pd.read_pickle(p)) for p in self.dataset_pathes]         # :391
+            self.dataset_names = [Path(p).name for p in self.dataset_pathes]
+        else:
+            datasets = [d if isinstance(d, SeriesArrays) else self.preprocess(d) for d in datasets]
+            self.dataset_names = [f"dataset_{k}" for k in range(len(datasets))]
+        super().__init__(list(datasets), *args, _multi_dataset=True,
+                         _episodes_between_dataset_switch=self.episodes_between_dataset_switch, **kwargs)

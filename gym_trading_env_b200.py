@@ -1,0 +1,15 @@
+"""Import shim: ``import gym_trading_env_b200`` loads the package that lives in ``gym-trading-env_b200/``.
+
+The product directory keeps the hyphenated name the project layout prescribes, which Python cannot
+import directly; this module replaces itself in ``sys.modules`` with that package.
+"""
+import importlib.util as _ilu
+import os as _os
+import sys as _sys
+
+_dir = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "gym-trading-env_b200")
+_spec = _ilu.spec_from_file_location(__name__, _os.path.join(_dir, "__init__.py"),
+                                     submodule_search_locations=[_dir])
+_mod = _ilu.module_from_spec(_spec)
+_sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,181 @@
+/*
+ * gte_b200.h — C-ABI of libgte_b200.so: the B200 (sm_100a) batched drop-in for the per-step
+ * simulation hot path of ten2net/Gym-Trading-Env.
+ *
+ * The reference has no FFI layer: the path sits behind the gymnasium Env API
+ * (src/gym_trading_env/__init__.py:3-14 registers `TradingEnv` / `MultiDatasetTradingEnv`;
+ * src/gym_trading_env/environments.py:163 `reset`, :233 `step`).  The entry points below are what a
+ * binding for a batched version of exactly those calls needs; each one names the reference
+ * function(s) it replaces.  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *  - plain C, POD structs, no torch types.  Every pointer inside the structs is a DEVICE pointer
+ *    (e.g. torch.Tensor.data_ptr()) unless stated otherwise; the structs themselves live on the host.
+ *  - the library never allocates, frees or retains device memory: it borrows the pointers for the
+ *    duration of the call (the caller owns every buffer; outputs are overwritten in place).
+ *  - calls only enqueue work on `stream` (a cudaStream_t passed as void*; NULL = default stream)
+ *    and return without synchronising.
+ *  - return value: 0 = success, GTE_ERR_ARG (-1) = bad argument, GTE_ERR_CUDA (-2) = CUDA error;
+ *    gte_last_error() returns a thread-local message for the last failing call.
+ *  - all money math is IEEE fp64 round-to-nearest in the reference's exact operation order with
+ *    no FMA contraction (utils/portfolio.py:7-46), so portfolio state and valuation are bit-exact.
+ */
+#ifndef GTE_B200_H
+#define GTE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTE_VERSION 100            /* 0.1.0 */
+#define GTE_MAX_POSITIONS 64
+#define GTE_MAX_DATASETS 64        /* least-used rotation keeps a 64-bit "used this round" mask per env */
+#define GTE_N_METRICS 8
+#define GTE_STEP_THREADS 256       /* envs per CTA of the step kernel; metric_partials has ceil(N/256) rows */
+
+#define GTE_OK 0
+#define GTE_ERR_ARG (-1)
+#define GTE_ERR_CUDA (-2)
+
+/* metric slots: sums over the episodes that FINISHED in this call, except SUM_REWARD (all envs) */
+enum GteMetric {
+    GTE_M_EPISODES = 0,            /* number of finished episodes                                  */
+    GTE_M_TERMINATED = 1,          /* ... that hit the valuation stop   (environments.py:246)       */
+    GTE_M_TRUNCATED = 2,           /* ... that hit end-of-data / max duration (:248-251)            */
+    GTE_M_SUM_PORTFOLIO_RETURN = 3,/* sum of valuation_end/initial - 1  (:282 "Portfolio Return")   */
+    GTE_M_SUM_MARKET_RETURN = 4,   /* sum of close_end/close_start - 1  (:281 "Market Return")      */
+    GTE_M_SUM_EPISODE_LENGTH = 5,  /* sum of episode lengths in steps                              */
+    GTE_M_SUM_REWARD = 6,          /* sum of this iteration's rewards over all envs                */
+    GTE_M_RESERVED = 7
+};
+
+/* observation-gather kernel variants (gte_gather_obs `variant`) */
+enum GteObsVariant {
+    GTE_OBS_AUTO = 0,              /* fastest variant the shape allows                              */
+    GTE_OBS_GENERIC = 1,           /* scalar gather, any shape (windows=None, odd row sizes)        */
+    GTE_OBS_VEC = 2,               /* 128-bit LDG/STG from the 16B-aligned window tables            */
+    GTE_OBS_TMA = 3                /* cp.async.bulk global->smem->global, dynamic columns patched in smem */
+};
+
+/* Constructor parameters: TradingEnv.__init__ (environments.py:79-110) and
+ * MultiDatasetTradingEnv.__init__ (:365-378). */
+typedef struct GteParams {
+    int32_t n_envs;                  /* envs owned by THIS process / GPU                               */
+    int32_t n_positions;             /* len(positions)  (:98, action space Discrete(P) :112)           */
+    int32_t windows;                 /* `windows` (:101); 0 = None                                     */
+    int32_t n_static;                /* static "feature*" columns (:130)                               */
+    int32_t n_dyn;                   /* 0 or 2: the default dynamic features (:20-24, :82)             */
+    int32_t max_episode_duration;    /* (:94) -1 = 'max'                                               */
+    int32_t n_datasets;              /* 1 for TradingEnv                                               */
+    int32_t initial_position_idx;    /* index into positions, -1 = 'random' (:105, :167)               */
+    int32_t episodes_between_switch; /* `episodes_between_dataset_switch` (:370)                       */
+    int32_t plan_episodes;           /* E of reset_plan[N,E,3]; 0 = draw resets from Philox            */
+    int32_t multi_dataset;           /* 1 = MultiDatasetTradingEnv.reset semantics (:393-400)          */
+    int32_t reserved0;
+    int64_t t_stride;                /* rows allocated per dataset in `price` / `features`             */
+    int64_t env_id_offset;           /* global index of env 0 (multi-GPU sharding; keys the RNG)       */
+    uint64_t seed;                   /* Philox key                                                     */
+    double fee;                      /* `trading_fees` (:102)                                          */
+    double rate;                     /* `borrow_interest_rate` (:103)                                  */
+    double v0;                       /* `portfolio_initial_value` (:104)                               */
+    double done_ratio;               /* terminated = valuation/v0 <= done_ratio; 0.7 in this fork (:246) */
+    double positions[GTE_MAX_POSITIONS]; /* `positions` (:98)                                          */
+} GteParams;
+
+/* Device-resident market data: what TradingEnv._set_df builds (environments.py:128-143). */
+typedef struct GteData {
+    const float* features;           /* f32 [n_datasets, t_stride, n_static]  (_obs_array static part, :141) */
+    const double* price;             /* f64 [n_datasets, t_stride]            (_price_array, :143)            */
+    const int32_t* lengths;          /* i32 [n_datasets]  len(df) of each dataset                              */
+    /* 16-byte-aligned window tables for the vector/TMA gather: copy c holds rows in the reference's
+     * own [t, n_static+n_dyn] layout (dynamic columns zero) shifted so that a window starting at row
+     * r0 with (r0*row_bytes) % 16 == 4*c starts on a 16-byte boundary.  NULL where unused. */
+    const float* window_table[4];
+    int64_t window_table_ds_stride;  /* bytes between datasets inside one copy (multiple of 16)               */
+} GteData;
+
+/* Per-env state, structure of arrays (the reference's Portfolio fields, utils/portfolio.py:2-6,
+ * plus TradingEnv._position/_step/_idx as indices).  idx = ep_start + step. */
+typedef struct GteState {
+    double* asset;                   /* f64 [N]  signed: negative = borrowed asset (portfolio.py:53)    */
+    double* fiat;                    /* f64 [N]  signed: negative = borrowed fiat  (portfolio.py:54)    */
+    double* interest_asset;          /* f64 [N]                                                        */
+    double* interest_fiat;           /* f64 [N]                                                        */
+    int32_t* pos_idx;                /* i32 [N]  index of TradingEnv._position in positions            */
+    int32_t* step;                   /* i32 [N]  TradingEnv._step                                      */
+    int32_t* ep_start;               /* i32 [N]  _idx at reset (episode start row)                     */
+    int32_t* dataset_idx;            /* i32 [N]  which dataset the env is on                           */
+    float* dyn_ring;                 /* f32 [N, max(windows,1), 2]: (position, real_position) of row r
+                                        at slot r % W; rows before ep_start read as zero               */
+    int32_t* plan_cursor;            /* i32 [N]  next episode slot of reset_plan                       */
+    uint64_t* ds_used;               /* u64 [N]  datasets used in the current rotation round (:383)    */
+    int32_t* ds_episodes;            /* i32 [N]  _episodes_on_this_dataset (:381,394)                  */
+    const int32_t* reset_plan;       /* i32 [N, E, 3] (start row, position idx, dataset idx) or NULL   */
+    int32_t* error_flag;             /* i32 [1]  bit 0: action out of range seen (treated as hold)     */
+} GteState;
+
+/* Outputs of one lockstep iteration.  reward / flags / valuation / real_position / info_* are the
+ * values of the step just taken (terminal values where an episode ended); obs and GteState are
+ * post-reset where the in-place auto-reset fired.  NULL pointers are skipped. */
+typedef struct GteStepOut {
+    double* reward;                  /* f64 [N]  log(valuation/previous valuation), 0 when terminated (:17-18,:263-267) */
+    uint8_t* terminated;             /* u8  [N]                                                         */
+    uint8_t* truncated;              /* u8  [N]                                                         */
+    double* valuation;               /* f64 [N]  info["portfolio_valuation"] (:241)               or NULL */
+    double* real_position;           /* f64 [N]  info["real_position"] (:259)                     or NULL */
+    int32_t* info_idx;               /* i32 [N]  info["idx"]                                      or NULL */
+    int32_t* info_step;              /* i32 [N]  info["step"]                                     or NULL */
+    double* pre_reset_portfolio;     /* f64 [4, N] asset, fiat, interest_asset, interest_fiat before the auto-reset, or NULL */
+    double* metric_partials;         /* f64 [ceil(N/GTE_STEP_THREADS), GTE_N_METRICS] scratch          */
+    double* metrics_step;            /* f64 [GTE_N_METRICS] this iteration's metrics                    */
+    double* metrics_total;           /* f64 [GTE_N_METRICS] running totals (+= metrics_step)    or NULL */
+    uint32_t* block_counter;         /* u32 [1]  zero-initialised scratch (self-resetting)              */
+} GteStepOut;
+
+/* Lazily computed info columns (History's last row, environments.py:253-264 / utils/history.py). */
+typedef struct GteInfo {
+    int32_t* idx; int32_t* step; int32_t* position_index; int32_t* dataset_idx;   /* i32 [N] or NULL */
+    double* position; double* real_position; double* portfolio_valuation;         /* f64 [N] or NULL */
+    double* data_close;                                                            /* f64 [N] or NULL */
+    double* distribution;            /* f64 [6, N]: asset, fiat, borrowed_asset, borrowed_fiat,
+                                        interest_asset, interest_fiat (portfolio.py:49-57) or NULL  */
+} GteInfo;
+
+int gte_version(void);
+const char* gte_last_error(void);
+
+/* Replaces TradingEnv.reset (environments.py:163-199) [+ MultiDatasetTradingEnv.reset :393-400 and,
+ * with first != 0, the dataset draw of MultiDatasetTradingEnv.__init__ :377-378] for every env whose
+ * mask byte is non-zero (mask == NULL: all envs).  Episode start / initial position / dataset come
+ * from state->reset_plan when params->plan_episodes > 0, else from Philox4x32-10 keyed by
+ * (seed, tick, global env id). */
+int gte_reset(const GteParams* params, const GteData* data, const GteState* state,
+              const uint8_t* mask, uint64_t tick, int first, void* stream);
+
+/* Replaces TradingEnv.step (environments.py:233-272) for N envs: _take_action/_trade (:204-215) ->
+ * Portfolio.trade_to_position (portfolio.py:18-43) -> index advance -> update_interest (:44-46) ->
+ * valorisation (:7-13) -> done/truncated (:244-251) -> basic_reward_function (:17-18) -> episode
+ * metrics (:279-283) -> in-place auto-reset when autoreset != 0.  actions: i64 [N] indices into
+ * positions; a negative action = hold (the reference's position_index=None, :234). */
+int gte_step(const GteParams* params, const GteData* data, const GteState* state,
+             const int64_t* actions, const GteStepOut* out, uint64_t tick, int autoreset, void* stream);
+
+/* Replaces TradingEnv._get_obs (environments.py:152-160): obs f32 [N, F] (windows=None) or
+ * [N, W, F], F = n_static + n_dyn; static columns gathered from the device-resident tables,
+ * dynamic columns from dyn_ring. */
+int gte_gather_obs(const GteParams* params, const GteData* data, const GteState* state,
+                   float* obs, int variant, void* stream);
+
+/* History's last row as tensors (environments.py:253-264, portfolio.py:49-57), from current state. */
+int gte_info(const GteParams* params, const GteData* data, const GteState* state,
+             const GteInfo* info, void* stream);
+
+/* Which gather variant GTE_OBS_AUTO resolves to for this shape (host-only helper). */
+int gte_obs_variant_for(const GteParams* params, const GteData* data);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTE_B200_H */

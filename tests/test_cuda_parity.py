@@ -1,0 +1,201 @@
+"""GPU: the CUDA path, called through the C-ABI (ctypes -> libgte_b200.so), against
+(a) the golden vectors recorded from the unmodified reference and (b) the CPU oracle on larger
+seeded inputs, with the same step-by-step comparison the oracle itself passes on the CPU.
+
+Bars (BASELINE.json north_star): position/step indices, flags and observations bit-exact;
+valuation and reward within 1e-12 relative (helpers.RTOL) — and, stronger, every fp64 portfolio
+quantity is also required to be BIT-exact (only `log` may differ, by <= 1 ulp)."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+DEVICE_GOLDEN = [n for n in H.GOLDEN_NAMES if n != "raw_stale_dynamic_rows"]   # raw H3 leak: oracle-only
+
+
+def _variants(g):
+    p = g["params"]
+    F = g["features"].shape[2] + (2 if p.get("dynamic_features", True) else 0)
+    if p["windows"] is not None and (p["windows"] * F * 4) % 16 == 0:
+        return ["generic", "vec", "tma"]
+    return ["generic"]
+
+
+@pytest.mark.parametrize("name", DEVICE_GOLDEN)
+def test_cuda_matches_reference_golden(name):
+    g = H.load_golden(name)
+    for variant in _variants(g):
+        env = H.make_device_env(g, obs_variant=variant)
+        stats = H.replay_golden(H.DeviceAdapter(env), g, exact_money=True)
+        env.check_errors()
+        assert stats["steps"] == g["actions"].size
+        assert stats["reward_bit_mismatch"] <= 0.25 * stats["steps"], variant
+
+
+def _compare_with_oracle(dev, orc_env, K, n_pos, seed, hold=0.05):
+    import torch
+    rng = np.random.default_rng(seed)
+    obs_d, _ = dev.reset()
+    obs_o = orc_env.reset()
+    H.assert_bits(obs_d.cpu().numpy(), obs_o, "reset obs")
+    c = lambda t: t.cpu().numpy()   # noqa: E731
+    total_eps = 0
+    for k in range(K):
+        a = rng.integers(0, n_pos, size=dev.num_envs)
+        a[rng.random(dev.num_envs) < hold] = -1
+        dev.step(torch.as_tensor(a, device=dev.device))
+        orc_env.step(a)
+        w = f"step {k}"
+        H.assert_bits(c(dev._obs), orc_env.obs, f"{w} obs")
+        H.assert_bits(c(dev._terminated), orc_env.terminated, f"{w} terminated")
+        H.assert_bits(c(dev._truncated), orc_env.truncated, f"{w} truncated")
+        H.assert_bits(c(dev._info_idx), orc_env.info_idx, f"{w} idx")
+        H.assert_bits(c(dev._info_step), orc_env.info_step, f"{w} step")
+        H.assert_bits(c(dev._valuation), orc_env.valuation, f"{w} valuation")
+        H.assert_bits(c(dev._real_position), orc_env.real_position, f"{w} real_position")
+        H.assert_close64(c(dev._reward), orc_env.reward, f"{w} reward")
+        for nm in ("asset", "fiat", "interest_asset", "interest_fiat"):
+            H.assert_bits(c(getattr(dev, "_" + nm)), getattr(orc_env, nm), f"{w} {nm}")
+        H.assert_bits(c(dev._pos_idx), orc_env.pos_idx, f"{w} pos_idx")
+        H.assert_bits(c(dev._ep_start), orc_env.ep_start, f"{w} ep_start")
+        H.assert_bits(c(dev._step), orc_env.step_, f"{w} step state")
+        H.assert_bits(c(dev._dataset_idx), orc_env.dataset_idx, f"{w} dataset")
+        m = c(dev._metrics_step)
+        assert m[0] == orc_env.metrics[0] and m[1] == orc_env.metrics[1] and m[2] == orc_env.metrics[2]
+        assert m[5] == orc_env.metrics[5]
+        np.testing.assert_allclose(m[3:5], orc_env.metrics[3:5], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(m[6], orc_env.metrics[6], rtol=1e-9, atol=1e-11)
+        total_eps += int(m[0])
+    np.testing.assert_allclose(c(dev._metrics_total)[0], total_eps)
+    dev.check_errors()
+    return total_eps
+
+
+@pytest.mark.parametrize("variant", ["tma", "vec", "generic"])
+def test_cuda_matches_oracle_philox_resets_c3_shape(variant):
+    """C3/C5 shape at reduced N: W=64, 8 static + 2 dynamic features, leveraged positions, D=100,
+    auto-reset with in-kernel Philox starts (no plan) — the oracle draws from the same stream."""
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    df = gte.make_gbm_ohlcv(6000, seed=5)
+    arr = gte.frame_to_arrays(df)
+    pos = [-3, -2, -1, 0, 1, 2, 3]
+    kw = dict(positions=pos, windows=64, trading_fees=1e-4, borrow_interest_rate=3e-6,
+              portfolio_initial_value=1000, max_episode_duration=100)
+    N = 3000     # not a multiple of the CTA size: exercises the ragged tail
+    dev = gte.TradingVectorEnv(arr, num_envs=N, seed=77, env_id_offset=12345, obs_variant=variant, verbose=0, **kw)
+    o = orc.OracleVecEnv(arr.features, arr.price, num_envs=N, seed=77, env_id_offset=12345, **kw)
+    eps = _compare_with_oracle(dev, o, K=230, n_pos=len(pos), seed=1)
+    assert eps >= 2 * N
+
+
+def test_cuda_matches_oracle_windows_none_c2_shape():
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    arr = gte.frame_to_arrays(gte.make_gbm_ohlcv(5000, seed=6))
+    pos = [-1, 0, 0.5, 1]
+    kw = dict(positions=pos, windows=None, trading_fees=1e-4, borrow_interest_rate=3e-6,
+              portfolio_initial_value=1000, max_episode_duration="max")
+    dev = gte.TradingVectorEnv(arr, num_envs=4096, seed=3, verbose=0, **kw)
+    o = orc.OracleVecEnv(arr.features, arr.price, num_envs=4096, seed=3, **kw)
+    _compare_with_oracle(dev, o, K=120, n_pos=len(pos), seed=2)
+
+
+def test_cuda_matches_oracle_multi_dataset_rotation():
+    """C4 shape at reduced size: ragged datasets, per-env dataset index, in-kernel least-used rotation."""
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    lens = [900, 1200, 1000, 1500, 800]
+    series = [gte.frame_to_arrays(gte.make_gbm_ohlcv(T, seed=40 + k)) for k, T in enumerate(lens)]
+    tmax = max(lens)
+    feats = np.zeros((len(lens), tmax, 8), np.float32)
+    price = np.ones((len(lens), tmax))
+    for k, s in enumerate(series):
+        feats[k, :s.length], price[k, :s.length] = s.features, s.price
+    pos = [-1, 0, 1, 2]
+    for k_switch in (1, 2):
+        kw = dict(positions=pos, windows=16, trading_fees=1e-4, borrow_interest_rate=3e-6,
+                  portfolio_initial_value=1000, max_episode_duration=25)
+        dev = gte.MultiDatasetTradingVectorEnv(datasets=series, episodes_between_dataset_switch=k_switch,
+                                               num_envs=1500, seed=9, verbose=0, **kw)
+        o = orc.OracleVecEnv(feats, price, np.array(lens), num_envs=1500, seed=9, multi_dataset=True,
+                             episodes_between_dataset_switch=k_switch, **kw)
+        _compare_with_oracle(dev, o, K=150, n_pos=len(pos), seed=3)
+        used = np.bincount(dev._dataset_idx.cpu().numpy(), minlength=len(lens))
+        assert (used > 0).all()
+
+
+def test_termination_rule_and_threshold_parameter():
+    """H1: done when valuation/initial <= 0.7 (this fork, environments.py:246); 0.0 = upstream rule."""
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    arr = gte.frame_to_arrays(gte.make_gbm_ohlcv(1500, seed=3, sigma=0.03))
+    pos = [-5, 0, 5]
+    kw = dict(positions=pos, windows=None, trading_fees=1e-3, borrow_interest_rate=1e-4,
+              portfolio_initial_value=1000, max_episode_duration="max")
+    for ratio in (0.7, 0.0):
+        dev = gte.TradingVectorEnv(arr, num_envs=512, seed=1, done_valuation_ratio=ratio, verbose=0, **kw)
+        o = orc.OracleVecEnv(arr.features, arr.price, num_envs=512, seed=1, done_ratio=ratio, **kw)
+        _compare_with_oracle(dev, o, K=200, n_pos=3, seed=4, hold=0.0)
+        term = float(dev.get_metrics()["terminated"].item())
+        assert (term > 50) if ratio == 0.7 else True
+
+
+def test_cabi_argument_errors_and_host_validation():
+    import gym_trading_env_b200 as gte
+    arr = gte.frame_to_arrays(gte.make_gbm_ohlcv(500, seed=0))
+    env = gte.TradingVectorEnv(arr, positions=[0, 1], windows=8, num_envs=16, verbose=0)
+    env.reset()
+    with pytest.raises(IndexError):
+        env.step(np.full(16, 2))                       # host actions are validated before launch
+    with pytest.raises(ValueError):
+        env.step(np.zeros(3, dtype=np.int64))
+    import torch
+    env.step(torch.full((16,), 5, dtype=torch.int64, device=env.device))   # device actions: flagged in-kernel
+    with pytest.raises(IndexError):
+        env.check_errors()
+    with pytest.raises(NotImplementedError):
+        gte.TradingVectorEnv(arr, reward_function=lambda h: 0.0, num_envs=2)
+    with pytest.raises(AssertionError):
+        gte.TradingVectorEnv(arr, positions=[0, 1], initial_position=0.5, num_envs=2)
+    with pytest.raises(ValueError):
+        gte.TradingVectorEnv(arr, windows=400, max_episode_duration=200, num_envs=2)
+    # the C entry points reject inconsistent structs instead of launching
+    import ctypes as C
+    from gym_trading_env_b200 import _cabi
+    bad = _cabi.GteParams()
+    C.memmove(C.byref(bad), C.byref(env._P), C.sizeof(bad))
+    bad.n_positions = 1000
+    rc = env._lib.gte_reset(C.byref(bad), C.byref(env._D), C.byref(env._S), None, 0, 0, None)
+    assert rc == -1 and b"n_positions" in env._lib.gte_last_error()
+
+
+def test_numpy_output_mode_and_infos():
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    arr = gte.frame_to_arrays(gte.make_gbm_ohlcv(2000, seed=2))
+    kw = dict(positions=[-1, 0, 1], windows=16, trading_fees=1e-4, borrow_interest_rate=3e-6,
+              portfolio_initial_value=1000, max_episode_duration=50)
+    env = gte.TradingVectorEnv(arr, num_envs=256, seed=5, output="numpy", verbose=0, **kw)
+    o = orc.OracleVecEnv(arr.features, arr.price, num_envs=256, seed=5, **kw)
+    obs, infos = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.dtype == np.float32 and obs.shape == (256, 16, 10)
+    H.assert_bits(obs, o.reset(), "reset obs (numpy)")
+    assert np.array_equal(infos["portfolio_valuation"].cpu().numpy(), np.full(256, 1000.0))
+    rng = np.random.default_rng(0)
+    for _ in range(60):
+        a = rng.integers(0, 3, size=256)
+        obs, rew, term, trunc, infos = env.step(a)
+        o.step(a)
+        H.assert_bits(obs, o.obs, "obs (numpy)")
+        assert term.dtype == np.bool_ and rew.dtype == np.float64
+        H.assert_close64(rew, o.reward, "reward")
+    # infos are History's last row of the CURRENT (post-reset) state
+    H.assert_bits(infos["idx"].cpu().numpy(), o.idx, "infos idx")
+    H.assert_bits(infos["position_index"].cpu().numpy(), o.pos_idx, "infos position_index")
+    dist = np.stack([infos[f"portfolio_distribution_{k}"].cpu().numpy() for k in
+                     ("asset", "fiat", "borrowed_asset", "borrowed_fiat", "interest_asset", "interest_fiat")])
+    assert np.array_equal(dist[0] - dist[2], o.asset) and np.array_equal(dist[1] - dist[3], o.fiat)
+    assert np.array_equal(dist[4], o.interest_asset) and np.array_equal(dist[5], o.interest_fiat)
