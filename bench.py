@@ -1,0 +1,345 @@
+"""bench.py — env-steps/s of the batched trading-env hot path on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c5|c3|c2|c4]
+
+Metric (BASELINE.json): env-steps/sec, whole box, device-timed; % of HBM roofline.
+A "step" is ONE lockstep iteration of the hot path over this rank's envs: the fused step kernel
+(trade / interest / valuation / reward / flags / in-place auto-reset) + the observation-window gather
+(+ the NCCL allreduce of the episode-metric vector when N > 1).  Default workload = BASELINE config 5
+sharded: 2^21 envs per GPU (2^24 over 8), positions -3..3, windows=64, 8 static + 2 dynamic
+features, max_episode_duration=720, fees 0.01 %, borrow 0.0003 %/step, synthetic GBM T=100 000.
+
+Prints ONE JSON line (rank 0).  `value` = device-timed throughput with everything resident in HBM;
+`e2e` = the same metric through the public VectorEnv API with HOST numpy buffers (pinned H2D of the
+actions, D2H of obs/reward/flags inside the timed region); `roofline` = the window-gather kernel
+(the dominant kernel) timed live with CUDA events; `cpu_baseline` = the scalar C oracle port
+(oracle/gte_oracle.c) on this box's host cores on a bounded sample of the same workload.
+`--impl reference` times that CPU port alone (all host threads) and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "env-steps/sec (whole box, device-timed)"
+UNIT = "env-steps/s"
+
+WORKLOADS = {
+    # name: (envs per GPU, positions, windows, max_episode_duration, n_datasets, rows per dataset)
+    "c5": dict(envs=1 << 21, positions=[-3, -2, -1, 0, 1, 2, 3], windows=64, duration=720, n_datasets=1, rows=100_000,
+               label="C5 shard: 2^21 envs/GPU (2^24 over 8), positions -3..3, windows=64, 8+2 features, D=720, GBM T=100k"),
+    "c3": dict(envs=65_536, positions=[-1, 0, 0.5, 1], windows=64, duration=720, n_datasets=1, rows=100_000,
+               label="C3: 65,536 envs, windows=64, 8+2 features, D=720, GBM T=100k"),
+    "c2": dict(envs=4096, positions=[-1, 0, 0.5, 1], windows=None, duration="max", n_datasets=1, rows=100_000,
+               label="C2: 4096 lockstep envs, windows=None, GBM T=100k"),
+    "c4": dict(envs=1 << 20, positions=[-1, 0, 0.5, 1], windows=64, duration=720, n_datasets=32, rows=1_000_000,
+               label="C4: MultiDataset 32 x 1M rows, per-env dataset index, 2^20 envs/GPU, windows=64, D=720"),
+}
+FEE, RATE, V0 = 0.01 / 100, 0.0003 / 100, 1000.0
+
+
+def algorithmic_bytes(windows, n_static=8, n_dyn=2):
+    """compulsory HBM bytes per env-step (dataset rows treated as cache-resident)."""
+    W = 1 if windows is None else windows
+    step = 2 * 44 + 8 + 10                                   # state r+w, action, reward+flags
+    obs = W * (n_static + n_dyn) * 4 + (W - 1) * n_dyn * 4   # window written + prior dynamic rows re-read
+    return step, obs
+
+
+def make_series(wl, gte):
+    if wl["n_datasets"] == 1:
+        return [gte.frame_to_arrays(gte.make_gbm_ohlcv(wl["rows"], seed=0))]
+    out = []
+    for k in range(wl["n_datasets"]):
+        f, p = gte.make_gbm_arrays(wl["rows"], seed=k)
+        out.append(gte.SeriesArrays(f, p, [f"feature_{j}" for j in range(f.shape[1])], {}, None))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:  # noqa: BLE001
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_rate(wl, n_sample, seconds, threads, seed=0):
+    """Time the scalar C oracle port on host cores: lockstep iterations over n_sample envs."""
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    series = make_series(dict(wl, n_datasets=1, rows=min(wl["rows"], 100_000)), gte)[0]
+    env = orc.OracleVecEnv(series.features, series.price, num_envs=n_sample, positions=wl["positions"],
+                           windows=wl["windows"], trading_fees=FEE, borrow_interest_rate=RATE,
+                           portfolio_initial_value=V0, max_episode_duration=wl["duration"], seed=seed,
+                           threads=threads)
+    env.reset()
+    rng = np.random.default_rng(1234)
+    acts = rng.integers(0, len(wl["positions"]), size=(16, n_sample))
+    env.rollout(acts, 20)
+    t0 = time.perf_counter()
+    env.rollout(acts, 20)
+    per_iter = max((time.perf_counter() - t0) / 20, 1e-7)
+    iters = int(max(20, min(200000, seconds / per_iter)))
+    t0 = time.perf_counter()
+    env.rollout(acts, iters)
+    dt = time.perf_counter() - t0
+    return n_sample * iters / dt, iters, dt
+
+
+def run_reference_arm(args, wl, rank):
+    """`--impl reference`: the reference algorithm's CPU port (oracle/gte_oracle.c, scalar C, faithful
+    per-env private dynamic-feature columns) on all host cores.  Rank 0 only."""
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    n_sample = 2048
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    series = make_series(dict(wl, n_datasets=1, rows=min(wl["rows"], 100_000)), gte)[0]
+    env = orc.OracleVecEnv(series.features, series.price, num_envs=n_sample, positions=wl["positions"],
+                           windows=wl["windows"], trading_fees=FEE, borrow_interest_rate=RATE,
+                           portfolio_initial_value=V0, max_episode_duration=wl["duration"], seed=0, threads=cores)
+    env.reset()
+    rng = np.random.default_rng(1234)
+    acts = rng.integers(0, len(wl["positions"]), size=(16, n_sample))
+    inner = 200                                   # lockstep iterations per bench "step" (bounded sample)
+    for _ in range(args.warmup):
+        env.rollout(acts, inner)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        env.rollout(acts, inner)
+    dt = time.perf_counter() - t0
+    value = n_sample * inner * args.steps / dt
+    sample = f"{n_sample} envs x {inner} lockstep iterations per step, {cores} host threads, scalar C port of the reference"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["label"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c5", choices=list(WORKLOADS))
+    ap.add_argument("--envs-per-gpu", type=int, default=None)
+    ap.add_argument("--obs-variant", default="auto")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.envs_per_gpu:
+        wl["envs"] = args.envs_per_gpu
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, wl, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import gym_trading_env_b200 as gte
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N = wl["envs"]
+    series = make_series(wl, gte)
+    kw = dict(positions=wl["positions"], windows=wl["windows"], trading_fees=FEE, borrow_interest_rate=RATE,
+              portfolio_initial_value=V0, max_episode_duration=wl["duration"], num_envs=N, device=dev,
+              seed=2024, env_id_offset=rank * N, obs_variant=args.obs_variant, verbose=0)
+    if wl["n_datasets"] > 1:
+        env = gte.MultiDatasetTradingVectorEnv(datasets=series, **kw)
+    else:
+        env = gte.TradingVectorEnv(series[0], **kw)
+    n_sets = 8
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    actions = torch.randint(0, len(wl["positions"]), (n_sets, N), generator=gen, device=dev, dtype=torch.int64)
+    env.reset()
+
+    side = torch.cuda.Stream(device=dev)
+    red_buf = torch.zeros(8, dtype=torch.float64, device=dev)
+    red_total = torch.zeros(8, dtype=torch.float64, device=dev)
+    side_done = [None]
+
+    def lockstep(k):
+        if side_done[0] is not None:
+            torch.cuda.current_stream().wait_event(side_done[0])     # metrics_step is about to be overwritten
+        env.step(actions[k % n_sets])
+        if world > 1:                                                # per-iteration NCCL allreduce, off the critical path
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                red_buf.copy_(env._metrics_step)
+                dist.all_reduce(red_buf)
+                red_total.add_(red_buf)
+                done = torch.cuda.Event()
+                done.record()
+            side_done[0] = done
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(max(args.warmup, 3)):
+        lockstep(k)
+    barrier()
+    env._obs_events = []                                             # live per-launch timing of the gather kernel
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        lockstep(k)
+    if world > 1:
+        torch.cuda.current_stream().wait_stream(side)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    obs_ms = [a.elapsed_time(b) for a, b in env._obs_events]
+    env._obs_events = None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    env.check_errors()
+    value = world * N * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (window gather), measured live over the timed region ----
+    a_step, a_obs = algorithmic_bytes(wl["windows"])
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    obs_ms_avg = sum(obs_ms) / max(len(obs_ms), 1)
+    achieved = (a_obs * N) / (obs_ms_avg * 1e-3) / 1e9 if obs_ms else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(f"{args.workload}:{env.obs_variant}:{N}")
+    roofline = {"bound": "hbm", "kernel": f"obs_{env.obs_variant}_kernel", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_env": a_obs, "kernel_ms": obs_ms_avg,
+                "whole_step": {"algorithmic_bytes_per_env_step": a_step + a_obs,
+                               "achieved": (a_step + a_obs) * N * args.steps / (ms * 1e-3) / 1e9,
+                               "frac": (a_step + a_obs) * N * args.steps / (ms * 1e-3) / 1e9 / peak,
+                               "frac_of_nominal_8TBs": (a_step + a_obs) * N * args.steps / (ms * 1e-3) / 1e9 / 8000.0}}
+
+    # ---- e2e: public API, HOST numpy actions in, HOST numpy obs/reward/flags out ----
+    e2e = None
+    if not args.no_e2e:
+        env_h = env
+        env_h.output = "numpy"
+        acts_h = actions.cpu().numpy()
+        env_h.step(acts_h[0])                                        # allocates + warms the pinned buffers
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.e2e_steps):
+            env_h.step(acts_h[k % n_sets])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        obs_bytes = env._obs.numel() * 4
+        e2e = {"value": world * N * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": N * 8,
+               "d2h_bytes_per_step": obs_bytes + N * 10, "steps": args.e2e_steps,
+               "note": "VectorEnv.step(numpy actions) -> numpy obs/reward/terminated/truncated via pinned buffers"}
+        env_h.output = "torch"
+        env_h.close()
+
+    # ---- CPU baseline (rank 0, N=1 only): scalar C port of the reference on the host cores ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = len(os.sched_getaffinity(0))
+        n_sample = 2048
+        v_all, iters, dt = cpu_port_rate(wl, n_sample, args.cpu_seconds, cores)
+        v_one, _, _ = cpu_port_rate(wl, 256, 3.0, 1)
+        cpu = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_sample} envs x {iters} lockstep iterations ({dt:.1f} s), same dataset/config, "
+                         f"oracle/gte_oracle.c on {cores} threads", "single_core_value": v_one}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["label"], "envs_per_gpu": N, "obs_variant": env.obs_variant,
+                       "l2_policy": "inputs larger than L2 (obs %.0f MB + state/ring %.0f MB per step vs 126 MB L2)"
+                                    % (env._obs.numel() * 4 / 1e6, (N * 44 + env._dyn_ring.numel() * 4) / 1e6),
+                       "parallelism": f"env-sharded x{world}, dataset replicated, NCCL allreduce of 8 fp64 metrics per iteration"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

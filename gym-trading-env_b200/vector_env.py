@@ -215,6 +215,7 @@ class TradingVectorEnv:
         self._k_switch = int(_episodes_between_dataset_switch)
         self._tick = 0
         self._needs_first = True
+        self._obs_events = None
         self.log_metrics = []
 
         series = df if isinstance(df, (list, tuple)) else [df]
@@ -396,8 +397,16 @@ class TradingVectorEnv:
 
     def _launch_obs(self, variant=None):
         v = self._obs_variant if variant is None else variant
+        ev = self._obs_events                       # bench.py: live CUDA-event timing of the gather kernel
+        if ev is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
         _cabi.check(self._lib.gte_gather_obs(C.byref(self._P), C.byref(self._D), C.byref(self._S),
                                              C.c_void_p(self._obs.data_ptr()), v, self._stream()), "gte_gather_obs")
+        if ev is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            ev.append((e0, e1))
 
     def _launch_info(self):
         _cabi.check(self._lib.gte_info(C.byref(self._P), C.byref(self._D), C.byref(self._S), C.byref(self._I),

@@ -181,9 +181,9 @@ void orc_get_obs(const OrcEnv* e, int i, float* obs) {
     for (int w = 0; w < W; ++w) {
         int row = idx + 1 - W + w;
         const float* st = e->features + ((int64_t)ds * e->t_stride + row) * e->n_static;
-        for (int c = 0; c < e->n_static; ++c) obs[w * F + c] = st[c];
+        memcpy(obs + w * F, st, sizeof(float) * (size_t)e->n_static);
         const float* d = e->dyn_cols + ((int64_t)i * e->t_stride + row) * e->n_dyn;
-        for (int c = 0; c < e->n_dyn; ++c) obs[w * F + e->n_static + c] = d[c];
+        memcpy(obs + w * F + e->n_static, d, sizeof(float) * (size_t)e->n_dyn);
     }
 }
 
@@ -348,6 +348,16 @@ void orc_step(OrcEnv* e, const int64_t* actions, uint64_t tick,
               double* final_state, float* final_obs, double* metrics) {
     orc_step_range(e, 0, e->n_envs, actions, tick, obs, reward, terminated, truncated, valuation,
                    real_position, info_idx, info_step, final_state, final_obs, metrics);
+}
+
+/* K lockstep iterations over the env slice [lo, hi) with actions[(k % n_sets), :] — envs are
+ * independent, so host threads can each roll their own slice forward without meeting every
+ * iteration (used only by bench.py's CPU-baseline legs). */
+void orc_rollout_range(OrcEnv* e, int lo, int hi, const int64_t* actions, int n_sets, int iters, uint64_t tick0,
+                       float* obs, double* reward, uint8_t* terminated, uint8_t* truncated, double* metrics) {
+    for (int k = 0; k < iters; ++k)
+        orc_step_range(e, lo, hi, actions + (int64_t)(k % n_sets) * e->n_envs, tick0 + (uint64_t)k, obs, reward,
+                       terminated, truncated, 0, 0, 0, 0, 0, 0, metrics);
 }
 
 int orc_struct_size(void) { return (int)sizeof(OrcEnv); }

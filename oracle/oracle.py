@@ -74,6 +74,7 @@ def lib():
         _lib.orc_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         _lib.orc_step.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 11
         _lib.orc_step_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64] + [C.c_void_p] * 11
+        _lib.orc_rollout_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64] + [C.c_void_p] * 5
     return _lib
 
 
@@ -225,3 +226,27 @@ class OracleVecEnv:
             [t.join() for t in ths]
             self.metrics[:] = parts.sum(0)
         return self.obs, self.reward, self.terminated, self.truncated
+
+    def rollout(self, action_sets, iters):
+        """`iters` lockstep iterations with actions cycling through action_sets[A, N]; each host thread
+        rolls its own env slice forward inside C (bench.py's CPU baseline — envs are independent)."""
+        a = np.ascontiguousarray(action_sets, dtype=np.int64)
+        assert a.ndim == 2 and a.shape[1] == self.num_envs
+        N, nt = self.num_envs, max(1, self.threads)
+        parts = np.zeros((nt, N_METRICS), np.float64)
+        bounds = [(N * t) // nt for t in range(nt + 1)]
+        tick0 = self.tick
+        self.tick += iters
+
+        def work(t):
+            self._lib.orc_rollout_range(C.byref(self._e), bounds[t], bounds[t + 1], _p(a), a.shape[0], int(iters),
+                                        tick0, _p(self.obs), _p(self.reward), _p(self.terminated),
+                                        _p(self.truncated), _p(parts[t]))
+        if nt == 1:
+            work(0)
+        else:
+            ths = [threading.Thread(target=work, args=(t,)) for t in range(nt)]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+        self.metrics[:] = parts.sum(0)
+        return self.metrics
