@@ -9,6 +9,8 @@
 //   tma     : one warp per env per pipeline stage; cp.async.bulk (TMA, 1-D) pulls the whole window
 //             global->shared, lanes patch the dynamic columns in shared memory, cp.async.bulk pushes
 //             the finished window shared->global.  The LSU only touches the 8-byte ring entries.
+#include <cstdlib>
+
 #include "gte_device.cuh"
 #include "gte_launch.h"
 
@@ -172,49 +174,50 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int kTmaWarps = 8;          // warps per CTA
-constexpr int kTmaStages = 4;         // window buffers per warp: current + kTmaDepth loading + 1 draining store
-constexpr int kTmaDepth = kTmaStages - 2;
-
-struct EnvMeta { int ep_start, idx, ds; };
+struct EnvMeta { int ep_start, step, ds; };   // raw loaded words: nothing is computed from them until use,
+                                              // so a prefetch never stalls the warp on its own load
 
 __device__ __forceinline__ EnvMeta load_meta(const GteState& S, int64_t env, int n_envs) {
     EnvMeta m;
-    m.ep_start = 0; m.idx = 0; m.ds = 0;
+    m.ep_start = 0; m.step = 0; m.ds = 0;
     if (env < n_envs) {
-        m.ep_start = S.ep_start[env];
-        m.idx = m.ep_start + S.step[env];
-        m.ds = S.dataset_idx[env];
+        m.ep_start = __ldg(S.ep_start + env);
+        m.step = __ldg(S.step + env);
+        m.ds = __ldg(S.dataset_idx + env);
     }
     return m;
 }
 
-// RPL = ring entries per lane = ceil(W / 32): the ring of the NEXT env is prefetched into registers
-// while the current window is in flight, so no HBM latency sits between "window landed" and "store".
-template <int RPL>
-__global__ void __launch_bounds__(kTmaWarps * 32)
+// One warp per env per pipeline stage.  STAGES window buffers per warp: the env being finished,
+// DEPTH = STAGES-2 windows loading ahead, one buffer draining its store.  RPL = ring entries per
+// lane = ceil(W/32).  Per-env metadata and ring entries are prefetched into registers one full
+// iteration before they are consumed.
+template <int RPL, int STAGES, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 obs_tma_kernel(const GteParams P, const GteData D, const GteState S, float* __restrict__ obs,
                const ObsShape sh) {
+    constexpr int DEPTH = STAGES - 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bars[kTmaWarps][kTmaStages];
+    __shared__ __align__(8) uint64_t bars[WARPS][STAGES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* wbuf = smem_raw + (size_t)warp * kTmaStages * sh.win_bytes;
+    unsigned char* wbuf = smem_raw + (size_t)warp * STAGES * sh.win_bytes;
     const int N = P.n_envs;
 
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kTmaStages; ++s) mbar_init(&bars[warp][s], 1);
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[warp][s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
 
-    const int64_t n_warps = (int64_t)gridDim.x * kTmaWarps;
-    const int64_t env0 = (int64_t)blockIdx.x * kTmaWarps + warp;
+    const int64_t n_warps = (int64_t)gridDim.x * WARPS;
+    const int64_t env0 = (int64_t)blockIdx.x * WARPS + warp;
 
     auto issue_load = [&](int64_t env, const EnvMeta& m, int stage) {   // lane 0 only
         if (env < N) {
             mbar_expect_tx(&bars[warp][stage], (uint32_t)sh.win_bytes);
-            bulk_g2s(wbuf + (size_t)stage * sh.win_bytes, window_src(D, sh, m.ds, m.idx + 1 - sh.W),
+            bulk_g2s(wbuf + (size_t)stage * sh.win_bytes,
+                     window_src(D, sh, m.ds, m.ep_start + m.step + 1 - sh.W),
                      (uint32_t)sh.win_bytes, &bars[warp][stage]);
         }
     };
@@ -227,29 +230,27 @@ obs_tma_kernel(const GteParams P, const GteData D, const GteState S, float* __re
         }
     };
 
-    // meta queue: mq[k] belongs to env + k*n_warps; mq[0..kTmaDepth] have their window load issued
-    EnvMeta mq[kTmaDepth + 2];
+    // mq[k] belongs to env + k*n_warps; mq[0..DEPTH] have their window load in flight.
+    EnvMeta mq[DEPTH + 2];
 #pragma unroll
-    for (int k = 0; k < kTmaDepth + 2; ++k) mq[k] = load_meta(S, env0 + (int64_t)k * n_warps, N);
-    float2 d_cur[RPL], d_nxt[RPL];
+    for (int k = 0; k < DEPTH + 2; ++k) mq[k] = load_meta(S, env0 + (int64_t)k * n_warps, N);
+    EnvMeta m_pend = load_meta(S, env0 + (int64_t)(DEPTH + 2) * n_warps, N);
+    float2 d_cur[RPL], d_pend[RPL];
     load_ring(env0, d_cur);
+    load_ring(env0 + n_warps, d_pend);
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k <= kTmaDepth; ++k) issue_load(env0 + (int64_t)k * n_warps, mq[k], k);
+        for (int k = 0; k <= DEPTH; ++k) issue_load(env0 + (int64_t)k * n_warps, mq[k], k);
     }
 
     int it = 0;
     for (int64_t env = env0; env < N; env += n_warps, ++it) {
-        const int stage = it % kTmaStages;
-        const uint32_t parity = (uint32_t)(it / kTmaStages) & 1u;
+        const int stage = it % STAGES;
+        const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
         unsigned char* buf = wbuf + (size_t)stage * sh.win_bytes;
         const EnvMeta m = mq[0];
-        const int r0 = m.idx + 1 - sh.W;
+        const int r0 = m.ep_start + m.step + 1 - sh.W;
         const int s0 = ((r0 % sh.W) + sh.W) % sh.W;
-
-        // prefetch for later iterations (no use of the results in this iteration)
-        load_ring(env + n_warps, d_nxt);
-        const EnvMeta m_far = load_meta(S, env + (int64_t)(kTmaDepth + 2) * n_warps, N);
 
         mbar_wait(&bars[warp][stage], parity);           // window (static cols + zero dyn cols) has landed
 
@@ -275,16 +276,60 @@ obs_tma_kernel(const GteParams P, const GteData D, const GteState S, float* __re
             // refill the buffer whose store was committed in the PREVIOUS iteration: allow only the
             // store just committed to be still reading shared memory.
             bulk_wait_read<1>();
-            issue_load(env + (int64_t)(kTmaDepth + 1) * n_warps, mq[kTmaDepth + 1], (it + kTmaDepth + 1) % kTmaStages);
+            issue_load(env + (int64_t)(DEPTH + 1) * n_warps, mq[DEPTH + 1], (it + DEPTH + 1) % STAGES);
         }
-        // rotate the queues
+        // rotate: consume the prefetches issued one iteration ago, then issue the next ones
 #pragma unroll
-        for (int k = 0; k < kTmaDepth + 1; ++k) mq[k] = mq[k + 1];
-        mq[kTmaDepth + 1] = m_far;
+        for (int k = 0; k < DEPTH + 1; ++k) mq[k] = mq[k + 1];
+        mq[DEPTH + 1] = m_pend;
+        m_pend = load_meta(S, env + (int64_t)(DEPTH + 3) * n_warps, N);
 #pragma unroll
-        for (int q = 0; q < RPL; ++q) d_cur[q] = d_nxt[q];
+        for (int q = 0; q < RPL; ++q) d_cur[q] = d_pend[q];
+        load_ring(env + 2 * n_warps, d_pend);
     }
     if (lane == 0) bulk_wait_read<0>();                   // smem must outlive the last store's reads
+}
+
+using ObsKernelFn = void (*)(const GteParams, const GteData, const GteState, float*, const ObsShape);
+
+template <int STAGES, int WARPS>
+static ObsKernelFn tma_kernel_for(int rpl) {
+    return rpl <= 1 ? obs_tma_kernel<1, STAGES, WARPS>
+                    : (rpl <= 2 ? obs_tma_kernel<2, STAGES, WARPS> : obs_tma_kernel<4, STAGES, WARPS>);
+}
+
+struct TmaConfig { int stages, warps; };
+
+// default pipeline shape; GTE_TMA_STAGES / GTE_TMA_WARPS override it for tuning runs
+static TmaConfig tma_config() {
+    static TmaConfig cfg = [] {
+        TmaConfig c{3, 8};
+        if (const char* e = getenv("GTE_TMA_STAGES")) c.stages = atoi(e);
+        if (const char* e = getenv("GTE_TMA_WARPS")) c.warps = atoi(e);
+        if (c.stages < 2 || c.stages > 6) c.stages = 3;
+        if (c.warps != 4 && c.warps != 8) c.warps = 8;
+        return c;
+    }();
+    return cfg;
+}
+
+static ObsKernelFn tma_kernel(const TmaConfig& c, int rpl) {
+    if (c.warps == 4) {
+        switch (c.stages) {
+            case 2: return tma_kernel_for<2, 4>(rpl);
+            case 3: return tma_kernel_for<3, 4>(rpl);
+            case 5: return tma_kernel_for<5, 4>(rpl);
+            case 6: return tma_kernel_for<6, 4>(rpl);
+            default: return tma_kernel_for<4, 4>(rpl);
+        }
+    }
+    switch (c.stages) {
+        case 2: return tma_kernel_for<2, 8>(rpl);
+        case 3: return tma_kernel_for<3, 8>(rpl);
+        case 5: return tma_kernel_for<5, 8>(rpl);
+        case 6: return tma_kernel_for<6, 8>(rpl);
+        default: return tma_kernel_for<4, 8>(rpl);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ launch
@@ -299,7 +344,10 @@ bool obs_vec_supported(const GteParams& P, const GteData& D) {
     return D.window_table_ds_stride % 16 == 0;
 }
 
-static size_t tma_smem_bytes(const ObsShape& sh) { return (size_t)kTmaWarps * kTmaStages * sh.win_bytes; }
+static size_t tma_smem_bytes(const ObsShape& sh) {
+    const TmaConfig c = tma_config();
+    return (size_t)c.warps * c.stages * sh.win_bytes;
+}
 
 bool obs_tma_supported(const GteParams& P, const GteData& D) {
     if (!obs_vec_supported(P, D)) return false;
@@ -340,17 +388,16 @@ cudaError_t launch_obs(const GteParams& P, const GteData& D, const GteState& S, 
     if (variant == GTE_OBS_TMA) {
         if (!obs_tma_supported(P, D)) return cudaErrorInvalidValue;
         const size_t smem = tma_smem_bytes(sh);
-        const int rpl = (sh.W + 31) / 32;
-        void (*kern)(const GteParams, const GteData, const GteState, float*, const ObsShape) =
-            rpl <= 1 ? obs_tma_kernel<1> : (rpl <= 2 ? obs_tma_kernel<2> : obs_tma_kernel<4>);
+        const TmaConfig cfg = tma_config();
+        ObsKernelFn kern = tma_kernel(cfg, (sh.W + 31) / 32);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        int per_sm = (int)((220 * 1024) / (smem + 1024));
+        int per_sm = (int)((227 * 1024) / (smem + 1024 + 8 * cfg.warps * cfg.stages));
         if (per_sm < 1) per_sm = 1;
-        if (per_sm > 8) per_sm = 8;
-        const int64_t need = ((int64_t)P.n_envs + kTmaWarps - 1) / kTmaWarps;
+        if (per_sm > 2048 / (cfg.warps * 32)) per_sm = 2048 / (cfg.warps * 32);
+        const int64_t need = ((int64_t)P.n_envs + cfg.warps - 1) / cfg.warps;
         const int grid = (int)(need < (int64_t)sms * per_sm ? need : (int64_t)sms * per_sm);
-        kern<<<grid, kTmaWarps * 32, smem, stream>>>(P, D, S, obs, sh);
+        kern<<<grid, cfg.warps * 32, smem, stream>>>(P, D, S, obs, sh);
         return cudaGetLastError();
     }
     return cudaErrorInvalidValue;

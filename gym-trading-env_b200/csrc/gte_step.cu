@@ -1,9 +1,11 @@
 // gte_step.cu — fused per-env transition kernel, reset kernel and info kernel (sm_100a).
 //
-// One thread per env, structure-of-arrays state in HBM (coalesced 8/4-byte accesses), persistent
-// grid-stride CTAs (grid = min(tiles, SMs x 8)) so that the per-CTA metric partials stay few.
+// One thread per env, structure-of-arrays state in HBM (coalesced 8/4-byte accesses), one 256-env
+// tile per CTA (a few consecutive tiles when N is huge, so the per-CTA metric partials stay bounded).
 // Replaces TradingEnv.step (environments.py:233-272) for N envs in lockstep; see
 // include/gte_b200.h for the boundary and DESIGN.md for the data layout / roofline.
+#include <cstdlib>
+
 #include "gte_device.cuh"
 #include "gte_launch.h"
 
@@ -176,14 +178,18 @@ __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O) {
     if (threadIdx.x == 0) *O.block_counter = 0u;         // self-resetting for the next launch
 }
 
-__global__ void __launch_bounds__(kStepThreads)
+// Each CTA owns `tiles_per_cta` CONSECUTIVE 256-env tiles (1 unless N > 256 x kMaxPartialRows), so the
+// grid is as wide as the problem (latency hiding comes from CTA-level parallelism, not a loop) while
+// the metric partials stay bounded.
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(kStepThreads, MIN_CTAS)
 step_kernel(const GteParams P, const GteData D, const GteState S, const int64_t* __restrict__ actions,
-            const GteStepOut O, uint64_t tick, int autoreset) {
+            const GteStepOut O, uint64_t tick, int autoreset, int tiles_per_cta) {
     MetricAcc acc;
-    for (int64_t base = (int64_t)blockIdx.x * kStepThreads; base < P.n_envs;
-         base += (int64_t)gridDim.x * kStepThreads) {
-        const int i = (int)(base + threadIdx.x);
-        if (i < P.n_envs) step_env(P, D, S, actions, O, tick, autoreset, i, acc);
+    const int64_t base0 = (int64_t)blockIdx.x * tiles_per_cta * kStepThreads;
+    for (int t = 0; t < tiles_per_cta; ++t) {
+        const int64_t i = base0 + (int64_t)t * kStepThreads + threadIdx.x;
+        if (i < P.n_envs) step_env(P, D, S, actions, O, tick, autoreset, (int)i, acc);
     }
     reduce_metrics(acc, O);
 }
@@ -269,16 +275,26 @@ int num_sms() {
     return g_num_sms;
 }
 
+static int step_tiles_per_cta(int n_envs) {
+    const int64_t tiles = ((int64_t)n_envs + kStepThreads - 1) / kStepThreads;
+    return (int)((tiles + kMaxPartialRows - 1) / kMaxPartialRows);
+}
+
 int step_grid(int n_envs) {
     const int64_t tiles = ((int64_t)n_envs + kStepThreads - 1) / kStepThreads;
-    int64_t cap = (int64_t)num_sms() * 8;
-    if (cap > kMaxPartialRows) cap = kMaxPartialRows;
-    return (int)(tiles < cap ? tiles : cap);
+    const int tpc = step_tiles_per_cta(n_envs);
+    return (int)((tiles + tpc - 1) / tpc);
 }
 
 cudaError_t launch_step(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
                         const GteStepOut& O, uint64_t tick, int autoreset, cudaStream_t stream) {
-    step_kernel<<<step_grid(P.n_envs), kStepThreads, 0, stream>>>(P, D, S, actions, O, tick, autoreset);
+    static const int min_ctas = [] { const char* e = getenv("GTE_STEP_MIN_CTAS"); return e ? atoi(e) : 3; }();
+    if (min_ctas >= 4)
+        step_kernel<4><<<step_grid(P.n_envs), kStepThreads, 0, stream>>>(P, D, S, actions, O, tick, autoreset,
+                                                                         step_tiles_per_cta(P.n_envs));
+    else
+        step_kernel<3><<<step_grid(P.n_envs), kStepThreads, 0, stream>>>(P, D, S, actions, O, tick, autoreset,
+                                                                         step_tiles_per_cta(P.n_envs));
     return cudaGetLastError();
 }
 

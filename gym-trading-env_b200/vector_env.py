@@ -138,7 +138,8 @@ class TradingVectorEnv:
     ``[N, E, 3]`` of (start row, position index, dataset index) consumed by successive resets
     instead of the RNG (record-and-replay for parity tests); ``obs_variant`` in
     {"auto","generic","vec","tma"}; ``output`` "torch" (CUDA tensors, default) or "numpy"
-    (pinned host buffers, host<->device copies inside `step`); ``autoreset`` (True = in-place).
+    (pinned host buffers, host<->device copies inside `step`); ``autoreset`` (True = in-place);
+    ``debug_outputs`` (also write the terminal step's idx/step/real_position/portfolio, +48 B/env).
 
     ``reward_function`` must be :func:`basic_reward_function` and ``dynamic_feature_functions`` the two
     defaults or ``[]``: arbitrary Python callbacks over a History cannot run inside the kernel and
@@ -155,7 +156,7 @@ class TradingVectorEnv:
                  max_episode_duration="max", verbose=1, name="Stock", render_mode="logs", *,
                  num_envs=1, device=None, seed=0, env_id_offset=0, done_valuation_ratio=0.7,
                  reset_plan=None, obs_variant="auto", output="torch", autoreset=True,
-                 _multi_dataset=False, _episodes_between_dataset_switch=1):
+                 debug_outputs=False, _multi_dataset=False, _episodes_between_dataset_switch=1):
         self._lib = _cabi.load()                      # fails loudly when the CUDA library is missing
         if not torch.cuda.is_available():
             raise RuntimeError("gym_trading_env_b200 needs a CUDA device (no CPU fallback)")
@@ -210,6 +211,7 @@ class TradingVectorEnv:
         self.done_valuation_ratio = float(done_valuation_ratio)
         self.output = output
         self.autoreset = bool(autoreset)
+        self.debug_outputs = bool(debug_outputs)
         self._obs_variant = _cabi.OBS_VARIANTS[obs_variant]
         self._multi = bool(_multi_dataset)
         self._k_switch = int(_episodes_between_dataset_switch)
@@ -367,9 +369,11 @@ class TradingVectorEnv:
         s.error_flag = self._error_flag.data_ptr()
         o = _cabi.GteStepOut()
         o.reward, o.terminated, o.truncated = self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr()
-        o.valuation, o.real_position = self._valuation.data_ptr(), self._real_position.data_ptr()
-        o.info_idx, o.info_step = self._info_idx.data_ptr(), self._info_step.data_ptr()
-        o.pre_reset_portfolio = self._pre_reset_portfolio.data_ptr()
+        o.valuation = self._valuation.data_ptr()
+        if self.debug_outputs:          # terminal-step info columns, only materialised for tests / final_info
+            o.real_position = self._real_position.data_ptr()
+            o.info_idx, o.info_step = self._info_idx.data_ptr(), self._info_step.data_ptr()
+            o.pre_reset_portfolio = self._pre_reset_portfolio.data_ptr()
         o.metric_partials, o.metrics_step = self._metric_partials.data_ptr(), self._metrics_step.data_ptr()
         o.metrics_total, o.block_counter = self._metrics_total.data_ptr(), self._block_counter.data_ptr()
         i = _cabi.GteInfo()

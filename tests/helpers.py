@@ -59,7 +59,7 @@ def make_device_env(g, plan=True, **over):
     import gym_trading_env_b200 as gte
     p = g["params"]
     kw = env_kwargs(g)
-    kw.update(num_envs=p["n_envs"], reset_plan=g["plan"] if plan else None, verbose=0)
+    kw.update(num_envs=p["n_envs"], reset_plan=g["plan"] if plan else None, verbose=0, debug_outputs=True)
     if not p.get("dynamic_features", True):
         kw["dynamic_feature_functions"] = []
     kw.update(over)

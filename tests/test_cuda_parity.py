@@ -85,7 +85,7 @@ def test_cuda_matches_oracle_philox_resets_c3_shape(variant):
     kw = dict(positions=pos, windows=64, trading_fees=1e-4, borrow_interest_rate=3e-6,
               portfolio_initial_value=1000, max_episode_duration=100)
     N = 3000     # not a multiple of the CTA size: exercises the ragged tail
-    dev = gte.TradingVectorEnv(arr, num_envs=N, seed=77, env_id_offset=12345, obs_variant=variant, verbose=0, **kw)
+    dev = gte.TradingVectorEnv(arr, num_envs=N, seed=77, env_id_offset=12345, obs_variant=variant, verbose=0, debug_outputs=True, **kw)
     o = orc.OracleVecEnv(arr.features, arr.price, num_envs=N, seed=77, env_id_offset=12345, **kw)
     eps = _compare_with_oracle(dev, o, K=230, n_pos=len(pos), seed=1)
     assert eps >= 2 * N
@@ -98,7 +98,7 @@ def test_cuda_matches_oracle_windows_none_c2_shape():
     pos = [-1, 0, 0.5, 1]
     kw = dict(positions=pos, windows=None, trading_fees=1e-4, borrow_interest_rate=3e-6,
               portfolio_initial_value=1000, max_episode_duration="max")
-    dev = gte.TradingVectorEnv(arr, num_envs=4096, seed=3, verbose=0, **kw)
+    dev = gte.TradingVectorEnv(arr, num_envs=4096, seed=3, verbose=0, debug_outputs=True, **kw)
     o = orc.OracleVecEnv(arr.features, arr.price, num_envs=4096, seed=3, **kw)
     _compare_with_oracle(dev, o, K=120, n_pos=len(pos), seed=2)
 
@@ -119,7 +119,7 @@ def test_cuda_matches_oracle_multi_dataset_rotation():
         kw = dict(positions=pos, windows=16, trading_fees=1e-4, borrow_interest_rate=3e-6,
                   portfolio_initial_value=1000, max_episode_duration=25)
         dev = gte.MultiDatasetTradingVectorEnv(datasets=series, episodes_between_dataset_switch=k_switch,
-                                               num_envs=1500, seed=9, verbose=0, **kw)
+                                               num_envs=1500, seed=9, verbose=0, debug_outputs=True, **kw)
         o = orc.OracleVecEnv(feats, price, np.array(lens), num_envs=1500, seed=9, multi_dataset=True,
                              episodes_between_dataset_switch=k_switch, **kw)
         _compare_with_oracle(dev, o, K=150, n_pos=len(pos), seed=3)
@@ -136,7 +136,8 @@ def test_termination_rule_and_threshold_parameter():
     kw = dict(positions=pos, windows=None, trading_fees=1e-3, borrow_interest_rate=1e-4,
               portfolio_initial_value=1000, max_episode_duration="max")
     for ratio in (0.7, 0.0):
-        dev = gte.TradingVectorEnv(arr, num_envs=512, seed=1, done_valuation_ratio=ratio, verbose=0, **kw)
+        dev = gte.TradingVectorEnv(arr, num_envs=512, seed=1, done_valuation_ratio=ratio, verbose=0,
+                                   debug_outputs=True, **kw)
         o = orc.OracleVecEnv(arr.features, arr.price, num_envs=512, seed=1, done_ratio=ratio, **kw)
         _compare_with_oracle(dev, o, K=200, n_pos=3, seed=4, hold=0.0)
         term = float(dev.get_metrics()["terminated"].item())
