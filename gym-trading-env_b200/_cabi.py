@@ -53,7 +53,7 @@ class GteState(C.Structure):
         ("interest_fiat", C.c_void_p), ("pos_idx", C.c_void_p), ("step", C.c_void_p),
         ("ep_start", C.c_void_p), ("dataset_idx", C.c_void_p), ("dyn_ring", C.c_void_p),
         ("plan_cursor", C.c_void_p), ("ds_used", C.c_void_p), ("ds_episodes", C.c_void_p),
-        ("reset_plan", C.c_void_p), ("error_flag", C.c_void_p),
+        ("reset_plan", C.c_void_p), ("error_flag", C.c_void_p), ("tick", C.c_void_p),
     ]
 
 
@@ -75,8 +75,8 @@ class GteInfo(C.Structure):
     ]
 
 
-EXPORTS = ["gte_version", "gte_last_error", "gte_reset", "gte_step", "gte_gather_obs", "gte_info",
-           "gte_obs_variant_for"]
+EXPORTS = ["gte_version", "gte_last_error", "gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs",
+           "gte_info", "gte_obs_variant_for", "gte_default_chunks"]
 
 
 def nvcc_command(out_path: str = LIB_PATH):
@@ -122,13 +122,16 @@ def load():
     lib.gte_version.restype = C.c_int
     lib.gte_last_error.restype = C.c_char_p
     P = C.POINTER
-    lib.gte_reset.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
-    lib.gte_step.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, P(GteStepOut), C.c_uint64,
-                             C.c_int, C.c_void_p]
+    lib.gte_reset.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, C.c_int, C.c_void_p]
+    lib.gte_step.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, P(GteStepOut), C.c_int, C.c_void_p]
     lib.gte_gather_obs.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, C.c_int, C.c_void_p]
+    lib.gte_step_obs.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, P(GteStepOut), C.c_void_p,
+                                 C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.gte_info.argtypes = [P(GteParams), P(GteData), P(GteState), P(GteInfo), C.c_void_p]
     lib.gte_obs_variant_for.argtypes = [P(GteParams), P(GteData)]
-    for name in ("gte_reset", "gte_step", "gte_gather_obs", "gte_info", "gte_obs_variant_for"):
+    lib.gte_default_chunks.argtypes = [C.c_int]
+    lib.gte_default_chunks.restype = C.c_int
+    for name in ("gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs", "gte_info", "gte_obs_variant_for"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

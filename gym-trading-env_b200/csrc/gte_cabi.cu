@@ -41,7 +41,7 @@ int check_common(const char* fn, const GteParams* p, const GteData* d, const Gte
     GTE_REQUIRE(fn, s->asset && s->fiat && s->interest_asset && s->interest_fiat);
     GTE_REQUIRE(fn, s->pos_idx && s->step && s->ep_start && s->dataset_idx);
     GTE_REQUIRE(fn, p->n_dyn == 0 || s->dyn_ring != nullptr);
-    GTE_REQUIRE(fn, s->plan_cursor && s->ds_used && s->ds_episodes && s->error_flag);
+    GTE_REQUIRE(fn, s->plan_cursor && s->ds_used && s->ds_episodes && s->error_flag && s->tick);
     GTE_REQUIRE(fn, p->plan_episodes == 0 || s->reset_plan != nullptr);
     return GTE_OK;
 }
@@ -55,33 +55,53 @@ int gte_version(void) { return GTE_VERSION; }
 const char* gte_last_error(void) { return g_err; }
 
 int gte_reset(const GteParams* params, const GteData* data, const GteState* state, const uint8_t* mask,
-              uint64_t tick, int first, void* stream) {
+              int first, void* stream) {
     if (int rc = check_common("gte_reset", params, data, state)) return rc;
-    return check_cuda("gte_reset", gte::launch_reset(*params, *data, *state, mask, tick, first,
+    return check_cuda("gte_reset", gte::launch_reset(*params, *data, *state, mask, first,
                                                      static_cast<cudaStream_t>(stream)));
 }
 
+static int check_step_out(const char* fn, const int64_t* actions, const GteStepOut* out) {
+    GTE_REQUIRE(fn, actions != nullptr && out != nullptr);
+    GTE_REQUIRE(fn, out->reward && out->terminated && out->truncated);
+    GTE_REQUIRE(fn, out->metric_partials && out->metrics_step && out->block_counter);
+    return GTE_OK;
+}
+
 int gte_step(const GteParams* params, const GteData* data, const GteState* state, const int64_t* actions,
-             const GteStepOut* out, uint64_t tick, int autoreset, void* stream) {
+             const GteStepOut* out, int autoreset, void* stream) {
     if (int rc = check_common("gte_step", params, data, state)) return rc;
-    GTE_REQUIRE("gte_step", actions != nullptr && out != nullptr);
-    GTE_REQUIRE("gte_step", out->reward && out->terminated && out->truncated);
-    GTE_REQUIRE("gte_step", out->metric_partials && out->metrics_step && out->block_counter);
-    return check_cuda("gte_step", gte::launch_step(*params, *data, *state, actions, *out, tick, autoreset,
+    if (int rc = check_step_out("gte_step", actions, out)) return rc;
+    return check_cuda("gte_step", gte::launch_step(*params, *data, *state, actions, *out, autoreset,
                                                    static_cast<cudaStream_t>(stream)));
+}
+
+static int check_variant(const char* fn, const GteParams* params, const GteData* data, int variant) {
+    GTE_REQUIRE(fn, variant >= GTE_OBS_AUTO && variant <= GTE_OBS_TMA);
+    if (variant == GTE_OBS_VEC && !gte::obs_vec_supported(*params, *data))
+        return fail_arg(fn, "GTE_OBS_VEC needs windows>0, 16-byte-multiple windows and window tables");
+    if (variant == GTE_OBS_TMA && !gte::obs_tma_supported(*params, *data))
+        return fail_arg(fn, "GTE_OBS_TMA needs the GTE_OBS_VEC conditions and windows<=128");
+    return GTE_OK;
+}
+
+int gte_step_obs(const GteParams* params, const GteData* data, const GteState* state, const int64_t* actions,
+                 const GteStepOut* out, float* obs, int autoreset, int variant, int n_chunks, void* stream) {
+    if (int rc = check_common("gte_step_obs", params, data, state)) return rc;
+    if (int rc = check_step_out("gte_step_obs", actions, out)) return rc;
+    GTE_REQUIRE("gte_step_obs", obs != nullptr && n_chunks >= 0 && n_chunks <= 16);
+    if (int rc = check_variant("gte_step_obs", params, data, variant)) return rc;
+    return check_cuda("gte_step_obs", gte::launch_step_obs(*params, *data, *state, actions, *out, obs, autoreset,
+                                                           variant, n_chunks, static_cast<cudaStream_t>(stream)));
 }
 
 int gte_gather_obs(const GteParams* params, const GteData* data, const GteState* state, float* obs,
                    int variant, void* stream) {
     if (int rc = check_common("gte_gather_obs", params, data, state)) return rc;
     GTE_REQUIRE("gte_gather_obs", obs != nullptr);
-    GTE_REQUIRE("gte_gather_obs", variant >= GTE_OBS_AUTO && variant <= GTE_OBS_TMA);
-    if (variant == GTE_OBS_VEC && !gte::obs_vec_supported(*params, *data))
-        return fail_arg("gte_gather_obs", "GTE_OBS_VEC needs windows>0, 16-byte-multiple windows and window tables");
-    if (variant == GTE_OBS_TMA && !gte::obs_tma_supported(*params, *data))
-        return fail_arg("gte_gather_obs", "GTE_OBS_TMA needs the GTE_OBS_VEC conditions and windows<=128");
-    return check_cuda("gte_gather_obs", gte::launch_obs(*params, *data, *state, obs, variant,
-                                                        static_cast<cudaStream_t>(stream)));
+    if (int rc = check_variant("gte_gather_obs", params, data, variant)) return rc;
+    return check_cuda("gte_gather_obs", gte::launch_obs_range(*params, *data, *state, obs, variant, 0,
+                                                              params->n_envs, static_cast<cudaStream_t>(stream)));
 }
 
 int gte_info(const GteParams* params, const GteData* data, const GteState* state, const GteInfo* info,
@@ -91,6 +111,8 @@ int gte_info(const GteParams* params, const GteData* data, const GteState* state
     return check_cuda("gte_info", gte::launch_info(*params, *data, *state, *info,
                                                    static_cast<cudaStream_t>(stream)));
 }
+
+int gte_default_chunks(int n_envs) { return n_envs > 0 ? gte::default_chunks(n_envs) : GTE_ERR_ARG; }
 
 int gte_obs_variant_for(const GteParams* params, const GteData* data) {
     if (params == nullptr || data == nullptr) return GTE_ERR_ARG;

@@ -12,16 +12,20 @@ int num_sms();
 int step_grid(int n_envs);
 
 cudaError_t launch_step(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
-                        const GteStepOut& O, uint64_t tick, int autoreset, cudaStream_t stream);
+                        const GteStepOut& O, int autoreset, cudaStream_t stream);
 cudaError_t launch_reset(const GteParams& P, const GteData& D, const GteState& S, const uint8_t* mask,
-                         uint64_t tick, int first, cudaStream_t stream);
+                         int first, cudaStream_t stream);
 cudaError_t launch_info(const GteParams& P, const GteData& D, const GteState& S, const GteInfo& I,
                         cudaStream_t stream);
 
 // Which gather variants the shape allows (vector/TMA need 16-byte-multiple windows + window tables).
 bool obs_vec_supported(const GteParams& P, const GteData& D);
 bool obs_tma_supported(const GteParams& P, const GteData& D);
-cudaError_t launch_obs(const GteParams& P, const GteData& D, const GteState& S, float* obs, int variant,
-                       cudaStream_t stream);
+cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteState& S, float* obs, int variant,
+                             int env_begin, int env_end, cudaStream_t stream);
+int default_chunks(int n_envs);
+cudaError_t launch_step_obs(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
+                            const GteStepOut& O, float* obs, int autoreset, int variant, int n_chunks,
+                            cudaStream_t stream);
 
 }  // namespace gte

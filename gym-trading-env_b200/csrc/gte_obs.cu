@@ -43,12 +43,12 @@ static ObsShape make_shape(const GteParams& P) {
 template <int G>
 __global__ void __launch_bounds__(256)
 obs_generic_kernel(const GteParams P, const GteData D, const GteState S, float* __restrict__ obs,
-                   const ObsShape sh) {
+                   const ObsShape sh, const int env_begin, const int env_end) {
     const int groups_per_block = 256 / G;
     const int lane = threadIdx.x % G;
     const int64_t n_groups = (int64_t)gridDim.x * groups_per_block;
     const int per_env = sh.W * sh.F;
-    for (int64_t env = (int64_t)blockIdx.x * groups_per_block + threadIdx.x / G; env < P.n_envs;
+    for (int64_t env = env_begin + (int64_t)blockIdx.x * groups_per_block + threadIdx.x / G; env < env_end;
          env += n_groups) {
         const int ep_start = S.ep_start[env];
         const int idx = ep_start + S.step[env];
@@ -97,10 +97,10 @@ __device__ __forceinline__ const char* window_src(const GteData& D, const ObsSha
 template <bool PAIR>     // PAIR: n_dyn == 2 and F even -> the dynamic pair is an aligned float2
 __global__ void __launch_bounds__(256)
 obs_vec_kernel(const GteParams P, const GteData D, const GteState S, float* __restrict__ obs,
-               const ObsShape sh) {
+               const ObsShape sh, const int env_begin, const int env_end) {
     const int lane = threadIdx.x & 31;
     const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); env < P.n_envs;
+    for (int64_t env = env_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); env < env_end;
          env += n_warps) {
         const int ep_start = S.ep_start[env];
         const int idx = ep_start + S.step[env];
@@ -169,6 +169,33 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
+// L2 eviction policies (createpolicy): the observation stream is written once and never re-read by this
+// path (evict_first), the window tables are re-read by every env (evict_last)
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                              uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void* gdst, const void* smem_src, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ float2 ld_nc_v2_hint(const float2* p, uint64_t policy) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;"
+                 : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(policy));
+    return v;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
@@ -195,13 +222,14 @@ __device__ __forceinline__ EnvMeta load_meta(const GteState& S, int64_t env, int
 template <int RPL, int STAGES, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 obs_tma_kernel(const GteParams P, const GteData D, const GteState S, float* __restrict__ obs,
-               const ObsShape sh) {
+               const ObsShape sh, const int env_begin, const int env_end, const int hints) {
     constexpr int DEPTH = STAGES - 2;
+    const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bars[WARPS][STAGES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wbuf = smem_raw + (size_t)warp * STAGES * sh.win_bytes;
-    const int N = P.n_envs;
+    const int N = env_end;               // exclusive upper bound of this launch's env range
 
     if (lane == 0) {
 #pragma unroll
@@ -211,14 +239,14 @@ obs_tma_kernel(const GteParams P, const GteData D, const GteState S, float* __re
     __syncwarp();
 
     const int64_t n_warps = (int64_t)gridDim.x * WARPS;
-    const int64_t env0 = (int64_t)blockIdx.x * WARPS + warp;
+    const int64_t env0 = env_begin + (int64_t)blockIdx.x * WARPS + warp;
 
     auto issue_load = [&](int64_t env, const EnvMeta& m, int stage) {   // lane 0 only
         if (env < N) {
             mbar_expect_tx(&bars[warp][stage], (uint32_t)sh.win_bytes);
-            bulk_g2s(wbuf + (size_t)stage * sh.win_bytes,
-                     window_src(D, sh, m.ds, m.ep_start + m.step + 1 - sh.W),
-                     (uint32_t)sh.win_bytes, &bars[warp][stage]);
+            const void* src = window_src(D, sh, m.ds, m.ep_start + m.step + 1 - sh.W);
+            if (hints & 2) bulk_g2s_hint(wbuf + (size_t)stage * sh.win_bytes, src, (uint32_t)sh.win_bytes, &bars[warp][stage], pol_last);
+            else bulk_g2s(wbuf + (size_t)stage * sh.win_bytes, src, (uint32_t)sh.win_bytes, &bars[warp][stage]);
         }
     };
     auto load_ring = [&](int64_t env, float2 (&d)[RPL]) {
@@ -226,7 +254,8 @@ obs_tma_kernel(const GteParams P, const GteData D, const GteState S, float* __re
 #pragma unroll
         for (int q = 0; q < RPL; ++q) {
             const int s = lane + 32 * q;
-            d[q] = (sh.nd > 0 && env < N && s < sh.W) ? __ldg(ring + s) : make_float2(0.f, 0.f);
+            d[q] = make_float2(0.f, 0.f);
+            if (sh.nd > 0 && env < N && s < sh.W) d[q] = (hints & 4) ? ld_nc_v2_hint(ring + s, pol_first) : __ldg(ring + s);
         }
     };
 
@@ -271,7 +300,9 @@ obs_tma_kernel(const GteParams P, const GteData D, const GteState S, float* __re
         }
         __syncwarp();
         if (lane == 0) {
-            bulk_s2g(reinterpret_cast<char*>(obs) + env * (int64_t)sh.win_bytes, buf, (uint32_t)sh.win_bytes);
+            char* dst = reinterpret_cast<char*>(obs) + env * (int64_t)sh.win_bytes;
+            if (hints & 1) bulk_s2g_hint(dst, buf, (uint32_t)sh.win_bytes, pol_first);
+            else bulk_s2g(dst, buf, (uint32_t)sh.win_bytes);
             bulk_commit();
             // refill the buffer whose store was committed in the PREVIOUS iteration: allow only the
             // store just committed to be still reading shared memory.
@@ -290,7 +321,7 @@ obs_tma_kernel(const GteParams P, const GteData D, const GteState S, float* __re
     if (lane == 0) bulk_wait_read<0>();                   // smem must outlive the last store's reads
 }
 
-using ObsKernelFn = void (*)(const GteParams, const GteData, const GteState, float*, const ObsShape);
+using ObsKernelFn = void (*)(const GteParams, const GteData, const GteState, float*, const ObsShape, int, int, int);
 
 template <int STAGES, int WARPS>
 static ObsKernelFn tma_kernel_for(int rpl) {
@@ -355,9 +386,11 @@ bool obs_tma_supported(const GteParams& P, const GteData& D) {
     return sh.W <= 128 && tma_smem_bytes(sh) <= 200 * 1024;
 }
 
-cudaError_t launch_obs(const GteParams& P, const GteData& D, const GteState& S, float* obs, int variant,
-                       cudaStream_t stream) {
+cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteState& S, float* obs, int variant,
+                             int env_begin, int env_end, cudaStream_t stream) {
     const ObsShape sh = make_shape(P);
+    const int n_envs = env_end - env_begin;
+    if (n_envs <= 0) return cudaSuccess;
     if (variant == GTE_OBS_AUTO)
         variant = obs_tma_supported(P, D) ? GTE_OBS_TMA : (obs_vec_supported(P, D) ? GTE_OBS_VEC : GTE_OBS_GENERIC);
     const int sms = num_sms();
@@ -365,24 +398,24 @@ cudaError_t launch_obs(const GteParams& P, const GteData& D, const GteState& S, 
         const int per_env = sh.W * sh.F;
         int G = 32;
         while (G > 1 && G / 2 >= per_env) G /= 2;
-        const int64_t need = ((int64_t)P.n_envs * G + 255) / 256;
+        const int64_t need = ((int64_t)n_envs * G + 255) / 256;
         const int grid = (int)(need < (int64_t)sms * 16 ? need : (int64_t)sms * 16);
         switch (G) {
-            case 32: obs_generic_kernel<32><<<grid, 256, 0, stream>>>(P, D, S, obs, sh); break;
-            case 16: obs_generic_kernel<16><<<grid, 256, 0, stream>>>(P, D, S, obs, sh); break;
-            case 8: obs_generic_kernel<8><<<grid, 256, 0, stream>>>(P, D, S, obs, sh); break;
-            case 4: obs_generic_kernel<4><<<grid, 256, 0, stream>>>(P, D, S, obs, sh); break;
-            case 2: obs_generic_kernel<2><<<grid, 256, 0, stream>>>(P, D, S, obs, sh); break;
-            default: obs_generic_kernel<1><<<grid, 256, 0, stream>>>(P, D, S, obs, sh); break;
+            case 32: obs_generic_kernel<32><<<grid, 256, 0, stream>>>(P, D, S, obs, sh, env_begin, env_end); break;
+            case 16: obs_generic_kernel<16><<<grid, 256, 0, stream>>>(P, D, S, obs, sh, env_begin, env_end); break;
+            case 8: obs_generic_kernel<8><<<grid, 256, 0, stream>>>(P, D, S, obs, sh, env_begin, env_end); break;
+            case 4: obs_generic_kernel<4><<<grid, 256, 0, stream>>>(P, D, S, obs, sh, env_begin, env_end); break;
+            case 2: obs_generic_kernel<2><<<grid, 256, 0, stream>>>(P, D, S, obs, sh, env_begin, env_end); break;
+            default: obs_generic_kernel<1><<<grid, 256, 0, stream>>>(P, D, S, obs, sh, env_begin, env_end); break;
         }
         return cudaGetLastError();
     }
     if (variant == GTE_OBS_VEC) {
         if (!obs_vec_supported(P, D)) return cudaErrorInvalidValue;
-        const int64_t need = ((int64_t)P.n_envs + 7) / 8;
+        const int64_t need = ((int64_t)n_envs + 7) / 8;
         const int grid = (int)(need < (int64_t)sms * 8 ? need : (int64_t)sms * 8);
-        if (sh.nd == 2 && sh.F % 2 == 0) obs_vec_kernel<true><<<grid, 256, 0, stream>>>(P, D, S, obs, sh);
-        else obs_vec_kernel<false><<<grid, 256, 0, stream>>>(P, D, S, obs, sh);
+        if (sh.nd == 2 && sh.F % 2 == 0) obs_vec_kernel<true><<<grid, 256, 0, stream>>>(P, D, S, obs, sh, env_begin, env_end);
+        else obs_vec_kernel<false><<<grid, 256, 0, stream>>>(P, D, S, obs, sh, env_begin, env_end);
         return cudaGetLastError();
     }
     if (variant == GTE_OBS_TMA) {
@@ -390,14 +423,21 @@ cudaError_t launch_obs(const GteParams& P, const GteData& D, const GteState& S, 
         const size_t smem = tma_smem_bytes(sh);
         const TmaConfig cfg = tma_config();
         ObsKernelFn kern = tma_kernel(cfg, (sh.W + 31) / 32);
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+        static ObsKernelFn configured_kern = nullptr;      // opt-in to > 48 KB dynamic smem once per kernel
+        static size_t configured_smem = 0;
+        if (kern != configured_kern || smem > configured_smem) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured_kern = kern;
+            configured_smem = smem;
+        }
         int per_sm = (int)((227 * 1024) / (smem + 1024 + 8 * cfg.warps * cfg.stages));
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 2048 / (cfg.warps * 32)) per_sm = 2048 / (cfg.warps * 32);
-        const int64_t need = ((int64_t)P.n_envs + cfg.warps - 1) / cfg.warps;
+        const int64_t need = ((int64_t)n_envs + cfg.warps - 1) / cfg.warps;
         const int grid = (int)(need < (int64_t)sms * per_sm ? need : (int64_t)sms * per_sm);
-        kern<<<grid, cfg.warps * 32, smem, stream>>>(P, D, S, obs, sh);
+        static const int hints = [] { const char* e = getenv("GTE_TMA_HINTS"); return e ? atoi(e) : 0; }();
+        kern<<<grid, cfg.warps * 32, smem, stream>>>(P, D, S, obs, sh, env_begin, env_end, hints);
         return cudaGetLastError();
     }
     return cudaErrorInvalidValue;

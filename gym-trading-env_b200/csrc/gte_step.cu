@@ -11,6 +11,8 @@
 
 namespace gte {
 
+constexpr int kChunkFirst = 1, kChunkLast = 2;
+
 struct StepThreadOut {       // what the gather phase of the fused kernel needs from the step phase
     int idx, ep_start, ds;
 };
@@ -123,7 +125,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // CTA-level metric reduction -> metric_partials[blockIdx.x]; the last CTA to arrive folds all
 // partial rows in a fixed order (deterministic) into metrics_step / metrics_total.
-__device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O) {
+__device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O, const GteState& S, int chunk_flags) {
     __shared__ double s_part[kStepThreads / 32][GTE_N_METRICS];
     __shared__ double s_fold[32][GTE_N_METRICS];
     __shared__ bool s_last;
@@ -172,10 +174,16 @@ __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O) {
     if (threadIdx.x < GTE_N_METRICS) {
         double tot = 0.0;
         for (int k = 0; k < kStepThreads / GTE_N_METRICS; ++k) tot = dadd(tot, s_fold[k][threadIdx.x]);
-        O.metrics_step[threadIdx.x] = tot;
+        // env chunks of one lockstep iteration run as consecutive launches: the first one overwrites
+        // metrics_step, later ones add to it in launch order (deterministic)
+        O.metrics_step[threadIdx.x] = (chunk_flags & kChunkFirst) ? tot : dadd(O.metrics_step[threadIdx.x], tot);
         if (O.metrics_total) O.metrics_total[threadIdx.x] = dadd(O.metrics_total[threadIdx.x], tot);
     }
-    if (threadIdx.x == 0) *O.block_counter = 0u;         // self-resetting for the next launch
+    if (threadIdx.x == 0) {
+        *O.block_counter = 0u;                           // self-resetting for the next launch
+        // every CTA of this iteration has read the tick by now: advance the Philox event counter
+        if (chunk_flags & kChunkLast) *S.tick = *S.tick + 1ull;
+    }
 }
 
 // Each CTA owns `tiles_per_cta` CONSECUTIVE 256-env tiles (1 unless N > 256 x kMaxPartialRows), so the
@@ -184,23 +192,25 @@ __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O) {
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(kStepThreads, MIN_CTAS)
 step_kernel(const GteParams P, const GteData D, const GteState S, const int64_t* __restrict__ actions,
-            const GteStepOut O, uint64_t tick, int autoreset, int tiles_per_cta) {
+            const GteStepOut O, int autoreset, int tiles_per_cta, int env_begin, int env_end, int chunk_flags) {
     MetricAcc acc;
-    const int64_t base0 = (int64_t)blockIdx.x * tiles_per_cta * kStepThreads;
+    const uint64_t tick = *S.tick;
+    const int64_t base0 = (int64_t)env_begin + (int64_t)blockIdx.x * tiles_per_cta * kStepThreads;
     for (int t = 0; t < tiles_per_cta; ++t) {
         const int64_t i = base0 + (int64_t)t * kStepThreads + threadIdx.x;
-        if (i < P.n_envs) step_env(P, D, S, actions, O, tick, autoreset, (int)i, acc);
+        if (i < env_end) step_env(P, D, S, actions, O, tick, autoreset, (int)i, acc);
     }
-    reduce_metrics(acc, O);
+    reduce_metrics(acc, O, S, chunk_flags);
 }
 
 // TradingEnv.reset for the masked envs (environments.py:163-199, :393-400); `first` also performs
 // the dataset draw of MultiDatasetTradingEnv.__init__ (:377-378).
 __global__ void __launch_bounds__(kStepThreads)
 reset_kernel(const GteParams P, const GteData D, const GteState S, const uint8_t* __restrict__ mask,
-             uint64_t tick, int first) {
+             int first) {
     const int i = blockIdx.x * kStepThreads + threadIdx.x;
     if (i >= P.n_envs) return;
+    const uint64_t tick = *S.tick;
     if (first) {
         S.ds_used[i] = 0;
         S.ds_episodes[i] = 0;
@@ -227,6 +237,8 @@ reset_kernel(const GteParams P, const GteData D, const GteState S, const uint8_t
     S.ep_start[i] = e.ep_start;
     S.dataset_idx[i] = e.ds;
 }
+
+__global__ void bump_tick_kernel(uint64_t* tick) { *tick = *tick + 1ull; }
 
 // History's last row from the current state (environments.py:253-264, portfolio.py:49-57).
 __global__ void __launch_bounds__(kStepThreads)
@@ -286,23 +298,101 @@ int step_grid(int n_envs) {
     return (int)((tiles + tpc - 1) / tpc);
 }
 
-cudaError_t launch_step(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
-                        const GteStepOut& O, uint64_t tick, int autoreset, cudaStream_t stream) {
-    static const int min_ctas = [] { const char* e = getenv("GTE_STEP_MIN_CTAS"); return e ? atoi(e) : 3; }();
+cudaError_t launch_step_range(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
+                              const GteStepOut& O, int autoreset, int env_begin, int env_end, int chunk_flags,
+                              cudaStream_t stream) {
+    static const int min_ctas = [] { const char* e = getenv("GTE_STEP_MIN_CTAS"); return e ? atoi(e) : 4; }();
+    const int n = env_end - env_begin;
+    const int grid = step_grid(n), tpc = step_tiles_per_cta(n);
+    // same shared-memory carve-out as the gather kernel, so CTAs of both can be resident on one SM
+    static const bool carveout_set = [] {
+        cudaFuncSetAttribute(step_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(step_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        return true;
+    }();
+    (void)carveout_set;
     if (min_ctas >= 4)
-        step_kernel<4><<<step_grid(P.n_envs), kStepThreads, 0, stream>>>(P, D, S, actions, O, tick, autoreset,
-                                                                         step_tiles_per_cta(P.n_envs));
+        step_kernel<4><<<grid, kStepThreads, 0, stream>>>(P, D, S, actions, O, autoreset, tpc, env_begin, env_end, chunk_flags);
     else
-        step_kernel<3><<<step_grid(P.n_envs), kStepThreads, 0, stream>>>(P, D, S, actions, O, tick, autoreset,
-                                                                         step_tiles_per_cta(P.n_envs));
+        step_kernel<3><<<grid, kStepThreads, 0, stream>>>(P, D, S, actions, O, autoreset, tpc, env_begin, env_end, chunk_flags);
     return cudaGetLastError();
 }
 
+cudaError_t launch_step(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
+                        const GteStepOut& O, int autoreset, cudaStream_t stream) {
+    return launch_step_range(P, D, S, actions, O, autoreset, 0, P.n_envs, kChunkFirst | kChunkLast, stream);
+}
+
 cudaError_t launch_reset(const GteParams& P, const GteData& D, const GteState& S, const uint8_t* mask,
-                         uint64_t tick, int first, cudaStream_t stream) {
+                         int first, cudaStream_t stream) {
     const int grid = (P.n_envs + kStepThreads - 1) / kStepThreads;
-    reset_kernel<<<grid, kStepThreads, 0, stream>>>(P, D, S, mask, tick, first);
+    reset_kernel<<<grid, kStepThreads, 0, stream>>>(P, D, S, mask, first);
+    bump_tick_kernel<<<1, 1, 0, stream>>>(S.tick);
     return cudaGetLastError();
+}
+
+// ---- one lockstep iteration = step + gather, env chunks pipelined over two streams ---------------
+// The step kernel is latency-bound (dependent loads + fp64 divide/log chains), the gather is
+// HBM-bound; running the step of chunk c+1 beside the gather of chunk c hides the former.
+struct AuxStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork[16] = {};
+    cudaEvent_t join = nullptr;
+    int device = -1;
+};
+static AuxStream g_aux[16];
+
+static cudaError_t aux_for_current_device(AuxStream** out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    AuxStream& a = g_aux[dev & 15];
+    if (a.stream == nullptr) {
+        if ((e = cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        for (auto& ev : a.fork)
+            if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming)) != cudaSuccess) return e;
+        a.device = dev;
+    }
+    *out = &a;
+    return cudaSuccess;
+}
+
+int default_chunks(int n_envs) {
+    // Measured on B200 (profiles/r01_tuning.md): running the step kernel of range c+1 beside the gather of
+    // range c does not beat two plain launches — the gather already saturates HBM writes and the extra
+    // launches add tails — so pipelining is opt-in (n_chunks > 1 or GTE_CHUNKS).
+    static const int forced = [] { const char* e = getenv("GTE_CHUNKS"); return e ? atoi(e) : 0; }();
+    (void)n_envs;
+    if (forced > 0) return forced > 16 ? 16 : forced;
+    return 1;
+}
+
+cudaError_t launch_step_obs(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
+                            const GteStepOut& O, float* obs, int autoreset, int variant, int n_chunks,
+                            cudaStream_t stream) {
+    if (n_chunks <= 0) n_chunks = default_chunks(P.n_envs);
+    if (n_chunks > 16) n_chunks = 16;
+    cudaError_t e;
+    if (n_chunks == 1) {
+        if ((e = launch_step(P, D, S, actions, O, autoreset, stream)) != cudaSuccess) return e;
+        return launch_obs_range(P, D, S, obs, variant, 0, P.n_envs, stream);
+    }
+    AuxStream* aux = nullptr;
+    if ((e = aux_for_current_device(&aux)) != cudaSuccess) return e;
+    const int64_t per = (((int64_t)P.n_envs + n_chunks - 1) / n_chunks + kStepThreads - 1) / kStepThreads * kStepThreads;
+    n_chunks = (int)(((int64_t)P.n_envs + per - 1) / per);         // drop empty tail chunks
+    for (int c = 0; c < n_chunks; ++c) {
+        const int b = (int)(c * per);
+        const int en = (int)((c + 1) * per < P.n_envs ? (c + 1) * per : P.n_envs);
+        const int flags = (c == 0 ? kChunkFirst : 0) | (c == n_chunks - 1 ? kChunkLast : 0);
+        if ((e = launch_step_range(P, D, S, actions, O, autoreset, b, en, flags, stream)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(aux->fork[c], stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(aux->stream, aux->fork[c], 0)) != cudaSuccess) return e;
+        if ((e = launch_obs_range(P, D, S, obs, variant, b, en, aux->stream)) != cudaSuccess) return e;
+    }
+    if ((e = cudaEventRecord(aux->join, aux->stream)) != cudaSuccess) return e;
+    return cudaStreamWaitEvent(stream, aux->join, 0);
 }
 
 cudaError_t launch_info(const GteParams& P, const GteData& D, const GteState& S, const GteInfo& I,

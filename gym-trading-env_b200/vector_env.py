@@ -137,8 +137,13 @@ class TradingVectorEnv:
     rule, environments.py:246; 0.0 = upstream "valuation <= 0"); ``reset_plan`` — int32
     ``[N, E, 3]`` of (start row, position index, dataset index) consumed by successive resets
     instead of the RNG (record-and-replay for parity tests); ``obs_variant`` in
-    {"auto","generic","vec","tma"}; ``output`` "torch" (CUDA tensors, default) or "numpy"
-    (pinned host buffers, host<->device copies inside `step`); ``autoreset`` (True = in-place);
+    {"auto","generic","vec","tma"}; ``output`` "torch" (CUDA tensors, default), "numpy" (everything
+    in pinned host buffers, host<->device copies inside `step`) or "hybrid" (reward / terminated /
+    truncated on the host, observations stay device-resident for an on-device policy; the copies
+    run on side streams beside the gather kernel); ``autoreset`` (True = in-place); ``cuda_graph``
+    (capture one lockstep iteration and replay it: removes the launch overhead at small N; actions
+    are then read from the env's own buffer); ``n_chunks`` (0 = auto: env ranges whose step kernel
+    is pipelined beside the previous range's gather);
     ``debug_outputs`` (also write the terminal step's idx/step/real_position/portfolio, +48 B/env).
 
     ``reward_function`` must be :func:`basic_reward_function` and ``dynamic_feature_functions`` the two
@@ -156,7 +161,7 @@ class TradingVectorEnv:
                  max_episode_duration="max", verbose=1, name="Stock", render_mode="logs", *,
                  num_envs=1, device=None, seed=0, env_id_offset=0, done_valuation_ratio=0.7,
                  reset_plan=None, obs_variant="auto", output="torch", autoreset=True,
-                 debug_outputs=False, _multi_dataset=False, _episodes_between_dataset_switch=1):
+                 debug_outputs=False, cuda_graph=False, n_chunks=0, _multi_dataset=False, _episodes_between_dataset_switch=1):
         self._lib = _cabi.load()                      # fails loudly when the CUDA library is missing
         if not torch.cuda.is_available():
             raise RuntimeError("gym_trading_env_b200 needs a CUDA device (no CPU fallback)")
@@ -198,8 +203,8 @@ class TradingVectorEnv:
         if max_episode_duration != "max" and (not isinstance(max_episode_duration, (int, np.integer))
                                               or max_episode_duration < 2):
             raise ValueError("max_episode_duration must be 'max' or an int >= 2")
-        if output not in ("torch", "numpy"):
-            raise ValueError("output must be 'torch' or 'numpy'")
+        if output not in ("torch", "numpy", "hybrid"):
+            raise ValueError("output must be 'torch', 'numpy' or 'hybrid'")
         if obs_variant not in _cabi.OBS_VARIANTS:
             raise ValueError(f"obs_variant must be one of {list(_cabi.OBS_VARIANTS)}")
 
@@ -212,12 +217,15 @@ class TradingVectorEnv:
         self.output = output
         self.autoreset = bool(autoreset)
         self.debug_outputs = bool(debug_outputs)
+        self.cuda_graph = bool(cuda_graph)
+        self.n_chunks = int(n_chunks)
+        self._graph = None
+        self._copy_in = self._copy_out = None
         self._obs_variant = _cabi.OBS_VARIANTS[obs_variant]
         self._multi = bool(_multi_dataset)
         self._k_switch = int(_episodes_between_dataset_switch)
         self._tick = 0
         self._needs_first = True
-        self._obs_events = None
         self.log_metrics = []
 
         series = df if isinstance(df, (list, tuple)) else [df]
@@ -312,6 +320,7 @@ class TradingVectorEnv:
         self._ds_used = torch.zeros(N, dtype=torch.int64, device=dev)
         self._dyn_ring = torch.zeros(N, W, 2, dtype=torch.float32, device=dev)
         self._error_flag = i32(1)
+        self._tick_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self._reset_plan = None
         if reset_plan is not None:
             plan = torch.as_tensor(np.ascontiguousarray(reset_plan), dtype=torch.int32)
@@ -367,6 +376,7 @@ class TradingVectorEnv:
         s.plan_cursor, s.ds_used, s.ds_episodes = self._plan_cursor.data_ptr(), self._ds_used.data_ptr(), self._ds_episodes.data_ptr()
         s.reset_plan = None if self._reset_plan is None else self._reset_plan.data_ptr()
         s.error_flag = self._error_flag.data_ptr()
+        s.tick = self._tick_dev.data_ptr()
         o = _cabi.GteStepOut()
         o.reward, o.terminated, o.truncated = self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr()
         o.valuation = self._valuation.data_ptr()
@@ -390,27 +400,15 @@ class TradingVectorEnv:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _next_tick(self):
-        t = self._tick
-        self._tick += 1
-        return t
-
     def _launch_reset(self, mask_ptr, first):
+        self._tick += 1
         _cabi.check(self._lib.gte_reset(C.byref(self._P), C.byref(self._D), C.byref(self._S), mask_ptr,
-                                        self._next_tick(), int(first), self._stream()), "gte_reset")
+                                        int(first), self._stream()), "gte_reset")
 
     def _launch_obs(self, variant=None):
         v = self._obs_variant if variant is None else variant
-        ev = self._obs_events                       # bench.py: live CUDA-event timing of the gather kernel
-        if ev is not None:
-            e0 = torch.cuda.Event(enable_timing=True)
-            e0.record()
         _cabi.check(self._lib.gte_gather_obs(C.byref(self._P), C.byref(self._D), C.byref(self._S),
                                              C.c_void_p(self._obs.data_ptr()), v, self._stream()), "gte_gather_obs")
-        if ev is not None:
-            e1 = torch.cuda.Event(enable_timing=True)
-            e1.record()
-            ev.append((e0, e1))
 
     def _launch_info(self):
         _cabi.check(self._lib.gte_info(C.byref(self._P), C.byref(self._D), C.byref(self._S), C.byref(self._I),
@@ -418,14 +416,40 @@ class TradingVectorEnv:
 
     def _launch_step(self, actions_ptr, autoreset=None):
         ar = self.autoreset if autoreset is None else autoreset
+        self._tick += 1
         _cabi.check(self._lib.gte_step(C.byref(self._P), C.byref(self._D), C.byref(self._S), actions_ptr,
-                                       C.byref(self._O), self._next_tick(), int(ar), self._stream()), "gte_step")
+                                       C.byref(self._O), int(ar), self._stream()), "gte_step")
+
+    def _launch_step_obs(self, actions_ptr, n_chunks=None):
+        """One lockstep iteration in one C call: step kernel(s) + gather kernel(s), chunk-pipelined."""
+        self._tick += 1
+        _cabi.check(self._lib.gte_step_obs(C.byref(self._P), C.byref(self._D), C.byref(self._S), actions_ptr,
+                                           C.byref(self._O), C.c_void_p(self._obs.data_ptr()), int(self.autoreset),
+                                           self._obs_variant, self.n_chunks if n_chunks is None else n_chunks,
+                                           self._stream()), "gte_step_obs")
+
+    def _capture_graph(self):
+        """Capture one lockstep iteration (actions read from self._actions_dev) into a CUDA graph.
+        Kernel arguments are all pointers/constants; the Philox tick lives on the device."""
+        g = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(device=self.device)
+        cap.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.graph(g, stream=cap):
+            self._launch_step_obs(C.c_void_p(self._actions_dev.data_ptr()))
+        self._tick -= 1                       # the capture itself executed nothing
+        torch.cuda.current_stream(self.device).wait_stream(cap)
+        self._graph = g
 
     def _host_buffers(self):
         if self._host is None:
             pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)   # noqa: E731
-            self._host = {"actions": pin(self._actions_dev), "obs": pin(self._obs), "reward": pin(self._reward),
-                          "terminated": pin(self._terminated), "truncated": pin(self._truncated)}
+            self._host = {"actions": pin(self._actions_dev), "reward": pin(self._reward),
+                          "terminated": pin(self._terminated), "truncated": pin(self._truncated),
+                          "error_flag": pin(self._error_flag)}
+            if self.output == "numpy":
+                self._host["obs"] = pin(self._obs)
+            self._copy_in = torch.cuda.Stream(device=self.device)
+            self._copy_out = torch.cuda.Stream(device=self.device)
         return self._host
 
     # ------------------------------------------------------------------ gymnasium vector API
@@ -452,30 +476,64 @@ class TradingVectorEnv:
     def step(self, actions):
         """One lockstep iteration (environments.py:233-272) with in-place auto-reset."""
         with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
             host_in = not (isinstance(actions, torch.Tensor) and actions.is_cuda)
             if host_in:
                 a = np.asarray(actions)
                 if a.shape != (self.num_envs,):
                     raise ValueError(f"actions must have shape ({self.num_envs},), got {a.shape}")
-                if a.size and (a.max() >= len(self.positions)):
-                    raise IndexError("list index out of range")      # what positions[position_index] raises (:234)
-                h = self._host_buffers()["actions"]
-                h.numpy()[...] = a
-                self._actions_dev.copy_(h, non_blocking=True)
+                hb = self._host_buffers()
+                src = None
+                if a.dtype == np.int64 and a.flags.c_contiguous and a.flags.writeable:
+                    t = torch.from_numpy(a)
+                    if t.is_pinned():
+                        src = t                                      # caller already staged them in pinned memory
+                if src is None:
+                    hb["actions"].numpy()[...] = a                   # pageable -> pinned staging copy
+                    src = hb["actions"]
+                # H2D on its own stream: it may run beside the previous iteration's gather.  Out-of-range
+                # actions are flagged by the kernel (positions[position_index] would raise, :234) and the
+                # flag rides back with the results in the host-output modes.
+                self._copy_in.wait_stream(main)
+                with torch.cuda.stream(self._copy_in):
+                    self._actions_dev.copy_(src, non_blocking=True)
+                main.wait_stream(self._copy_in)
                 act = self._actions_dev
             else:
                 act = actions
                 if act.dtype != torch.int64 or not act.is_contiguous() or act.shape != (self.num_envs,) \
                         or act.device != self.device:
                     act = act.to(device=self.device, dtype=torch.int64).contiguous().view(self.num_envs)
-            self._launch_step(C.c_void_p(act.data_ptr()))
-            self._launch_obs()
+            if self.output == "hybrid":
+                # reward / flags leave for the host right after the step kernel, beside the gather
+                hb = self._host_buffers()
+                self._launch_step(C.c_void_p(act.data_ptr()))
+                self._copy_out.wait_stream(main)
+                with torch.cuda.stream(self._copy_out):
+                    for k, t in (("reward", self._reward), ("terminated", self._terminated),
+                                 ("truncated", self._truncated), ("error_flag", self._error_flag)):
+                        hb[k].copy_(t, non_blocking=True)
+                self._launch_obs()
+                self._copy_out.synchronize()
+                self._raise_on_flag(int(hb["error_flag"][0]))
+                return (self._obs, hb["reward"].numpy(), hb["terminated"].numpy().view(np.bool_),
+                        hb["truncated"].numpy().view(np.bool_), self.infos)
+            if self.cuda_graph:
+                if act.data_ptr() != self._actions_dev.data_ptr():
+                    self._actions_dev.copy_(act, non_blocking=True)
+                if self._graph is None:
+                    self._capture_graph()
+                self._tick += 1
+                self._graph.replay()
+            else:
+                self._launch_step_obs(C.c_void_p(act.data_ptr()))
             if self.output == "numpy":
                 h = self._host_buffers()
                 for k, t in (("obs", self._obs), ("reward", self._reward), ("terminated", self._terminated),
-                             ("truncated", self._truncated)):
+                             ("truncated", self._truncated), ("error_flag", self._error_flag)):
                     h[k].copy_(t, non_blocking=True)
-                torch.cuda.current_stream(self.device).synchronize()
+                main.synchronize()
+                self._raise_on_flag(int(h["error_flag"][0]))
                 return (h["obs"].numpy(), h["reward"].numpy(), h["terminated"].numpy().view(np.bool_),
                         h["truncated"].numpy().view(np.bool_), self.infos)
             return self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), self.infos
@@ -490,6 +548,7 @@ class TradingVectorEnv:
 
     def close(self):
         self._host = None
+        self._graph = None
 
     # ------------------------------------------------------------------ metrics / errors / state
     def get_metrics(self, total=True):
@@ -508,7 +567,14 @@ class TradingVectorEnv:
 
     def check_errors(self):
         """Synchronising check of the in-kernel error flags (device-resident actions are not validated on the host)."""
-        flag = int(self._error_flag.item())
+        self._raise_on_flag(int(self._error_flag.item()))
+
+    def pinned_actions(self):
+        """A pinned int64 [N] numpy array: fill it and pass it to `step()` to skip the staging copy."""
+        return torch.empty(self.num_envs, dtype=torch.int64, pin_memory=True).numpy()
+
+    @staticmethod
+    def _raise_on_flag(flag):
         if flag & 1:
             raise IndexError("an action >= len(positions) was passed to step() (treated as hold)")
         if flag & 2:
@@ -517,22 +583,23 @@ class TradingVectorEnv:
     def state_dict(self):
         """Env state as tensors (checkpoint/resume: SURVEY.md §5)."""
         names = ["asset", "fiat", "interest_asset", "interest_fiat", "pos_idx", "step", "ep_start", "dataset_idx",
-                 "dyn_ring", "plan_cursor", "ds_used", "ds_episodes", "metrics_total"]
-        d = {n: getattr(self, "_" + n).clone() for n in names}
-        d["tick"] = self._tick
-        return d
+                 "dyn_ring", "plan_cursor", "ds_used", "ds_episodes", "metrics_total", "tick_dev"]
+        return {n: getattr(self, "_" + n).clone() for n in names}
 
     def load_state_dict(self, d):
         for n, v in d.items():
-            if n == "tick":
-                self._tick = int(v)
-            else:
-                getattr(self, "_" + n).copy_(v)
+            getattr(self, "_" + n).copy_(v)
+        self._tick += 1                    # invalidates the lazily computed infos
         self._needs_first = False
 
     @property
     def idx(self):
         return self._ep_start + self._step
+
+    @property
+    def chunks(self):
+        """Env ranges one `step()` is pipelined over (step kernel of range c+1 beside gather of range c)."""
+        return self.n_chunks if self.n_chunks > 0 else int(self._lib.gte_default_chunks(self.num_envs))
 
     @property
     def obs_variant(self):

@@ -113,7 +113,11 @@ typedef struct GteState {
     uint64_t* ds_used;               /* u64 [N]  datasets used in the current rotation round (:383)    */
     int32_t* ds_episodes;            /* i32 [N]  _episodes_on_this_dataset (:381,394)                  */
     const int32_t* reset_plan;       /* i32 [N, E, 3] (start row, position idx, dataset idx) or NULL   */
-    int32_t* error_flag;             /* i32 [1]  bit 0: action out of range seen (treated as hold)     */
+    int32_t* error_flag;             /* i32 [1]  bit 0: action out of range seen (treated as hold);
+                                                 bit 1: an env was stepped past the end of its data    */
+    uint64_t* tick;                  /* u64 [1]  event counter keying the Philox draws; every gte_reset /
+                                        gte_step / gte_step_obs call advances it by one ON THE DEVICE, so
+                                        a captured CUDA graph of a step replays with fresh draws       */
 } GteState;
 
 /* Outputs of one lockstep iteration.  reward / flags / valuation / real_position / info_* are the
@@ -147,12 +151,12 @@ int gte_version(void);
 const char* gte_last_error(void);
 
 /* Replaces TradingEnv.reset (environments.py:163-199) [+ MultiDatasetTradingEnv.reset :393-400 and,
- * with first != 0, the dataset draw of MultiDatasetTradingEnv.__init__ :377-378] for every env whose
- * mask byte is non-zero (mask == NULL: all envs).  Episode start / initial position / dataset come
- * from state->reset_plan when params->plan_episodes > 0, else from Philox4x32-10 keyed by
- * (seed, tick, global env id). */
+ * with first != 0, ONLY the dataset draw of MultiDatasetTradingEnv.__init__ :377-378] for every env
+ * whose mask byte is non-zero (mask == NULL: all envs).  Episode start / initial position / dataset
+ * come from state->reset_plan when params->plan_episodes > 0, else from Philox4x32-10 keyed by
+ * (seed, *state->tick, global env id). */
 int gte_reset(const GteParams* params, const GteData* data, const GteState* state,
-              const uint8_t* mask, uint64_t tick, int first, void* stream);
+              const uint8_t* mask, int first, void* stream);
 
 /* Replaces TradingEnv.step (environments.py:233-272) for N envs: _take_action/_trade (:204-215) ->
  * Portfolio.trade_to_position (portfolio.py:18-43) -> index advance -> update_interest (:44-46) ->
@@ -160,7 +164,7 @@ int gte_reset(const GteParams* params, const GteData* data, const GteState* stat
  * metrics (:279-283) -> in-place auto-reset when autoreset != 0.  actions: i64 [N] indices into
  * positions; a negative action = hold (the reference's position_index=None, :234). */
 int gte_step(const GteParams* params, const GteData* data, const GteState* state,
-             const int64_t* actions, const GteStepOut* out, uint64_t tick, int autoreset, void* stream);
+             const int64_t* actions, const GteStepOut* out, int autoreset, void* stream);
 
 /* Replaces TradingEnv._get_obs (environments.py:152-160): obs f32 [N, F] (windows=None) or
  * [N, W, F], F = n_static + n_dyn; static columns gathered from the device-resident tables,
@@ -168,9 +172,21 @@ int gte_step(const GteParams* params, const GteData* data, const GteState* state
 int gte_gather_obs(const GteParams* params, const GteData* data, const GteState* state,
                    float* obs, int variant, void* stream);
 
+/* One whole lockstep iteration — what a vector env's step() returns: gte_step + gte_gather_obs.
+ * The envs are cut into n_chunks ranges (0 = choose; 1 = two plain launches) and the step kernel of
+ * range c+1 runs beside the gather of range c on a library-owned side stream (forked from and
+ * joined back into `stream` with events, so the call is still stream-ordered and graph-capturable):
+ * the latency-bound transition math hides under the HBM-bound gather. */
+int gte_step_obs(const GteParams* params, const GteData* data, const GteState* state,
+                 const int64_t* actions, const GteStepOut* out, float* obs, int autoreset,
+                 int variant, int n_chunks, void* stream);
+
 /* History's last row as tensors (environments.py:253-264, portfolio.py:49-57), from current state. */
 int gte_info(const GteParams* params, const GteData* data, const GteState* state,
              const GteInfo* info, void* stream);
+
+/* How many env ranges gte_step_obs uses for n_chunks = 0 (host-only helper). */
+int gte_default_chunks(int n_envs);
 
 /* Which gather variant GTE_OBS_AUTO resolves to for this shape (host-only helper). */
 int gte_obs_variant_for(const GteParams* params, const GteData* data);

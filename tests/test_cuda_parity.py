@@ -149,8 +149,10 @@ def test_cabi_argument_errors_and_host_validation():
     arr = gte.frame_to_arrays(gte.make_gbm_ohlcv(500, seed=0))
     env = gte.TradingVectorEnv(arr, positions=[0, 1], windows=8, num_envs=16, verbose=0)
     env.reset()
+    env_np = gte.TradingVectorEnv(arr, positions=[0, 1], windows=8, num_envs=16, verbose=0, output="numpy")
+    env_np.reset()
     with pytest.raises(IndexError):
-        env.step(np.full(16, 2))                       # host actions are validated before launch
+        env_np.step(np.full(16, 2))                    # flagged in-kernel, raised when the results reach the host
     with pytest.raises(ValueError):
         env.step(np.zeros(3, dtype=np.int64))
     import torch
@@ -200,3 +202,45 @@ def test_numpy_output_mode_and_infos():
                      ("asset", "fiat", "borrowed_asset", "borrowed_fiat", "interest_asset", "interest_fiat")])
     assert np.array_equal(dist[0] - dist[2], o.asset) and np.array_equal(dist[1] - dist[3], o.fiat)
     assert np.array_equal(dist[4], o.interest_asset) and np.array_equal(dist[5], o.interest_fiat)
+
+
+@pytest.mark.parametrize("mode", ["chunks3", "graph", "graph_chunks", "hybrid"])
+def test_step_obs_pipelined_graph_and_hybrid_modes_match_oracle(mode):
+    """gte_step_obs with env-range pipelining over two streams, CUDA-graph replay (device-resident
+    Philox tick) and the hybrid host/device output mode must all produce the plain two-launch results."""
+    import torch
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    arr = gte.frame_to_arrays(gte.make_gbm_ohlcv(4000, seed=8))
+    pos = [-2, -1, 0, 1, 2]
+    kw = dict(positions=pos, windows=32, trading_fees=1e-4, borrow_interest_rate=3e-6,
+              portfolio_initial_value=1000, max_episode_duration=40)
+    N = 2500
+    extra = {"chunks3": dict(n_chunks=3), "graph": dict(cuda_graph=True),
+             "graph_chunks": dict(cuda_graph=True, n_chunks=4), "hybrid": dict(output="hybrid")}[mode]
+    dev = gte.TradingVectorEnv(arr, num_envs=N, seed=21, verbose=0, **extra, **kw)
+    o = orc.OracleVecEnv(arr.features, arr.price, num_envs=N, seed=21, **kw)
+    obs, _ = dev.reset()
+    H.assert_bits(obs.cpu().numpy(), o.reset(), "reset obs")
+    rng = np.random.default_rng(5)
+    for k in range(130):
+        a = rng.integers(0, len(pos), size=N)
+        if mode == "hybrid":
+            obs, rew, term, trunc, _ = dev.step(a)
+            assert isinstance(rew, np.ndarray) and isinstance(obs, torch.Tensor)
+            rew, term, trunc = rew.copy(), term.copy(), trunc.copy()
+        else:
+            obs, rew, term, trunc, _ = dev.step(torch.as_tensor(a, device=dev.device))
+            rew, term, trunc = rew.cpu().numpy(), term.cpu().numpy(), trunc.cpu().numpy()
+        o.step(a)
+        H.assert_bits(obs.cpu().numpy(), o.obs, f"step {k} obs ({mode})")
+        H.assert_bits(term, o.terminated.astype(bool), f"step {k} terminated")
+        H.assert_bits(trunc, o.truncated.astype(bool), f"step {k} truncated")
+        H.assert_close64(rew, o.reward, f"step {k} reward")
+        H.assert_bits(dev._valuation.cpu().numpy(), o.valuation, f"step {k} valuation")
+        H.assert_bits(dev._ep_start.cpu().numpy(), o.ep_start, f"step {k} ep_start (Philox tick)")
+        m = dev._metrics_step.cpu().numpy()
+        assert m[0] == o.metrics[0] and m[5] == o.metrics[5]
+        np.testing.assert_allclose(m[6], o.metrics[6], rtol=1e-9, atol=1e-11)
+    assert int(dev._tick_dev.item()) == 2 + 130
+    dev.check_errors()
