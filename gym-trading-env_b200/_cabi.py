@@ -76,7 +76,7 @@ class GteInfo(C.Structure):
 
 
 EXPORTS = ["gte_version", "gte_last_error", "gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs",
-           "gte_info", "gte_obs_variant_for", "gte_default_chunks"]
+           "gte_info", "gte_obs_variant_for", "gte_default_chunks", "gte_struct_size"]
 
 
 def nvcc_command(out_path: str = LIB_PATH):
@@ -133,6 +133,12 @@ def load():
     lib.gte_default_chunks.restype = C.c_int
     for name in ("gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs", "gte_info", "gte_obs_variant_for"):
         getattr(lib, name).restype = C.c_int
+    lib.gte_struct_size.argtypes = [C.c_int]
+    lib.gte_struct_size.restype = C.c_int
+    for which, st in enumerate((GteParams, GteData, GteState, GteStepOut, GteInfo)):
+        if lib.gte_struct_size(which) != C.sizeof(st):
+            raise RuntimeError(f"ABI mismatch: {st.__name__} is {C.sizeof(st)} bytes here, "
+                               f"{lib.gte_struct_size(which)} in {LIB_PATH} — rebuild the library")
     _lib = lib
     return lib
 

@@ -112,6 +112,17 @@ int gte_info(const GteParams* params, const GteData* data, const GteState* state
                                                    static_cast<cudaStream_t>(stream)));
 }
 
+int gte_struct_size(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(GteParams);
+        case 1: return (int)sizeof(GteData);
+        case 2: return (int)sizeof(GteState);
+        case 3: return (int)sizeof(GteStepOut);
+        case 4: return (int)sizeof(GteInfo);
+        default: return GTE_ERR_ARG;
+    }
+}
+
 int gte_default_chunks(int n_envs) { return n_envs > 0 ? gte::default_chunks(n_envs) : GTE_ERR_ARG; }
 
 int gte_obs_variant_for(const GteParams* params, const GteData* data) {

@@ -89,7 +89,7 @@ __device__ __forceinline__ Portfolio target_portfolio(double position, double va
     return s;
 }
 
-// ---- Philox4x32-10 (Salmon et al., SC'11); identical constants in oracle/gte_oracle.c ------------
+// ---- Philox4x32-10 (Salmon et al., SC'11; Random123 known-answer vectors in tests/) -------------
 __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {

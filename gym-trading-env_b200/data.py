@@ -103,3 +103,36 @@ def make_gbm_arrays(T: int, seed: int = 0, sigma: float = 0.002, n_features: int
         h = horizons[j % len(horizons)]
         feats[:, j] = close[64:] / close[64 - h:T + 64 - h] - 1.0
     return np.ascontiguousarray(feats.astype(np.float32)), np.ascontiguousarray(close[64:])
+
+
+def window_table_classes(row_bytes: int):
+    """Alignment classes c = ((r0*row_bytes) >> 2) & 3 a window start row r0 can fall in."""
+    return sorted({((r * row_bytes) >> 2) & 3 for r in range(4)})
+
+
+def build_window_tables(features: np.ndarray, n_dyn: int):
+    """Host-side layout of the 16-byte-aligned window tables used by the vector / TMA gathers.
+
+    features: float32 [n_datasets, t_stride, n_static].  Returns ``(tables, shifts, ds_stride)``:
+    ``tables[c]`` is a uint8 buffer (to be placed at a 16-byte-aligned device address) holding every
+    dataset's rows in the reference's own ``_obs_array`` layout ``[t, n_static+n_dyn]`` (dynamic
+    columns zero, environments.py:135-141), starting ``shifts[c] = (16 - 4c) % 16`` bytes into the
+    buffer, datasets ``ds_stride`` bytes apart; a window whose first row r0 has
+    ``(r0*row_bytes) % 16 == 4c`` then starts on a 16-byte boundary of copy c.
+    """
+    n_ds, t_stride, ns = features.shape
+    F = ns + n_dyn
+    row_bytes = 4 * F
+    rows = np.zeros((n_ds, t_stride, F), dtype=np.float32)
+    rows[:, :, :ns] = features
+    raw = rows.reshape(n_ds, -1).view(np.uint8)
+    ds_stride = ((t_stride * row_bytes + 15) // 16) * 16
+    tables, shifts = {}, {}
+    for c in window_table_classes(row_bytes):
+        shift = (16 - 4 * c) % 16
+        host = np.zeros(n_ds * ds_stride + 16, dtype=np.uint8)
+        for k in range(n_ds):
+            o = shift + k * ds_stride
+            host[o:o + raw.shape[1]] = raw[k]
+        tables[c], shifts[c] = host, shift
+    return tables, shifts, ds_stride

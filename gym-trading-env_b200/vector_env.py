@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .data import SeriesArrays, frame_to_arrays
+from .data import SeriesArrays, build_window_tables, frame_to_arrays
 
 
 # ---- names the reference exports and callers pass back in (identity-compared, never called) -------
@@ -289,22 +289,12 @@ class TradingVectorEnv:
         row_bytes = 4 * F
         if (int(self.windows) * row_bytes) % 16 != 0:
             return
-        n_ds, t_stride, ns = feats.shape
-        rows = np.zeros((n_ds, t_stride, F), dtype=np.float32)
-        rows[:, :, :ns] = feats
-        ds_stride = ((t_stride * row_bytes + 15) // 16) * 16
-        raw = rows.reshape(n_ds, -1).view(np.uint8)
-        classes = sorted({((r * row_bytes) >> 2) & 3 for r in range(4)})
-        for c in classes:
-            shift = (16 - 4 * c) % 16
-            host = np.zeros(n_ds * ds_stride + 16, dtype=np.uint8)
-            for k in range(n_ds):
-                o = shift + k * ds_stride
-                host[o:o + raw.shape[1]] = raw[k]
+        tables, shifts, ds_stride = build_window_tables(feats, self._n_dyn)
+        for c, host in tables.items():
             t = torch.from_numpy(host).to(self.device)
             assert t.data_ptr() % 16 == 0
             self._window_tables[c] = t
-            self._window_ptrs[c] = t.data_ptr() + shift
+            self._window_ptrs[c] = t.data_ptr() + shifts[c]
         self._window_ds_stride = ds_stride
 
     # ------------------------------------------------------------------ device state

@@ -185,6 +185,10 @@ int gte_step_obs(const GteParams* params, const GteData* data, const GteState* s
 int gte_info(const GteParams* params, const GteData* data, const GteState* state,
              const GteInfo* info, void* stream);
 
+/* sizeof() of the ABI structs as compiled: 0 GteParams, 1 GteData, 2 GteState, 3 GteStepOut, 4 GteInfo
+ * (bindings assert their own layout against it). */
+int gte_struct_size(int which);
+
 /* How many env ranges gte_step_obs uses for n_chunks = 0 (host-only helper). */
 int gte_default_chunks(int n_envs);
 

@@ -1,0 +1,66 @@
+"""CPU: the C-ABI shared library loads without a GPU and exports every symbol include/gte_b200.h
+declares, with the struct layouts the ctypes binding assumes.  No compute calls are made."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "gte_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gte_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_entry_points():
+    names = _declared_functions()
+    for required in ("gte_version", "gte_last_error", "gte_reset", "gte_step", "gte_gather_obs",
+                     "gte_step_obs", "gte_info"):
+        assert required in names
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from gym_trading_env_b200 import _cabi
+    if not os.path.exists(_cabi.LIB_PATH):
+        _cabi.build()
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in _declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/gte_b200.h but not exported"
+    assert set(_cabi.EXPORTS) == set(_declared_functions())
+    lib.gte_version.restype = ctypes.c_int
+    assert lib.gte_version() == 100
+
+
+def test_ctypes_struct_layout_matches_the_compiled_structs():
+    from gym_trading_env_b200 import _cabi
+    lib = _cabi.load()      # load() itself raises on an ABI mismatch
+    for which, st in enumerate((_cabi.GteParams, _cabi.GteData, _cabi.GteState, _cabi.GteStepOut, _cabi.GteInfo)):
+        assert lib.gte_struct_size(which) == ctypes.sizeof(st), st.__name__
+    assert lib.gte_struct_size(99) == -1
+    assert lib.gte_default_chunks(1 << 21) >= 1
+
+
+def test_bad_arguments_are_rejected_before_any_cuda_call():
+    """Argument validation happens on the host: NULL structs -> GTE_ERR_ARG and a message, no launch."""
+    from gym_trading_env_b200 import _cabi
+    lib = _cabi.load()
+    rc = lib.gte_reset(None, None, None, None, 0, None)
+    assert rc == -1 and b"gte_reset" in lib.gte_last_error()
+    p, d, s = _cabi.GteParams(), _cabi.GteData(), _cabi.GteState()
+    rc = lib.gte_step(ctypes.byref(p), ctypes.byref(d), ctypes.byref(s), None, None, 1, None)
+    assert rc == -1 and b"n_envs" in lib.gte_last_error()
+    with pytest.raises(ValueError):
+        _cabi.check(rc, "gte_step")
+
+
+def test_product_package_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under gym-trading-env_b200/ may import or name it."""
+    pkg = os.path.join(ROOT, "gym-trading-env_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "gte_oracle" not in text and "libgte_oracle" not in text, f

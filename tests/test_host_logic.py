@@ -1,0 +1,72 @@
+"""CPU: host-side logic — data staging rules, window-table layout, env sharding, import shim."""
+import numpy as np
+import pandas as pd
+import pytest
+
+import gym_trading_env_b200 as gte
+from gym_trading_env_b200.data import build_window_tables, window_table_classes
+
+
+def test_frame_to_arrays_follows_set_df_rules():
+    df = gte.make_gbm_ohlcv(400, seed=1)
+    df["my_feature_x"] = np.arange(400, dtype=np.float64) / 3.0       # name CONTAINS "feature" (environments.py:130)
+    df["label"] = "x"
+    a = gte.frame_to_arrays(df)
+    assert a.feature_names == [c for c in df.columns if "feature" in c] and a.feature_names[-1] == "my_feature_x"
+    assert a.features.dtype == np.float32 and a.price.dtype == np.float64
+    # numpy's own fp64->fp32 cast, as `_set_df` does (:141)
+    assert np.array_equal(a.features, np.array(df[a.feature_names], dtype=np.float32))
+    assert np.array_equal(a.price, df["close"].to_numpy())
+    assert set(a.info) == {"open", "high", "low", "close", "volume"}
+    with pytest.raises(ValueError):
+        gte.frame_to_arrays(df.drop(columns=["close"]))
+
+
+def test_gbm_generator_is_deterministic_and_has_eight_features():
+    a, b = gte.make_gbm_ohlcv(1000, seed=3), gte.make_gbm_ohlcv(1000, seed=3)
+    assert a.equals(b) and len(a) == 1000 and not a.isna().any().any()
+    assert len([c for c in a.columns if "feature" in c]) == 8
+    assert isinstance(a.index, pd.DatetimeIndex)
+    f, p = gte.make_gbm_arrays(5000, seed=2)
+    assert f.shape == (5000, 8) and f.dtype == np.float32 and p.shape == (5000,) and np.isfinite(f).all()
+
+
+@pytest.mark.parametrize("ns,nd,W", [(8, 2, 64), (5, 2, 24), (3, 0, 16), (7, 2, 16), (8, 0, 4)])
+def test_window_tables_put_every_window_on_a_16_byte_boundary(ns, nd, W):
+    rng = np.random.default_rng(0)
+    feats = rng.standard_normal((3, 50, ns)).astype(np.float32)
+    tables, shifts, ds_stride = build_window_tables(feats, nd)
+    F, rb = ns + nd, 4 * (ns + nd)
+    assert ds_stride % 16 == 0 and set(tables) == set(window_table_classes(rb))
+    for ds in range(3):
+        for r0 in range(0, 50 - W):
+            off = r0 * rb
+            c = (off >> 2) & 3
+            start = shifts[c] + ds * ds_stride + off
+            assert start % 16 == 0                                        # TMA / 128-bit load alignment
+            win = tables[c][start:start + W * rb].view(np.float32).reshape(W, F)
+            assert np.array_equal(win[:, :ns], feats[ds, r0:r0 + W]) and not win[:, ns:].any()
+
+
+def test_shard_envs_partitions_the_index_range():
+    from gym_trading_env_b200.vector_env import shard_envs
+    for total, world in [(1 << 24, 8), (65536, 4), (10, 3), (7, 8)]:
+        spans = [shard_envs(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+        for (o1, c1), (o2, _) in zip(spans, spans[1:]):
+            assert o1 + c1 == o2
+        assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def test_import_shim_points_at_the_hyphenated_package_dir():
+    import os
+    assert os.path.basename(os.path.dirname(gte.__file__)) == "gym-trading-env_b200"
+    assert gte.__version__
+
+
+def test_constructor_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gte.TradingVectorEnv(gte.make_gbm_ohlcv(300, seed=0), num_envs=4)
