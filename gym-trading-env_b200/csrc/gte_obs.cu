@@ -24,6 +24,7 @@ struct ObsShape {
     int W, F, ns, nd;            // window rows, row floats, static cols, dynamic cols
     uint32_t magicF;             // ceil(2^32 / F)
     int row_bytes, win_bytes, n_vec;
+    int w_mask;                  // W-1 when W is a power of two, else -1
 };
 
 static ObsShape make_shape(const GteParams& P) {
@@ -36,6 +37,7 @@ static ObsShape make_shape(const GteParams& P) {
     s.row_bytes = s.F * 4;
     s.win_bytes = s.W * s.row_bytes;
     s.n_vec = s.win_bytes / 16;
+    s.w_mask = (s.W & (s.W - 1)) == 0 ? s.W - 1 : -1;
     return s;
 }
 
@@ -169,67 +171,48 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
-// L2 eviction policies (createpolicy): the observation stream is written once and never re-read by this
-// path (evict_first), the window tables are re-read by every env (evict_last)
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
-                                              uint64_t policy) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g_hint(void* gdst, const void* smem_src, uint32_t bytes, uint64_t policy) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                 :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy) : "memory");
-}
-__device__ __forceinline__ float2 ld_nc_v2_hint(const float2* p, uint64_t policy) {
-    float2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;"
-                 : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(policy));
-    return v;
-}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-struct EnvMeta { int ep_start, step, ds; };   // raw loaded words: nothing is computed from them until use,
-                                              // so a prefetch never stalls the warp on its own load
+// What the gather needs to know about one env, computed ONCE per env by the lane that owns it in the
+// current 32-env block (in parallel across lanes) and then broadcast with shuffles: the per-env loop
+// of a warp is a latency chain, so nothing expensive (64-bit address math, modulo) stays inside it.
+struct EnvPre {
+    unsigned long long src;      // 16-byte-aligned address of the env's window in the window table
+    int r0;                      // absolute row of window row 0
+    int s0;                      // ring slot of window row 0
+    int ep_start;                // rows before it read as zero
+};
 
-__device__ __forceinline__ EnvMeta load_meta(const GteState& S, int64_t env, int n_envs) {
-    EnvMeta m;
-    m.ep_start = 0; m.step = 0; m.ds = 0;
-    if (env < n_envs) {
-        m.ep_start = __ldg(S.ep_start + env);
-        m.step = __ldg(S.step + env);
-        m.ds = __ldg(S.dataset_idx + env);
-    }
-    return m;
-}
-
-// One warp per env per pipeline stage.  STAGES window buffers per warp: the env being finished,
-// DEPTH = STAGES-2 windows loading ahead, one buffer draining its store.  RPL = ring entries per
-// lane = ceil(W/32).  Per-env metadata and ring entries are prefetched into registers one full
-// iteration before they are consumed.
-template <int RPL, int STAGES, int WARPS>
+// One warp per GROUP of G consecutive envs per pipeline stage, everything bulky moved by the TMA engine.
+// The TMA unit of an SM serves bulk operations at a fixed cost per OPERATION (~50 cycles measured: three
+// operations per env capped the kernel at ~1.0 ms regardless of bytes), so operations are merged wherever
+// the bytes are contiguous: consecutive envs have contiguous rings and contiguous output windows.
+//   * per group, lane 0 issues onto the stage's mbarrier: G cp.async.bulk window loads (one per env, from
+//     the L2-resident window table) and ONE cp.async.bulk for the G rings (G*W*8 contiguous bytes, HBM);
+//   * when the barrier flips, lanes patch the dynamic columns smem->smem (rows before the episode start
+//     stay zero), fence.proxy.async once, and lane 0 issues ONE cp.async.bulk shared->global for the G
+//     finished windows (G*W*F*4 contiguous bytes);
+//   * STAGES group buffers per warp: the group being finished, DEPTH = STAGES-2 groups loading ahead, one
+//     store draining.  No register-staged global loads in the loop: a warp works through 32 CONSECUTIVE
+//     envs, whose (ep_start, step, dataset) words are fetched with one coalesced load per array a whole
+//     32-env block ahead and turned into addresses / ring slots once per env by the owning lane.
+template <int STAGES, int WARPS, int G>
 __global__ void __launch_bounds__(WARPS * 32)
 obs_tma_kernel(const GteParams P, const GteData D, const GteState S, float* __restrict__ obs,
-               const ObsShape sh, const int env_begin, const int env_end, const int hints) {
+               const ObsShape sh, const int env_begin, const int env_end) {
     constexpr int DEPTH = STAGES - 2;
-    const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
+    constexpr int GROUPS = 32 / G;                               // groups per 32-env block
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bars[WARPS][STAGES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* wbuf = smem_raw + (size_t)warp * STAGES * sh.win_bytes;
-    const int N = env_end;               // exclusive upper bound of this launch's env range
+    const uint32_t win_bytes = (uint32_t)sh.win_bytes;
+    const uint32_t ring_bytes = sh.nd > 0 ? (uint32_t)sh.W * 8u : 0u;
+    const uint32_t stage_bytes = (win_bytes + ring_bytes) * G;   // [G windows][G rings]
+    unsigned char* wbuf = smem_raw + (size_t)warp * STAGES * stage_bytes;
 
     if (lane == 0) {
 #pragma unroll
@@ -239,128 +222,144 @@ obs_tma_kernel(const GteParams P, const GteData D, const GteState S, float* __re
     __syncwarp();
 
     const int64_t n_warps = (int64_t)gridDim.x * WARPS;
-    const int64_t env0 = env_begin + (int64_t)blockIdx.x * WARPS + warp;
-
-    auto issue_load = [&](int64_t env, const EnvMeta& m, int stage) {   // lane 0 only
-        if (env < N) {
-            mbar_expect_tx(&bars[warp][stage], (uint32_t)sh.win_bytes);
-            const void* src = window_src(D, sh, m.ds, m.ep_start + m.step + 1 - sh.W);
-            if (hints & 2) bulk_g2s_hint(wbuf + (size_t)stage * sh.win_bytes, src, (uint32_t)sh.win_bytes, &bars[warp][stage], pol_last);
-            else bulk_g2s(wbuf + (size_t)stage * sh.win_bytes, src, (uint32_t)sh.win_bytes, &bars[warp][stage]);
+    const int64_t warp_global = (int64_t)blockIdx.x * WARPS + warp;
+    // first env of block k of this warp (blocks of 32 consecutive envs, strided over the grid)
+    auto block_env0 = [&](int k) -> int64_t { return env_begin + ((warp_global + (int64_t)k * n_warps) << 5); };
+    auto load_block = [&](int k) {
+        EnvPre p;
+        p.src = 0ull; p.r0 = 0; p.s0 = 0; p.ep_start = 0;
+        const int64_t env = block_env0(k) + lane;
+        if (env < env_end) {
+            const int ep = __ldg(S.ep_start + env), st = __ldg(S.step + env), ds = __ldg(S.dataset_idx + env);
+            p.ep_start = ep;
+            p.r0 = ep + st + 1 - sh.W;
+            p.s0 = sh.w_mask >= 0 ? (p.r0 & sh.w_mask) : (((p.r0 % sh.W) + sh.W) % sh.W);
+            p.src = (unsigned long long)window_src(D, sh, ds, p.r0);
         }
-    };
-    auto load_ring = [&](int64_t env, float2 (&d)[RPL]) {
-        const float2* __restrict__ ring = reinterpret_cast<const float2*>(S.dyn_ring) + env * sh.W;
-#pragma unroll
-        for (int q = 0; q < RPL; ++q) {
-            const int s = lane + 32 * q;
-            d[q] = make_float2(0.f, 0.f);
-            if (sh.nd > 0 && env < N && s < sh.W) d[q] = (hints & 4) ? ld_nc_v2_hint(ring + s, pol_first) : __ldg(ring + s);
-        }
+        return p;
     };
 
-    // mq[k] belongs to env + k*n_warps; mq[0..DEPTH] have their window load in flight.
-    EnvMeta mq[DEPTH + 2];
-#pragma unroll
-    for (int k = 0; k < DEPTH + 2; ++k) mq[k] = load_meta(S, env0 + (int64_t)k * n_warps, N);
-    EnvMeta m_pend = load_meta(S, env0 + (int64_t)(DEPTH + 2) * n_warps, N);
-    float2 d_cur[RPL], d_pend[RPL];
-    load_ring(env0, d_cur);
-    load_ring(env0 + n_warps, d_pend);
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k <= DEPTH; ++k) issue_load(env0 + (int64_t)k * n_warps, mq[k], k);
-    }
+    EnvPre pc = load_block(0), pn = load_block(1);               // current / next 32-env block (one env per lane)
 
-    int it = 0;
-    for (int64_t env = env0; env < N; env += n_warps, ++it) {
-        const int stage = it % STAGES;
-        const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
-        unsigned char* buf = wbuf + (size_t)stage * sh.win_bytes;
-        const EnvMeta m = mq[0];
-        const int r0 = m.ep_start + m.step + 1 - sh.W;
-        const int s0 = ((r0 % sh.W) + sh.W) % sh.W;
-
-        mbar_wait(&bars[warp][stage], parity);           // window (static cols + zero dyn cols) has landed
-
-        if (sh.nd > 0) {
-            float* fbuf = reinterpret_cast<float*>(buf);
+    // all lanes call (shuffles); lane 0 issues the loads of group gi of block ki; cur_k = block of pc
+    auto issue = [&](int ki, int gi, int cur_k, int stage) {
+        const int64_t env0 = block_env0(ki) + gi * G;
+        const int64_t left = (int64_t)env_end - env0;
+        const int n_valid = left >= G ? G : (left > 0 ? (int)left : 0);
+        unsigned char* sbuf = wbuf + (size_t)stage * stage_bytes;
+        uint64_t* bar = &bars[warp][stage];
+        if (lane == 0 && n_valid > 0) {
+            mbar_expect_tx(bar, (uint32_t)n_valid * (win_bytes + ring_bytes));
+            if (ring_bytes)                                       // the G rings are contiguous: one operation
+                bulk_g2s(sbuf + (size_t)G * win_bytes, S.dyn_ring + env0 * (int64_t)sh.W * 2,
+                         (uint32_t)n_valid * ring_bytes, bar);
+        }
 #pragma unroll
-            for (int q = 0; q < RPL; ++q) {
-                const int s = lane + 32 * q;
-                int w = s - s0;
-                if (w < 0) w += sh.W;
-                if (s < sh.W && r0 + w >= m.ep_start) {
-                    float* qd = fbuf + w * sh.F + sh.ns;
-                    qd[0] = d_cur[q].x;
-                    if (sh.nd > 1) qd[1] = d_cur[q].y;
+        for (int g = 0; g < G; ++g) {
+            const unsigned long long src = __shfl_sync(FULL, ki != cur_k ? pn.src : pc.src, gi * G + g);
+            if (lane == 0 && g < n_valid) bulk_g2s(sbuf + (size_t)g * win_bytes, reinterpret_cast<const void*>(src), win_bytes, bar);
+        }
+    };
+
+#pragma unroll
+    for (int q0 = 0; q0 <= DEPTH; ++q0) issue(q0 / GROUPS, q0 % GROUPS, 0, q0);
+
+    int q = 0;                                                   // groups finished by this warp so far
+    for (int k = 0; block_env0(k) < env_end; ++k) {
+        const int64_t env_k = block_env0(k);
+        for (int gi = 0; gi < GROUPS; ++gi, ++q) {
+            const int64_t env0 = env_k + gi * G;
+            const int64_t left = (int64_t)env_end - env0;
+            if (left <= 0) break;                                // ragged tail of the last block (warp-uniform)
+            const int n_valid = left >= G ? G : (int)left;
+            const int stage = q % STAGES;
+            const uint32_t parity = (uint32_t)(q / STAGES) & 1u;
+            unsigned char* sbuf = wbuf + (size_t)stage * stage_bytes;
+
+            mbar_wait(&bars[warp][stage], parity);               // the group's windows + rings have landed
+
+            if (ring_bytes) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const int r0 = __shfl_sync(FULL, pc.r0, gi * G + g);
+                    const int s0 = __shfl_sync(FULL, pc.s0, gi * G + g);
+                    const int ep_start = __shfl_sync(FULL, pc.ep_start, gi * G + g);
+                    if (g < n_valid) {
+                        float* fbuf = reinterpret_cast<float*>(sbuf + (size_t)g * win_bytes);
+                        const float2* rbuf = reinterpret_cast<const float2*>(sbuf + (size_t)G * win_bytes + (size_t)g * ring_bytes);
+                        for (int s = lane; s < sh.W; s += 32) {
+                            int w = s - s0;
+                            if (w < 0) w += sh.W;
+                            if (r0 + w >= ep_start) {            // rows before the episode start stay zero
+                                const float2 d = rbuf[s];
+                                float* qd = fbuf + w * sh.F + sh.ns;
+                                qd[0] = d.x;
+                                qd[1] = d.y;
+                            }
+                        }
+                    }
                 }
+                fence_proxy_async();                             // generic-proxy smem writes -> visible to TMA
             }
-            fence_proxy_async();                          // generic-proxy smem writes -> visible to TMA
+            __syncwarp();
+            if (lane == 0) {
+                // the G finished windows are contiguous in smem and in the output: one operation
+                bulk_s2g(reinterpret_cast<char*>(obs) + env0 * (int64_t)win_bytes, sbuf, (uint32_t)n_valid * win_bytes);
+                bulk_commit();
+                // the stage refilled below is the one whose store was committed in the PREVIOUS iteration:
+                // allow only the store just committed to be still reading shared memory
+                bulk_wait_read<1>();
+            }
+            __syncwarp();
+            const int qi = gi + DEPTH + 1;                       // group to start loading now
+            issue(k + qi / GROUPS, qi % GROUPS, k, (q + DEPTH + 1) % STAGES);
         }
-        __syncwarp();
-        if (lane == 0) {
-            char* dst = reinterpret_cast<char*>(obs) + env * (int64_t)sh.win_bytes;
-            if (hints & 1) bulk_s2g_hint(dst, buf, (uint32_t)sh.win_bytes, pol_first);
-            else bulk_s2g(dst, buf, (uint32_t)sh.win_bytes);
-            bulk_commit();
-            // refill the buffer whose store was committed in the PREVIOUS iteration: allow only the
-            // store just committed to be still reading shared memory.
-            bulk_wait_read<1>();
-            issue_load(env + (int64_t)(DEPTH + 1) * n_warps, mq[DEPTH + 1], (it + DEPTH + 1) % STAGES);
-        }
-        // rotate: consume the prefetches issued one iteration ago, then issue the next ones
-#pragma unroll
-        for (int k = 0; k < DEPTH + 1; ++k) mq[k] = mq[k + 1];
-        mq[DEPTH + 1] = m_pend;
-        m_pend = load_meta(S, env + (int64_t)(DEPTH + 3) * n_warps, N);
-#pragma unroll
-        for (int q = 0; q < RPL; ++q) d_cur[q] = d_pend[q];
-        load_ring(env + 2 * n_warps, d_pend);
+        pc = pn;                                                 // loaded a whole block ago: no stall
+        pn = load_block(k + 2);
     }
-    if (lane == 0) bulk_wait_read<0>();                   // smem must outlive the last store's reads
+    if (lane == 0) bulk_wait_read<0>();                          // smem must outlive the last store's reads
 }
 
-using ObsKernelFn = void (*)(const GteParams, const GteData, const GteState, float*, const ObsShape, int, int, int);
+using ObsKernelFn = void (*)(const GteParams, const GteData, const GteState, float*, const ObsShape, int, int);
 
-template <int STAGES, int WARPS>
-static ObsKernelFn tma_kernel_for(int rpl) {
-    return rpl <= 1 ? obs_tma_kernel<1, STAGES, WARPS>
-                    : (rpl <= 2 ? obs_tma_kernel<2, STAGES, WARPS> : obs_tma_kernel<4, STAGES, WARPS>);
-}
+struct TmaConfig { int stages, warps, group; };
 
-struct TmaConfig { int stages, warps; };
-
-// default pipeline shape; GTE_TMA_STAGES / GTE_TMA_WARPS override it for tuning runs
+// default pipeline shape; GTE_TMA_STAGES / GTE_TMA_WARPS / GTE_TMA_GROUP override it for tuning runs
 static TmaConfig tma_config() {
     static TmaConfig cfg = [] {
-        TmaConfig c{3, 8};
+        TmaConfig c{3, 2, 4};
         if (const char* e = getenv("GTE_TMA_STAGES")) c.stages = atoi(e);
         if (const char* e = getenv("GTE_TMA_WARPS")) c.warps = atoi(e);
-        if (c.stages < 2 || c.stages > 6) c.stages = 3;
-        if (c.warps != 4 && c.warps != 8) c.warps = 8;
+        if (const char* e = getenv("GTE_TMA_GROUP")) c.group = atoi(e);
+        if (c.stages != 3 && c.stages != 4 && c.stages != 6) c.stages = 3;
+        if (c.warps != 1 && c.warps != 2 && c.warps != 4 && c.warps != 8) c.warps = 2;
+        if (c.group != 1 && c.group != 2 && c.group != 4 && c.group != 8) c.group = 4;
         return c;
     }();
     return cfg;
 }
 
-static ObsKernelFn tma_kernel(const TmaConfig& c, int rpl) {
-    if (c.warps == 4) {
-        switch (c.stages) {
-            case 2: return tma_kernel_for<2, 4>(rpl);
-            case 3: return tma_kernel_for<3, 4>(rpl);
-            case 5: return tma_kernel_for<5, 4>(rpl);
-            case 6: return tma_kernel_for<6, 4>(rpl);
-            default: return tma_kernel_for<4, 4>(rpl);
-        }
+template <int STAGES, int WARPS>
+static ObsKernelFn tma_kernel_g(int g) {
+    switch (g) {
+        case 1: return obs_tma_kernel<STAGES, WARPS, 1>;
+        case 2: return obs_tma_kernel<STAGES, WARPS, 2>;
+        case 8: return obs_tma_kernel<STAGES, WARPS, 8>;
+        default: return obs_tma_kernel<STAGES, WARPS, 4>;
     }
-    switch (c.stages) {
-        case 2: return tma_kernel_for<2, 8>(rpl);
-        case 3: return tma_kernel_for<3, 8>(rpl);
-        case 5: return tma_kernel_for<5, 8>(rpl);
-        case 6: return tma_kernel_for<6, 8>(rpl);
-        default: return tma_kernel_for<4, 8>(rpl);
+}
+template <int STAGES>
+static ObsKernelFn tma_kernel_w(int w, int g) {
+    switch (w) {
+        case 1: return tma_kernel_g<STAGES, 1>(g);
+        case 4: return tma_kernel_g<STAGES, 4>(g);
+        case 8: return tma_kernel_g<STAGES, 8>(g);
+        default: return tma_kernel_g<STAGES, 2>(g);
     }
+}
+static ObsKernelFn tma_kernel(const TmaConfig& c) {
+    return c.stages == 3 ? tma_kernel_w<3>(c.warps, c.group)
+                         : (c.stages == 4 ? tma_kernel_w<4>(c.warps, c.group) : tma_kernel_w<6>(c.warps, c.group));
 }
 
 // ------------------------------------------------------------------------------------------ launch
@@ -377,13 +376,14 @@ bool obs_vec_supported(const GteParams& P, const GteData& D) {
 
 static size_t tma_smem_bytes(const ObsShape& sh) {
     const TmaConfig c = tma_config();
-    return (size_t)c.warps * c.stages * sh.win_bytes;
+    return (size_t)c.warps * c.stages * c.group * ((size_t)sh.win_bytes + (sh.nd > 0 ? (size_t)sh.W * 8 : 0));
 }
 
 bool obs_tma_supported(const GteParams& P, const GteData& D) {
     if (!obs_vec_supported(P, D)) return false;
     const ObsShape sh = make_shape(P);
-    return sh.W <= 128 && tma_smem_bytes(sh) <= 200 * 1024;
+    // the ring of one env (W*8 bytes) must itself be a 16-byte multiple for cp.async.bulk
+    return (sh.nd == 0 || (sh.W * 8) % 16 == 0) && (sh.nd == 0 || sh.nd == 2) && tma_smem_bytes(sh) <= 200 * 1024;
 }
 
 cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteState& S, float* obs, int variant,
@@ -422,7 +422,7 @@ cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteStat
         if (!obs_tma_supported(P, D)) return cudaErrorInvalidValue;
         const size_t smem = tma_smem_bytes(sh);
         const TmaConfig cfg = tma_config();
-        ObsKernelFn kern = tma_kernel(cfg, (sh.W + 31) / 32);
+        ObsKernelFn kern = tma_kernel(cfg);
         static ObsKernelFn configured_kern = nullptr;      // opt-in to > 48 KB dynamic smem once per kernel
         static size_t configured_smem = 0;
         if (kern != configured_kern || smem > configured_smem) {
@@ -434,10 +434,10 @@ cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteStat
         int per_sm = (int)((227 * 1024) / (smem + 1024 + 8 * cfg.warps * cfg.stages));
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 2048 / (cfg.warps * 32)) per_sm = 2048 / (cfg.warps * 32);
-        const int64_t need = ((int64_t)n_envs + cfg.warps - 1) / cfg.warps;
+        if (per_sm > 32) per_sm = 32;
+        const int64_t need = (((int64_t)n_envs + 31) / 32 + cfg.warps - 1) / cfg.warps;   // one 32-env block per warp at least
         const int grid = (int)(need < (int64_t)sms * per_sm ? need : (int64_t)sms * per_sm);
-        static const int hints = [] { const char* e = getenv("GTE_TMA_HINTS"); return e ? atoi(e) : 0; }();
-        kern<<<grid, cfg.warps * 32, smem, stream>>>(P, D, S, obs, sh, env_begin, env_end, hints);
+        kern<<<grid, cfg.warps * 32, smem, stream>>>(P, D, S, obs, sh, env_begin, env_end);
         return cudaGetLastError();
     }
     return cudaErrorInvalidValue;
