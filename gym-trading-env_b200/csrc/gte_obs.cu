@@ -186,108 +186,146 @@ struct EnvPre {
     int ep_start;                // rows before it read as zero
 };
 
-// One warp per GROUP of G consecutive envs per pipeline stage, everything bulky moved by the TMA engine.
-// The TMA unit of an SM serves bulk operations at a fixed cost per OPERATION (~50 cycles measured: three
-// operations per env capped the kernel at ~1.0 ms regardless of bytes), so operations are merged wherever
-// the bytes are contiguous: consecutive envs have contiguous rings and contiguous output windows.
-//   * per group, lane 0 issues onto the stage's mbarrier: G cp.async.bulk window loads (one per env, from
-//     the L2-resident window table) and ONE cp.async.bulk for the G rings (G*W*8 contiguous bytes, HBM);
-//   * when the barrier flips, lanes patch the dynamic columns smem->smem (rows before the episode start
-//     stay zero), fence.proxy.async once, and lane 0 issues ONE cp.async.bulk shared->global for the G
-//     finished windows (G*W*F*4 contiguous bytes);
-//   * STAGES group buffers per warp: the group being finished, DEPTH = STAGES-2 groups loading ahead, one
-//     store draining.  No register-staged global loads in the loop: a warp works through 32 CONSECUTIVE
-//     envs, whose (ep_start, step, dataset) words are fetched with one coalesced load per array a whole
-//     32-env block ahead and turned into addresses / ring slots once per env by the owning lane.
-template <int STAGES, int WARPS, int G>
-__global__ void __launch_bounds__(WARPS * 32)
-obs_tma_kernel(const GteParams P, const GteData D, const GteState S, float* __restrict__ obs,
-               const ObsShape sh, const int env_begin, const int env_end) {
-    constexpr int DEPTH = STAGES - 2;
-    constexpr int GROUPS = 32 / G;                               // groups per 32-env block
+// ---- TMA gather: warp-specialised producer / consumer pipeline -----------------------------------------
+// One CTA = 4 consumer warps + 1 producer warp working on ONE pipeline of groups of G consecutive envs
+// (a 32-env tile = 32/G groups; tiles strided over the grid):
+//   producer warp : owns the metadata of the next 32-env tile (one env per lane, one coalesced load per
+//                   array a whole tile ahead), turns it ONCE per env into the window address / ring slot,
+//                   waits for a free stage (empty mbarrier), publishes (r0, s0, ep_start) to shared memory
+//                   and issues the group's TMA loads: G cp.async.bulk window copies from the L2-resident
+//                   window table onto the window stage's full mbarrier, and ONE cp.async.bulk for the G
+//                   contiguous rings (HBM) onto the ring stage's full mbarrier;
+//   consumer warps: wait on both full mbarriers, patch the dynamic columns smem->smem with a thread-per-row
+//                   mapping (128 threads = G envs x 128/G threads; rows before the episode start stay
+//                   zero), fence.proxy.async, meet on a named barrier; one thread then hands the ring stage
+//                   back, issues the SINGLE bulk store of the G contiguous windows and, once the PREVIOUS
+//                   group's store has finished reading shared memory, hands that window stage back.
+// Evidence for this shape is in profiles/r01_tuning.md (per-warp pipelines were bound by the instruction
+// chain of too few resident warps; consumers of a unified pipeline mostly waited on the HBM ring loads).
+constexpr int kCoopConsumerWarps = 4;
+constexpr int kCoopThreads = (kCoopConsumerWarps + 1) * 32;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_barrier() {
+    asm volatile("bar.sync 1, %0;" :: "n"(kCoopConsumerWarps * 32) : "memory");
+}
+
+// WS window stages and RS >= WS ring stages per CTA, G envs per stage.  The rings come from HBM (slow under a
+// saturating write stream) and only need the env index, the windows come from L2 and need the env's
+// metadata: the ring pipeline runs RS-WS groups further ahead, so the big window buffers are only held
+// for an L2 round trip + patch + store drain.
+template <int WS, int RS, int G>
+__global__ void __launch_bounds__(kCoopThreads)
+obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float* __restrict__ obs,
+                    const ObsShape sh, const int env_begin, const int env_end) {
+    static_assert(RS >= WS, "the ring pipeline is at least as deep as the window pipeline");
+    constexpr int GROUPS = 32 / G;                               // groups per 32-env tile
+    constexpr int NCONS = kCoopConsumerWarps * 32;
+    constexpr int TPE = NCONS / G;                               // consumer threads per env
+    constexpr int LEAD = RS - WS;                                // extra groups the ring loads run ahead
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bars[WARPS][STAGES];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ __align__(8) uint64_t full_w[WS], empty_w[WS], full_r[RS], empty_r[RS];
+    __shared__ int4 meta[2][32];                                 // per tile parity: {r0, s0, ep_start, -}
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t win_bytes = (uint32_t)sh.win_bytes;
     const uint32_t ring_bytes = sh.nd > 0 ? (uint32_t)sh.W * 8u : 0u;
-    const uint32_t stage_bytes = (win_bytes + ring_bytes) * G;   // [G windows][G rings]
-    unsigned char* wbuf = smem_raw + (size_t)warp * STAGES * stage_bytes;
+    const uint32_t wstage_bytes = win_bytes * G, rstage_bytes = ring_bytes * G;
+    unsigned char* wbase = smem_raw;
+    unsigned char* rbase = smem_raw + (size_t)WS * wstage_bytes;
 
-    if (lane == 0) {
+    if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[warp][s], 1);
+        for (int s = 0; s < WS; ++s) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], 1); }
+#pragma unroll
+        for (int s = 0; s < RS; ++s) { mbar_init(&full_r[s], 1); mbar_init(&empty_r[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
+    __syncthreads();
 
-    const int64_t n_warps = (int64_t)gridDim.x * WARPS;
-    const int64_t warp_global = (int64_t)blockIdx.x * WARPS + warp;
-    // first env of block k of this warp (blocks of 32 consecutive envs, strided over the grid)
-    auto block_env0 = [&](int k) -> int64_t { return env_begin + ((warp_global + (int64_t)k * n_warps) << 5); };
-    auto load_block = [&](int k) {
-        EnvPre p;
-        p.src = 0ull; p.r0 = 0; p.s0 = 0; p.ep_start = 0;
-        const int64_t env = block_env0(k) + lane;
-        if (env < env_end) {
-            const int ep = __ldg(S.ep_start + env), st = __ldg(S.step + env), ds = __ldg(S.dataset_idx + env);
-            p.ep_start = ep;
-            p.r0 = ep + st + 1 - sh.W;
-            p.s0 = sh.w_mask >= 0 ? (p.r0 & sh.w_mask) : (((p.r0 % sh.W) + sh.W) % sh.W);
-            p.src = (unsigned long long)window_src(D, sh, ds, p.r0);
-        }
-        return p;
+    // tile k of this CTA = 32 consecutive envs, tiles strided over the grid; group q = (tile q/GROUPS, slot q%GROUPS)
+    auto tile_env0 = [&](int k) -> int64_t { return env_begin + (((int64_t)blockIdx.x + (int64_t)k * gridDim.x) << 5); };
+    auto group_env0 = [&](int q) -> int64_t { return tile_env0(q / GROUPS) + (q % GROUPS) * G; };
+    auto group_valid = [&](int q) -> int {                       // envs of group q inside [env_begin, env_end)
+        const int64_t left = (int64_t)env_end - group_env0(q);
+        return left >= G ? G : (left > 0 ? (int)left : 0);
     };
 
-    EnvPre pc = load_block(0), pn = load_block(1);               // current / next 32-env block (one env per lane)
-
-    // all lanes call (shuffles); lane 0 issues the loads of group gi of block ki; cur_k = block of pc
-    auto issue = [&](int ki, int gi, int cur_k, int stage) {
-        const int64_t env0 = block_env0(ki) + gi * G;
-        const int64_t left = (int64_t)env_end - env0;
-        const int n_valid = left >= G ? G : (left > 0 ? (int)left : 0);
-        unsigned char* sbuf = wbuf + (size_t)stage * stage_bytes;
-        uint64_t* bar = &bars[warp][stage];
-        if (lane == 0 && n_valid > 0) {
-            mbar_expect_tx(bar, (uint32_t)n_valid * (win_bytes + ring_bytes));
-            if (ring_bytes)                                       // the G rings are contiguous: one operation
-                bulk_g2s(sbuf + (size_t)G * win_bytes, S.dyn_ring + env0 * (int64_t)sh.W * 2,
-                         (uint32_t)n_valid * ring_bytes, bar);
-        }
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const unsigned long long src = __shfl_sync(FULL, ki != cur_k ? pn.src : pc.src, gi * G + g);
-            if (lane == 0 && g < n_valid) bulk_g2s(sbuf + (size_t)g * win_bytes, reinterpret_cast<const void*>(src), win_bytes, bar);
-        }
-    };
-
-#pragma unroll
-    for (int q0 = 0; q0 <= DEPTH; ++q0) issue(q0 / GROUPS, q0 % GROUPS, 0, q0);
-
-    int q = 0;                                                   // groups finished by this warp so far
-    for (int k = 0; block_env0(k) < env_end; ++k) {
-        const int64_t env_k = block_env0(k);
-        for (int gi = 0; gi < GROUPS; ++gi, ++q) {
-            const int64_t env0 = env_k + gi * G;
-            const int64_t left = (int64_t)env_end - env0;
-            if (left <= 0) break;                                // ragged tail of the last block (warp-uniform)
-            const int n_valid = left >= G ? G : (int)left;
-            const int stage = q % STAGES;
-            const uint32_t parity = (uint32_t)(q / STAGES) & 1u;
-            unsigned char* sbuf = wbuf + (size_t)stage * stage_bytes;
-
-            mbar_wait(&bars[warp][stage], parity);               // the group's windows + rings have landed
-
-            if (ring_bytes) {
+    if (warp == kCoopConsumerWarps) {
+        // ------------------------------------------------------------------ producer warp
+        auto load_tile = [&](int k) {
+            EnvPre p;
+            p.src = 0ull; p.r0 = 0; p.s0 = 0; p.ep_start = 0;
+            const int64_t env = tile_env0(k) + lane;
+            if (env < env_end) {
+                const int ep = __ldg(S.ep_start + env), st = __ldg(S.step + env), ds = __ldg(S.dataset_idx + env);
+                p.ep_start = ep;
+                p.r0 = ep + st + 1 - sh.W;
+                p.s0 = sh.w_mask >= 0 ? (p.r0 & sh.w_mask) : (((p.r0 % sh.W) + sh.W) % sh.W);
+                p.src = (unsigned long long)window_src(D, sh, ds, p.r0);
+            }
+            return p;
+        };
+        auto issue_ring = [&](int qr) {                          // lane 0; needs nothing but the env index
+            const int nv = group_valid(qr);
+            if (nv > 0 && ring_bytes) {
+                const int stage = qr % RS, use = qr / RS;
+                if (use > 0) mbar_wait(&empty_r[stage], (uint32_t)(use - 1) & 1u);
+                mbar_expect_tx(&full_r[stage], (uint32_t)nv * ring_bytes);
+                bulk_g2s(rbase + (size_t)stage * rstage_bytes, S.dyn_ring + group_env0(qr) * (int64_t)sh.W * 2,
+                         (uint32_t)nv * ring_bytes, &full_r[stage]);
+            }
+        };
+        EnvPre pc = load_tile(0), pn = load_tile(1);
+        if (lane == 0)
+            for (int qr = 0; qr < LEAD; ++qr) issue_ring(qr);
+        int q = 0;
+        for (int k = 0; tile_env0(k) < env_end; ++k) {
+            for (int gi = 0; gi < GROUPS; ++gi, ++q) {
+                const int n_valid = group_valid(q);
+                if (n_valid == 0) break;
+                if (lane == 0) issue_ring(q + LEAD);
+                __syncwarp();
+                const int stage = q % WS, use = q / WS;
+                if (use > 0) mbar_wait(&empty_w[stage], (uint32_t)(use - 1) & 1u);     // stage handed back
+                if (gi == 0) {                                   // after the wait: tile k-2 is fully consumed
+                    meta[k & 1][lane] = make_int4(pc.r0, pc.s0, pc.ep_start, 0);
+                    __syncwarp();
+                }
+                unsigned char* sbuf = wbase + (size_t)stage * wstage_bytes;
+                if (lane == 0) mbar_expect_tx(&full_w[stage], (uint32_t)n_valid * win_bytes);   // release: publishes meta
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const int r0 = __shfl_sync(FULL, pc.r0, gi * G + g);
-                    const int s0 = __shfl_sync(FULL, pc.s0, gi * G + g);
-                    const int ep_start = __shfl_sync(FULL, pc.ep_start, gi * G + g);
+                    const unsigned long long src = __shfl_sync(FULL, pc.src, gi * G + g);
+                    if (lane == 0 && g < n_valid)
+                        bulk_g2s(sbuf + (size_t)g * win_bytes, reinterpret_cast<const void*>(src), win_bytes, &full_w[stage]);
+                }
+            }
+            pc = pn;
+            pn = load_tile(k + 2);
+        }
+    } else {
+        // ------------------------------------------------------------------ consumer warps
+        const int g = tid / TPE, t = tid % TPE;
+        int q = 0;
+        for (int k = 0; tile_env0(k) < env_end; ++k) {
+            for (int gi = 0; gi < GROUPS; ++gi, ++q) {
+                const int n_valid = group_valid(q);
+                if (n_valid == 0) break;
+                const int64_t env0 = group_env0(q);
+                const int ws = q % WS, rs = q % RS;
+                unsigned char* sbuf = wbase + (size_t)ws * wstage_bytes;
+                mbar_wait(&full_w[ws], (uint32_t)(q / WS) & 1u);             // windows landed (acquire: meta too)
+                if (ring_bytes) {
+                    mbar_wait(&full_r[rs], (uint32_t)(q / RS) & 1u);         // rings landed
                     if (g < n_valid) {
+                        const int4 m = meta[k & 1][gi * G + g];
+                        const int r0 = m.x, s0 = m.y, ep_start = m.z;
                         float* fbuf = reinterpret_cast<float*>(sbuf + (size_t)g * win_bytes);
-                        const float2* rbuf = reinterpret_cast<const float2*>(sbuf + (size_t)G * win_bytes + (size_t)g * ring_bytes);
-                        for (int s = lane; s < sh.W; s += 32) {
+                        const float2* rbuf = reinterpret_cast<const float2*>(rbase + (size_t)rs * rstage_bytes + (size_t)g * ring_bytes);
+                        for (int s = t; s < sh.W; s += TPE) {
                             int w = s - s0;
                             if (w < 0) w += sh.W;
                             if (r0 + w >= ep_start) {            // rows before the episode start stay zero
@@ -298,68 +336,61 @@ obs_tma_kernel(const GteParams P, const GteData D, const GteState S, float* __re
                             }
                         }
                     }
+                    fence_proxy_async();                         // generic-proxy smem writes -> visible to TMA
                 }
-                fence_proxy_async();                             // generic-proxy smem writes -> visible to TMA
+                consumer_barrier();
+                if (tid == 0) {
+                    if (ring_bytes) mbar_arrive(&empty_r[rs]);   // the rings of this group are consumed
+                    bulk_s2g(reinterpret_cast<char*>(obs) + env0 * (int64_t)win_bytes, sbuf, (uint32_t)n_valid * win_bytes);
+                    bulk_commit();
+                    if (q > 0) {
+                        bulk_wait_read<1>();                     // the previous group's store has left smem
+                        mbar_arrive(&empty_w[(q - 1) % WS]);
+                    }
+                }
             }
-            __syncwarp();
-            if (lane == 0) {
-                // the G finished windows are contiguous in smem and in the output: one operation
-                bulk_s2g(reinterpret_cast<char*>(obs) + env0 * (int64_t)win_bytes, sbuf, (uint32_t)n_valid * win_bytes);
-                bulk_commit();
-                // the stage refilled below is the one whose store was committed in the PREVIOUS iteration:
-                // allow only the store just committed to be still reading shared memory
-                bulk_wait_read<1>();
-            }
-            __syncwarp();
-            const int qi = gi + DEPTH + 1;                       // group to start loading now
-            issue(k + qi / GROUPS, qi % GROUPS, k, (q + DEPTH + 1) % STAGES);
         }
-        pc = pn;                                                 // loaded a whole block ago: no stall
-        pn = load_block(k + 2);
+        if (tid == 0) bulk_wait_read<0>();                       // smem must outlive the last store's reads
     }
-    if (lane == 0) bulk_wait_read<0>();                          // smem must outlive the last store's reads
 }
 
 using ObsKernelFn = void (*)(const GteParams, const GteData, const GteState, float*, const ObsShape, int, int);
 
-struct TmaConfig { int stages, warps, group; };
+struct TmaConfig { int wstages, rstages, group; };
 
-// default pipeline shape; GTE_TMA_STAGES / GTE_TMA_WARPS / GTE_TMA_GROUP override it for tuning runs
-static TmaConfig tma_config() {
-    static TmaConfig cfg = [] {
-        TmaConfig c{3, 2, 4};
-        if (const char* e = getenv("GTE_TMA_STAGES")) c.stages = atoi(e);
-        if (const char* e = getenv("GTE_TMA_WARPS")) c.warps = atoi(e);
-        if (const char* e = getenv("GTE_TMA_GROUP")) c.group = atoi(e);
-        if (c.stages != 3 && c.stages != 4 && c.stages != 6) c.stages = 3;
-        if (c.warps != 1 && c.warps != 2 && c.warps != 4 && c.warps != 8) c.warps = 2;
-        if (c.group != 1 && c.group != 2 && c.group != 4 && c.group != 8) c.group = 4;
-        return c;
-    }();
-    return cfg;
+static size_t tma_smem_bytes(const ObsShape& sh, const TmaConfig& c) {
+    const size_t ring = sh.nd > 0 ? (size_t)sh.W * 8 : 0;
+    return (size_t)c.group * ((size_t)c.wstages * sh.win_bytes + (size_t)c.rstages * ring);
 }
 
-template <int STAGES, int WARPS>
-static ObsKernelFn tma_kernel_g(int g) {
-    switch (g) {
-        case 1: return obs_tma_kernel<STAGES, WARPS, 1>;
-        case 2: return obs_tma_kernel<STAGES, WARPS, 2>;
-        case 8: return obs_tma_kernel<STAGES, WARPS, 8>;
-        default: return obs_tma_kernel<STAGES, WARPS, 4>;
-    }
-}
-template <int STAGES>
-static ObsKernelFn tma_kernel_w(int w, int g) {
-    switch (w) {
-        case 1: return tma_kernel_g<STAGES, 1>(g);
-        case 4: return tma_kernel_g<STAGES, 4>(g);
-        case 8: return tma_kernel_g<STAGES, 8>(g);
-        default: return tma_kernel_g<STAGES, 2>(g);
-    }
-}
 static ObsKernelFn tma_kernel(const TmaConfig& c) {
-    return c.stages == 3 ? tma_kernel_w<3>(c.warps, c.group)
-                         : (c.stages == 4 ? tma_kernel_w<4>(c.warps, c.group) : tma_kernel_w<6>(c.warps, c.group));
+    // (window stages, ring stages, envs per group) combinations compiled in
+    switch (c.wstages * 10000 + c.rstages * 100 + c.group) {
+        case 31201: return obs_tma_coop_kernel<3, 12, 1>;
+        case 31202: return obs_tma_coop_kernel<3, 12, 2>;
+        case 31204: return obs_tma_coop_kernel<3, 12, 4>;
+        case 41204: return obs_tma_coop_kernel<4, 12, 4>;
+        case 40404: return obs_tma_coop_kernel<4, 4, 4>;
+        case 30808: return obs_tma_coop_kernel<3, 8, 8>;
+        case 20608: return obs_tma_coop_kernel<2, 6, 8>;
+        case 40408: return obs_tma_coop_kernel<4, 4, 8>;
+        default: return nullptr;
+    }
+}
+
+// Pipeline shape: 3 window stages + 12 ring stages of the largest group (4, 2, 1 envs) that still leaves
+// two CTAs per SM; GTE_TMA_STAGES / GTE_TMA_RSTAGES / GTE_TMA_GROUP override it for tuning runs.
+static TmaConfig tma_config(const ObsShape& sh) {
+    static const int ws = [] { const char* e = getenv("GTE_TMA_STAGES"); return e ? atoi(e) : 0; }();
+    static const int rs = [] { const char* e = getenv("GTE_TMA_RSTAGES"); return e ? atoi(e) : 0; }();
+    static const int g = [] { const char* e = getenv("GTE_TMA_GROUP"); return e ? atoi(e) : 0; }();
+    if (ws > 0 && rs > 0 && g > 0) {
+        const TmaConfig c{ws, rs, g};
+        if (tma_kernel(c) != nullptr) return c;
+    }
+    TmaConfig c{3, 12, 4};
+    while (c.group > 1 && tma_smem_bytes(sh, c) > 100 * 1024) c.group /= 2;
+    return c;
 }
 
 // ------------------------------------------------------------------------------------------ launch
@@ -374,16 +405,12 @@ bool obs_vec_supported(const GteParams& P, const GteData& D) {
     return D.window_table_ds_stride % 16 == 0;
 }
 
-static size_t tma_smem_bytes(const ObsShape& sh) {
-    const TmaConfig c = tma_config();
-    return (size_t)c.warps * c.stages * c.group * ((size_t)sh.win_bytes + (sh.nd > 0 ? (size_t)sh.W * 8 : 0));
-}
-
 bool obs_tma_supported(const GteParams& P, const GteData& D) {
     if (!obs_vec_supported(P, D)) return false;
     const ObsShape sh = make_shape(P);
     // the ring of one env (W*8 bytes) must itself be a 16-byte multiple for cp.async.bulk
-    return (sh.nd == 0 || (sh.W * 8) % 16 == 0) && (sh.nd == 0 || sh.nd == 2) && tma_smem_bytes(sh) <= 200 * 1024;
+    return (sh.nd == 0 || (sh.W * 8) % 16 == 0) && (sh.nd == 0 || sh.nd == 2) &&
+           tma_smem_bytes(sh, tma_config(sh)) <= 200 * 1024;
 }
 
 cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteState& S, float* obs, int variant,
@@ -420,9 +447,11 @@ cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteStat
     }
     if (variant == GTE_OBS_TMA) {
         if (!obs_tma_supported(P, D)) return cudaErrorInvalidValue;
-        const size_t smem = tma_smem_bytes(sh);
-        const TmaConfig cfg = tma_config();
+        const TmaConfig cfg = tma_config(sh);
+        const size_t smem = tma_smem_bytes(sh, cfg);
         ObsKernelFn kern = tma_kernel(cfg);
+        if (kern == nullptr) return cudaErrorInvalidValue;
+        const int threads = kCoopThreads;
         static ObsKernelFn configured_kern = nullptr;      // opt-in to > 48 KB dynamic smem once per kernel
         static size_t configured_smem = 0;
         if (kern != configured_kern || smem > configured_smem) {
@@ -431,13 +460,13 @@ cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteStat
             configured_kern = kern;
             configured_smem = smem;
         }
-        int per_sm = (int)((227 * 1024) / (smem + 1024 + 8 * cfg.warps * cfg.stages));
+        int per_sm = (int)((227 * 1024) / (smem + 2048));
         if (per_sm < 1) per_sm = 1;
-        if (per_sm > 2048 / (cfg.warps * 32)) per_sm = 2048 / (cfg.warps * 32);
+        if (per_sm > 2048 / threads) per_sm = 2048 / threads;
         if (per_sm > 32) per_sm = 32;
-        const int64_t need = (((int64_t)n_envs + 31) / 32 + cfg.warps - 1) / cfg.warps;   // one 32-env block per warp at least
+        const int64_t need = ((int64_t)n_envs + 31) / 32;          // work unit = one 32-env tile per CTA
         const int grid = (int)(need < (int64_t)sms * per_sm ? need : (int64_t)sms * per_sm);
-        kern<<<grid, cfg.warps * 32, smem, stream>>>(P, D, S, obs, sh, env_begin, env_end);
+        kern<<<grid, threads, smem, stream>>>(P, D, S, obs, sh, env_begin, env_end);
         return cudaGetLastError();
     }
     return cudaErrorInvalidValue;
