@@ -14,7 +14,7 @@ _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_CSRC, "libgte_b200.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_PKG), "include")
 SOURCES = ["gte_step.cu", "gte_obs.cu", "gte_cabi.cu"]
-HEADERS = ["gte_device.cuh", "gte_launch.h", os.path.join(INCLUDE_DIR, "gte_b200.h")]
+HEADERS = ["gte_device.cuh", "gte_step_env.cuh", "gte_tma.cuh", "gte_launch.h", os.path.join(INCLUDE_DIR, "gte_b200.h")]
 
 GTE_MAX_POSITIONS = 64
 GTE_MAX_DATASETS = 64

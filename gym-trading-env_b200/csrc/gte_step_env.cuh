@@ -1,0 +1,188 @@
+// gte_step_env.cuh — the transition of ONE env (TradingEnv.step, environments.py:233-272, line by line) and the
+// deterministic metric reduction, used by the step kernel (gte_step.cu).
+#pragma once
+
+#include "gte_device.cuh"
+
+namespace gte {
+
+constexpr int kChunkFirst = 1, kChunkLast = 2;
+
+struct StepThreadOut {       // what the gather phase of the fused kernel needs from the step phase
+    int idx, ep_start, ds;   // post-reset row index, episode start, dataset
+    float dyn_pos, dyn_rp;   // the dynamic features of row idx (position, real_position), as written to the ring
+};
+
+struct MetricAcc {           // per-thread accumulators (deterministic: fixed tile order per thread)
+    double sum_pr = 0.0, sum_mr = 0.0, sum_rew = 0.0;
+    int episodes = 0, terminated = 0, truncated = 0, sum_len = 0;
+};
+
+// The transition of ONE env (the reference's step(), line by line).
+__device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteData& D, const GteState& S,
+                                                  const int64_t* __restrict__ actions,
+                                                  const GteStepOut& O, uint64_t tick, int autoreset,
+                                                  int i, MetricAcc& acc) {
+    EnvRegs e;
+    e.pf.asset = S.asset[i];
+    e.pf.fiat = S.fiat[i];
+    e.pf.ia = S.interest_asset[i];
+    e.pf.ifi = S.interest_fiat[i];
+    e.pos_idx = S.pos_idx[i];
+    e.step = S.step[i];
+    e.ep_start = S.ep_start[i];
+    e.ds = (P.n_datasets > 1) ? S.dataset_idx[i] : 0;
+    int64_t a = actions[i];
+
+    const double* __restrict__ price = D.price + (int64_t)e.ds * P.t_stride;
+    const int T = D.lengths[e.ds];
+    int idx = e.ep_start + e.step;
+    if (idx + 1 >= T) {              // stepping past the end of the data without a reset (caller bug)
+        atomicOr(S.error_flag, 2);
+        idx = T - 2;
+    }
+    if (a >= (int64_t)P.n_positions) { atomicOr(S.error_flag, 1); a = -1; }
+
+    const double p0 = __ldg(price + idx);                                    // price BEFORE advancing (:204-207)
+    const double p1 = __ldg(price + idx + 1);
+    // history["portfolio_valuation", -2]: the previous row's valuation.  The state on entry is exactly
+    // the state that row was valued with, at the same price, so it is recomputed bit-identically
+    // instead of being stored; the first row of an episode holds portfolio_initial_value (:194).
+    const double val0 = valorisation(e.pf, p0);
+    const double prev_val = (e.step == 0) ? P.v0 : val0;
+
+    if (a >= 0) {                                                            // :234 (None = hold)
+        const double target = P.positions[a];
+        if (target != P.positions[e.pos_idx]) {                              // :213-215 value compare
+            trade_to_position(e.pf, target, p0, P.fee, val0);                // :204-211
+            e.pos_idx = (int)a;
+        }
+    }
+    idx += 1;                                                                // :235
+    e.step += 1;                                                             // :236
+    update_interest(e.pf, P.rate);                                           // :240
+    const double val = valorisation(e.pf, p1);                               // :241
+    const bool done = ddiv(val, P.v0) <= P.done_ratio;                       // :246
+    bool trunc = idx >= T - 1;                                               // :248
+    if (P.max_episode_duration >= 0 && e.step >= P.max_episode_duration - 1) trunc = true;   // :250
+    const double rp = real_position(e.pf, p1, val);                          // :259
+    const double rew = done ? 0.0 : log(ddiv(val, prev_val));                // :263-267 -> :17-18
+
+    O.reward[i] = rew;
+    O.terminated[i] = (uint8_t)done;
+    O.truncated[i] = (uint8_t)trunc;
+    if (O.valuation) O.valuation[i] = val;
+    if (O.real_position) O.real_position[i] = rp;
+    if (O.info_idx) O.info_idx[i] = idx;
+    if (O.info_step) O.info_step[i] = e.step;
+    if (O.pre_reset_portfolio) {
+        const int64_t N = P.n_envs;
+        O.pre_reset_portfolio[i] = e.pf.asset;
+        O.pre_reset_portfolio[N + i] = e.pf.fiat;
+        O.pre_reset_portfolio[2 * N + i] = e.pf.ia;
+        O.pre_reset_portfolio[3 * N + i] = e.pf.ifi;
+    }
+    float dyn_pos = (float)P.positions[e.pos_idx], dyn_rp = (float)rp;        // fp64 -> fp32 as numpy casts (:154)
+    if (P.n_dyn > 0) {                                                       // _get_obs write-back (:153-154)
+        const int W = P.windows > 0 ? P.windows : 1;
+        float2* ring = reinterpret_cast<float2*>(S.dyn_ring) + (int64_t)i * W + (idx % W);
+        *ring = make_float2(dyn_pos, dyn_rp);
+    }
+    acc.sum_rew = dadd(acc.sum_rew, rew);
+    if (done || trunc) {                                                     // :269-271 calculate_metrics
+        acc.episodes += 1;
+        acc.terminated += done ? 1 : 0;
+        acc.truncated += trunc ? 1 : 0;
+        acc.sum_len += e.step;
+        acc.sum_pr = dadd(acc.sum_pr, dsub(ddiv(val, P.v0), 1.0));           // :282
+        acc.sum_mr = dadd(acc.sum_mr, dsub(ddiv(p1, __ldg(price + e.ep_start)), 1.0));   // :281
+        if (autoreset) {
+            reset_env(P, D, S, i, tick, e);                                  // in-place auto-reset
+            idx = e.ep_start;
+            dyn_pos = dyn_rp = (float)P.positions[e.pos_idx];                // first row: (position, position) :191-192
+            if (P.n_datasets > 1) S.dataset_idx[i] = e.ds;
+        }
+    }
+    S.asset[i] = e.pf.asset;
+    S.fiat[i] = e.pf.fiat;
+    S.interest_asset[i] = e.pf.ia;
+    S.interest_fiat[i] = e.pf.ifi;
+    S.pos_idx[i] = e.pos_idx;
+    S.step[i] = e.step;
+    S.ep_start[i] = e.ep_start;
+    StepThreadOut r;
+    r.idx = idx; r.ep_start = e.ep_start; r.ds = e.ds;
+    r.dyn_pos = dyn_pos; r.dyn_rp = dyn_rp;
+    return r;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = dadd(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// CTA-level metric reduction -> metric_partials[blockIdx.x]; the last CTA to arrive folds all
+// partial rows in a fixed order (deterministic) into metrics_step / metrics_total.
+static __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O, const GteState& S, int chunk_flags) {
+    __shared__ double s_part[kStepThreads / 32][GTE_N_METRICS];
+    __shared__ double s_fold[32][GTE_N_METRICS];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    const double w_rew = warp_sum(acc.sum_rew);
+    const int w_ep = __reduce_add_sync(0xffffffffu, acc.episodes);
+    double w_pr = 0.0, w_mr = 0.0;
+    int w_term = 0, w_trunc = 0, w_len = 0;
+    if (w_ep > 0) {                                      // warp-uniform: episode ends are rare
+        w_pr = warp_sum(acc.sum_pr);
+        w_mr = warp_sum(acc.sum_mr);
+        w_term = __reduce_add_sync(0xffffffffu, acc.terminated);
+        w_trunc = __reduce_add_sync(0xffffffffu, acc.truncated);
+        w_len = __reduce_add_sync(0xffffffffu, acc.sum_len);
+    }
+    if (lane == 0) {
+        s_part[warp][GTE_M_EPISODES] = (double)w_ep;
+        s_part[warp][GTE_M_TERMINATED] = (double)w_term;
+        s_part[warp][GTE_M_TRUNCATED] = (double)w_trunc;
+        s_part[warp][GTE_M_SUM_PORTFOLIO_RETURN] = w_pr;
+        s_part[warp][GTE_M_SUM_MARKET_RETURN] = w_mr;
+        s_part[warp][GTE_M_SUM_EPISODE_LENGTH] = (double)w_len;
+        s_part[warp][GTE_M_SUM_REWARD] = w_rew;
+        s_part[warp][GTE_M_RESERVED] = 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x < GTE_N_METRICS) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kStepThreads / 32; ++w) t = dadd(t, s_part[w][threadIdx.x]);
+        O.metric_partials[(int64_t)blockIdx.x * GTE_N_METRICS + threadIdx.x] = t;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(O.block_counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int m = threadIdx.x % GTE_N_METRICS, g = threadIdx.x / GTE_N_METRICS;   // 32 groups x 8 metrics
+    double t = 0.0;
+    for (int b = g; b < (int)gridDim.x; b += kStepThreads / GTE_N_METRICS)
+        t = dadd(t, __ldcg(O.metric_partials + (int64_t)b * GTE_N_METRICS + m));
+    s_fold[g][m] = t;
+    __syncthreads();
+    if (threadIdx.x < GTE_N_METRICS) {
+        double tot = 0.0;
+        for (int k = 0; k < kStepThreads / GTE_N_METRICS; ++k) tot = dadd(tot, s_fold[k][threadIdx.x]);
+        // env chunks of one lockstep iteration run as consecutive launches: the first one overwrites
+        // metrics_step, later ones add to it in launch order (deterministic)
+        O.metrics_step[threadIdx.x] = (chunk_flags & kChunkFirst) ? tot : dadd(O.metrics_step[threadIdx.x], tot);
+        if (O.metrics_total) O.metrics_total[threadIdx.x] = dadd(O.metrics_total[threadIdx.x], tot);
+    }
+    if (threadIdx.x == 0) {
+        *O.block_counter = 0u;                           // self-resetting for the next launch
+        // every CTA of this iteration has read the tick by now: advance the Philox event counter
+        if (chunk_flags & kChunkLast) *S.tick = *S.tick + 1ull;
+    }
+}
+
+}  // namespace gte
