@@ -82,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:  # noqa: BLE001
             self.proc = None
@@ -94,7 +94,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         for r in self.rows:
@@ -171,7 +171,7 @@ def run_reference_arm(args, wl, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5", choices=list(WORKLOADS))
@@ -326,7 +326,7 @@ def main():
         for mode in ("hybrid", "numpy"):
             env.output = mode
             env._host = None
-            n_it = args.e2e_steps if mode == "numpy" else max(args.steps, 10)
+            n_it = args.e2e_steps if mode == "numpy" else min(max(args.steps, 10), 100)
             for k in range(2):
                 env.step(acts_h[k % n_sets])                         # allocates + warms the pinned buffers
             barrier()
@@ -375,7 +375,7 @@ def main():
                                     % (env._obs.numel() * 4 / 1e6, (N * 44 + env._dyn_ring.numel() * 4) / 1e6),
                        "parallelism": f"env-sharded x{world}, dataset replicated, NCCL allreduce of 8 fp64 metrics per iteration"},
             "clocks": clocks, "e2e": e2e, "e2e_full_obs_to_host": e2e_full,
-            "gpu_launches": 2 * env.chunks * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": (1 if wl["windows"] is None else 2 * env.chunks) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

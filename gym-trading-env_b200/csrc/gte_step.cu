@@ -17,13 +17,25 @@ namespace gte {
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(kStepThreads, MIN_CTAS)
 step_kernel(const GteParams P, const GteData D, const GteState S, const int64_t* __restrict__ actions,
-            const GteStepOut O, int autoreset, int tiles_per_cta, int env_begin, int env_end, int chunk_flags) {
+            const GteStepOut O, int autoreset, int tiles_per_cta, int env_begin, int env_end, int chunk_flags,
+            float* __restrict__ obs_rows) {
     MetricAcc acc;
     const uint64_t tick = *S.tick;
     const int64_t base0 = (int64_t)env_begin + (int64_t)blockIdx.x * tiles_per_cta * kStepThreads;
     for (int t = 0; t < tiles_per_cta; ++t) {
         const int64_t i = base0 + (int64_t)t * kStepThreads + threadIdx.x;
-        if (i < env_end) step_env(P, D, S, actions, O, tick, autoreset, (int)i, acc);
+        if (i < env_end) {
+            const StepThreadOut r = step_env(P, D, S, actions, O, tick, autoreset, (int)i, acc);
+            if (obs_rows != nullptr) {
+                // windows=None (environments.py:156-157): the observation is the single row idx, written by the
+                // env's own thread -> one launch per lockstep iteration at small N
+                const int F = P.n_static + P.n_dyn;
+                const float* __restrict__ f = D.features + ((int64_t)r.ds * P.t_stride + r.idx) * P.n_static;
+                float* __restrict__ o = obs_rows + i * F;
+                for (int c = 0; c < P.n_static; ++c) o[c] = __ldg(f + c);
+                if (P.n_dyn > 0) { o[P.n_static] = r.dyn_pos; o[P.n_static + 1] = r.dyn_rp; }
+            }
+        }
     }
     reduce_metrics(acc, O, S, chunk_flags);
 }
@@ -125,7 +137,7 @@ int step_grid(int n_envs) {
 
 cudaError_t launch_step_range(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
                               const GteStepOut& O, int autoreset, int env_begin, int env_end, int chunk_flags,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, float* obs_rows = nullptr) {
     static const int min_ctas = [] { const char* e = getenv("GTE_STEP_MIN_CTAS"); return e ? atoi(e) : 4; }();
     const int n = env_end - env_begin;
     const int grid = step_grid(n), tpc = step_tiles_per_cta(n);
@@ -137,9 +149,9 @@ cudaError_t launch_step_range(const GteParams& P, const GteData& D, const GteSta
     }();
     (void)carveout_set;
     if (min_ctas >= 4)
-        step_kernel<4><<<grid, kStepThreads, 0, stream>>>(P, D, S, actions, O, autoreset, tpc, env_begin, env_end, chunk_flags);
+        step_kernel<4><<<grid, kStepThreads, 0, stream>>>(P, D, S, actions, O, autoreset, tpc, env_begin, env_end, chunk_flags, obs_rows);
     else
-        step_kernel<3><<<grid, kStepThreads, 0, stream>>>(P, D, S, actions, O, autoreset, tpc, env_begin, env_end, chunk_flags);
+        step_kernel<3><<<grid, kStepThreads, 0, stream>>>(P, D, S, actions, O, autoreset, tpc, env_begin, env_end, chunk_flags, obs_rows);
     return cudaGetLastError();
 }
 
@@ -199,6 +211,8 @@ cudaError_t launch_step_obs(const GteParams& P, const GteData& D, const GteState
     if (n_chunks <= 0) n_chunks = default_chunks(P.n_envs);
     if (n_chunks > 16) n_chunks = 16;
     cudaError_t e;
+    if (P.windows == 0)            // windows=None: the step kernel writes the one-row observation itself
+        return launch_step_range(P, D, S, actions, O, autoreset, 0, P.n_envs, kChunkFirst | kChunkLast, stream, obs);
     if (n_chunks == 1) {
         if ((e = launch_step(P, D, S, actions, O, autoreset, stream)) != cudaSuccess) return e;
         return launch_obs_range(P, D, S, obs, variant, 0, P.n_envs, stream);
