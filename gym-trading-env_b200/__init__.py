@@ -15,7 +15,8 @@ from .data import (SeriesArrays, build_window_tables, frame_to_arrays, make_gbm_
 __version__ = "0.1.0"
 
 _LAZY = {"TradingVectorEnv", "MultiDatasetTradingVectorEnv", "basic_reward_function",
-         "dynamic_feature_last_position_taken", "dynamic_feature_real_position", "shard_envs", "LazyInfos"}
+         "dynamic_feature_last_position_taken", "dynamic_feature_real_position", "shard_envs", "LazyInfos",
+         "DeviceReward", "log_return_reward", "simple_return_reward"}
 
 
 def __getattr__(name):          # torch / the CUDA library are only imported when an env class is used

@@ -21,6 +21,7 @@ GTE_MAX_DATASETS = 64
 GTE_N_METRICS = 8
 GTE_STEP_THREADS = 256
 GTE_MAX_PARTIAL_ROWS = 4096
+REWARD_LOG_RETURN, REWARD_SIMPLE_RETURN = 0, 1
 OBS_AUTO, OBS_GENERIC, OBS_VEC, OBS_TMA = 0, 1, 2, 3
 OBS_VARIANTS = {"auto": OBS_AUTO, "generic": OBS_GENERIC, "vec": OBS_VEC, "tma": OBS_TMA}
 METRIC_NAMES = ["episodes", "terminated", "truncated", "sum_portfolio_return", "sum_market_return",
@@ -33,9 +34,10 @@ class GteParams(C.Structure):
         ("n_static", C.c_int32), ("n_dyn", C.c_int32), ("max_episode_duration", C.c_int32),
         ("n_datasets", C.c_int32), ("initial_position_idx", C.c_int32),
         ("episodes_between_switch", C.c_int32), ("plan_episodes", C.c_int32),
-        ("multi_dataset", C.c_int32), ("reserved0", C.c_int32),
+        ("multi_dataset", C.c_int32), ("reward_kind", C.c_int32),
         ("t_stride", C.c_int64), ("env_id_offset", C.c_int64), ("seed", C.c_uint64),
         ("fee", C.c_double), ("rate", C.c_double), ("v0", C.c_double), ("done_ratio", C.c_double),
+        ("reward_scale", C.c_double), ("reward_lo", C.c_double), ("reward_hi", C.c_double),
         ("positions", C.c_double * GTE_MAX_POSITIONS),
     ]
 

@@ -36,6 +36,8 @@ int check_common(const char* fn, const GteParams* p, const GteData* d, const Gte
     GTE_REQUIRE(fn, p->plan_episodes >= 0);
     GTE_REQUIRE(fn, p->t_stride >= 2);
     GTE_REQUIRE(fn, p->v0 > 0.0);
+    GTE_REQUIRE(fn, p->reward_kind == GTE_REWARD_LOG_RETURN || p->reward_kind == GTE_REWARD_SIMPLE_RETURN);
+    GTE_REQUIRE(fn, p->reward_lo <= p->reward_hi);
     GTE_REQUIRE(fn, d->price != nullptr && d->lengths != nullptr);
     GTE_REQUIRE(fn, p->n_static == 0 || d->features != nullptr);
     GTE_REQUIRE(fn, s->asset && s->fiat && s->interest_asset && s->interest_fiat);

@@ -66,7 +66,15 @@ __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteD
     bool trunc = idx >= T - 1;                                               // :248
     if (P.max_episode_duration >= 0 && e.step >= P.max_episode_duration - 1) trunc = true;   // :250
     const double rp = real_position(e.pf, p1, val);                          // :259
-    const double rew = done ? 0.0 : log(ddiv(val, prev_val));                // :263-267 -> :17-18
+    double rew = 0.0;                                                        // :263 (stays 0 when terminated)
+    if (!done) {                                                             // :265-267 reward_function(history)
+        double x = (P.reward_kind == GTE_REWARD_SIMPLE_RETURN) ? ddiv(dsub(val, prev_val), prev_val)
+                                                               : log(ddiv(val, prev_val));      // :17-18
+        x = dmul(P.reward_scale, x);                                         // 1 * x is exact
+        x = (x < P.reward_lo) ? P.reward_lo : x;                             // np.clip = minimum(maximum(x, lo), hi)
+        x = (x > P.reward_hi) ? P.reward_hi : x;
+        rew = x;
+    }
 
     O.reward[i] = rew;
     O.terminated[i] = (uint8_t)done;

@@ -44,6 +44,41 @@ def dynamic_feature_real_position(history=None):
 _DEFAULT_DYNAMIC = [dynamic_feature_last_position_taken, dynamic_feature_real_position]
 
 
+class DeviceReward:
+    """A reward functor fused into the CUDA step kernel:
+    ``reward = clip(scale * f(valuation[-1], valuation[-2]), lo, hi)`` with ``f`` the log-return
+    (``kind="log_return"``, the reference's ``basic_reward_function``, environments.py:17-18) or the simple
+    return ``(v[-1]-v[-2])/v[-2]`` (``kind="simple_return"``).  Covers the variants the reference's callers
+    pass as Python callbacks — ``np.clip(log_return, -0.002, 0.005)`` (luckymodel/envs/env.py:16-18),
+    ``100 * log_return`` (luckymodel/scripts/test_env.py:20-22), ``max(0, simple_return)`` (env.py:19) —
+    without a CPU fallback.  Evaluated only when the step did not terminate (environments.py:265-267)."""
+
+    KINDS = {"log_return": _cabi.REWARD_LOG_RETURN, "simple_return": _cabi.REWARD_SIMPLE_RETURN}
+
+    def __init__(self, kind="log_return", scale=1.0, clip=None):
+        if kind not in self.KINDS:
+            raise ValueError(f"kind must be one of {list(self.KINDS)}")
+        self.kind, self.scale = kind, float(scale)
+        lo, hi = (-np.inf, np.inf) if clip is None else clip
+        self.lo = -np.inf if lo is None else float(lo)
+        self.hi = np.inf if hi is None else float(hi)
+        if not self.lo <= self.hi:
+            raise ValueError("clip must be (lo, hi) with lo <= hi")
+
+    def __repr__(self):
+        return f"DeviceReward(kind={self.kind!r}, scale={self.scale}, clip=({self.lo}, {self.hi}))"
+
+
+def log_return_reward(scale=1.0, clip=None):
+    """``clip(scale * log(v[-1]/v[-2]), *clip)`` on the device."""
+    return DeviceReward("log_return", scale, clip)
+
+
+def simple_return_reward(scale=1.0, clip=None):
+    """``clip(scale * (v[-1]-v[-2])/v[-2], *clip)`` on the device."""
+    return DeviceReward("simple_return", scale, clip)
+
+
 def _fn_name(f):
     return getattr(f, "__name__", None)
 
@@ -146,7 +181,8 @@ class TradingVectorEnv:
     is pipelined beside the previous range's gather);
     ``debug_outputs`` (also write the terminal step's idx/step/real_position/portfolio, +48 B/env).
 
-    ``reward_function`` must be :func:`basic_reward_function` and ``dynamic_feature_functions`` the two
+    ``reward_function`` must be :func:`basic_reward_function` or a :class:`DeviceReward` from the fused
+    catalogue (log / simple return with scale and clip), and ``dynamic_feature_functions`` the two
     defaults or ``[]``: arbitrary Python callbacks over a History cannot run inside the kernel and
     there is deliberately no CPU fallback (NotImplementedError).
 
@@ -182,10 +218,15 @@ class TradingVectorEnv:
             "The 'initial_position' parameter must be 'random' or a position mentionned in the 'position' (default is [0, 1]) parameter."
         assert render_mode is None or render_mode in self.metadata["render_modes"]
         self.render_mode = render_mode
-        if reward_function is not basic_reward_function and _fn_name(reward_function) != "basic_reward_function":
+        if isinstance(reward_function, DeviceReward):
+            self._reward_spec = reward_function
+        elif reward_function is basic_reward_function or _fn_name(reward_function) == "basic_reward_function":
+            self._reward_spec = DeviceReward()
+        else:
             raise NotImplementedError(
-                "only basic_reward_function (log-return, environments.py:17-18) is fused into the CUDA step "
-                "kernel; arbitrary Python reward callbacks are not supported (no CPU fallback)")
+                "reward_function must be basic_reward_function (log-return, environments.py:17-18) or a "
+                "DeviceReward (log_return_reward / simple_return_reward with scale and clip): arbitrary Python "
+                "callbacks over a History cannot run inside the CUDA step kernel and there is no CPU fallback")
         self.reward_function = reward_function
         dyn = list(dynamic_feature_functions)
         if len(dyn) == 0:
@@ -350,6 +391,8 @@ class TradingVectorEnv:
         p.t_stride, p.env_id_offset, p.seed = self._t_stride, self.env_id_offset, self.seed & (2**64 - 1)
         p.fee, p.rate = float(self.trading_fees), float(self.borrow_interest_rate)
         p.v0, p.done_ratio = self.portfolio_initial_value, self.done_valuation_ratio
+        p.reward_kind = DeviceReward.KINDS[self._reward_spec.kind]
+        p.reward_scale, p.reward_lo, p.reward_hi = self._reward_spec.scale, self._reward_spec.lo, self._reward_spec.hi
         for i, x in enumerate(self.positions):
             p.positions[i] = float(x)
         d = _cabi.GteData()

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GTE_VERSION 100            /* 0.1.0 */
+#define GTE_VERSION 101            /* 0.1.1 */
 #define GTE_MAX_POSITIONS 64
 #define GTE_MAX_DATASETS 64        /* least-used rotation keeps a 64-bit "used this round" mask per env */
 #define GTE_N_METRICS 8
@@ -49,6 +49,15 @@ enum GteMetric {
     GTE_M_SUM_EPISODE_LENGTH = 5,  /* sum of episode lengths in steps                              */
     GTE_M_SUM_REWARD = 6,          /* sum of this iteration's rewards over all envs                */
     GTE_M_RESERVED = 7
+};
+
+/* Fused reward functors.  The reference takes an arbitrary Python `reward_function(history)`
+ * (environments.py:50-51, :266); the catalogue covers the default and the variants its callers use:
+ * luckymodel/envs/env.py:16-18 (log-return clipped to [-0.002, 0.005]), luckymodel/scripts/test_env.py:20-22
+ * (100 x log-return), and the simple / positive-part return of env.py:19. */
+enum GteRewardKind {
+    GTE_REWARD_LOG_RETURN = 0,     /* f = log(v_t / v_{t-1})                 basic_reward_function, :17-18 */
+    GTE_REWARD_SIMPLE_RETURN = 1   /* f = (v_t - v_{t-1}) / v_{t-1}                                         */
 };
 
 /* observation-gather kernel variants (gte_gather_obs `variant`) */
@@ -73,7 +82,7 @@ typedef struct GteParams {
     int32_t episodes_between_switch; /* `episodes_between_dataset_switch` (:370)                       */
     int32_t plan_episodes;           /* E of reset_plan[N,E,3]; 0 = draw resets from Philox            */
     int32_t multi_dataset;           /* 1 = MultiDatasetTradingEnv.reset semantics (:393-400)          */
-    int32_t reserved0;
+    int32_t reward_kind;             /* enum GteRewardKind: which fused reward functor (:50-51 `reward_function`) */
     int64_t t_stride;                /* rows allocated per dataset in `price` / `features`             */
     int64_t env_id_offset;           /* global index of env 0 (multi-GPU sharding; keys the RNG)       */
     uint64_t seed;                   /* Philox key                                                     */
@@ -81,6 +90,9 @@ typedef struct GteParams {
     double rate;                     /* `borrow_interest_rate` (:103)                                  */
     double v0;                       /* `portfolio_initial_value` (:104)                               */
     double done_ratio;               /* terminated = valuation/v0 <= done_ratio; 0.7 in this fork (:246) */
+    double reward_scale;             /* reward = clip(reward_scale * f(valuation, previous valuation),      */
+    double reward_lo;                /*               reward_lo, reward_hi); defaults 1, -inf, +inf give   */
+    double reward_hi;                /*               basic_reward_function bit for bit                    */
     double positions[GTE_MAX_POSITIONS]; /* `positions` (:98)                                          */
 } GteParams;
 

@@ -41,10 +41,14 @@ typedef struct OrcEnv {
     int32_t dyn_mode;                /* 0 = faithful private columns (stale rows leak, H3); 1 = zeroed on reset */
     int32_t plan_episodes;           /* E of plan[N,E,3]; 0 = no plan -> Philox */
     int32_t multi_dataset;           /* 1 = MultiDatasetTradingEnv semantics (:393-400) */
+    int32_t reward_kind;             /* 0 = log-return (basic_reward_function :17-18), 1 = simple return */
+    int32_t pad0;
     int64_t t_stride;                /* rows allocated per dataset */
     int64_t env_id_offset;           /* global id of env 0 (multi-GPU sharding) */
     uint64_t seed;
     double fee, rate, v0, done_ratio;
+    double reward_scale, reward_lo, reward_hi;   /* reward = clip(scale * f, lo, hi): the callers' variants
+                                                    (luckymodel/envs/env.py:16-18, scripts/test_env.py:20-22) */
     /* ---- data: _set_df (:128-143) ---- */
     const double* positions;         /* [P] */
     const float* features;           /* [n_datasets, t_stride, n_static] */
@@ -312,7 +316,14 @@ void orc_step_range(OrcEnv* e, int lo, int hi, const int64_t* actions, uint64_t 
         if (e->max_episode_duration >= 0 && step >= e->max_episode_duration - 1) trunc = 1;   /* :250 */
         double rp = ((s[0] - s[2]) * p) / val;                           /* :259 real_position */
         double rew = 0.0;                                                /* :263 */
-        if (!done) rew = log(val / e->prev_val[i]);                      /* :265-267 -> :17-18 */
+        if (!done) {                                                     /* :265-267 reward_function(history) */
+            double x = e->reward_kind == 1 ? (val - e->prev_val[i]) / e->prev_val[i]
+                                           : log(val / e->prev_val[i]);  /* :17-18 */
+            x = e->reward_scale * x;
+            x = (x < e->reward_lo) ? e->reward_lo : x;                   /* np.clip */
+            x = (x > e->reward_hi) ? e->reward_hi : x;
+            rew = x;
+        }
         e->asset[i] = s[0]; e->fiat[i] = s[1]; e->interest_asset[i] = s[2]; e->interest_fiat[i] = s[3];
         e->step[i] = step;
         e->prev_val[i] = val;

@@ -63,15 +63,36 @@ def stack_series(dfs):
     return feats, price, np.array([a.length for a in arrs], np.int32)
 
 
-def make_case(name, dfs, *, n_envs, n_steps, action_seed, hold_fraction=0.0, **kw):
+# reward callbacks exactly as the reference's callers write them
+def reward_clipped_log_return(history):          # luckymodel/envs/env.py:16-18
+    log_return = np.log(history["portfolio_valuation", -1] / history["portfolio_valuation", -2])
+    return np.clip(log_return, -0.002, 0.005)
+
+
+def reward_scaled_log_return(history):           # luckymodel/scripts/test_env.py:20-22
+    return 100 * np.log(history["portfolio_valuation", -1] / history["portfolio_valuation", -2])
+
+
+def reward_simple_return(history):               # the commented-out variant of luckymodel/envs/env.py:19, unclipped
+    return (history["portfolio_valuation", -1] - history["portfolio_valuation", -2]) / history["portfolio_valuation", -2]
+
+
+REWARDS = {"clipped_log_return": (reward_clipped_log_return, dict(reward_kind=0, reward_scale=1.0, reward_clip=(-0.002, 0.005))),
+           "scaled_log_return": (reward_scaled_log_return, dict(reward_kind=0, reward_scale=100.0, reward_clip=(None, None))),
+           "simple_return": (reward_simple_return, dict(reward_kind=1, reward_scale=1.0, reward_clip=(None, None)))}
+
+
+def make_case(name, dfs, *, n_envs, n_steps, action_seed, hold_fraction=0.0, reward=None, **kw):
     positions = kw["positions"]
     rng = np.random.default_rng(action_seed)
     actions = rng.integers(0, len(positions), size=(n_steps, n_envs)).astype(np.int64)
     if hold_fraction > 0:
         actions[rng.random(actions.shape) < hold_fraction] = -1
-    rec = rh.run_lockstep(dfs, n_envs, actions, **kw)
+    rec = rh.run_lockstep(dfs, n_envs, actions, reward_function=REWARDS[reward][0] if reward else None, **kw)
     feats, price, lengths = stack_series(dfs)
     params = dict(kw)
+    if reward:
+        params["reward"] = REWARDS[reward][1]
     params.update(n_envs=n_envs, n_steps=n_steps, action_seed=action_seed, name=name,
                   reference="ten2net/Gym-Trading-Env src/gym_trading_env (unmodified), numpy %s" % np.__version__)
     out = {k: rec[k] for k in RECORD_KEYS}
@@ -129,6 +150,11 @@ def main():
     make_case("btc_example_config", [btc], n_envs=4, n_steps=300, action_seed=19,
               positions=[-1, -0.5, 0, 0.5, 1, 1.5, 2], windows=5, initial_position="random",
               max_episode_duration=100, max_episodes=8, **common)
+    # the reward callbacks the reference's callers use (fused device catalogue, "next" row of SURVEY.md §8f)
+    for rname in REWARDS:
+        make_case("reward_" + rname, [vol], n_envs=6, n_steps=160, action_seed=30, reward=rname,
+                  positions=[-2, -1, 0, 1, 2], windows=None, initial_position="random",
+                  max_episode_duration=60, max_episodes=16, **common)
     # MultiDatasetTradingEnv: ragged datasets, least-used rotation, switch every episode / every 3 episodes
     multi = [gte.make_gbm_ohlcv(T, seed=20 + k) for k, T in enumerate([300, 420, 360, 500])]
     make_case("multi_dataset_k1", multi, n_envs=6, n_steps=260, action_seed=20,

@@ -38,8 +38,10 @@ class _OrcEnv(C.Structure):
         ("n_datasets", C.c_int32), ("initial_position_idx", C.c_int32),
         ("episodes_between_switch", C.c_int32), ("dyn_mode", C.c_int32),
         ("plan_episodes", C.c_int32), ("multi_dataset", C.c_int32),
+        ("reward_kind", C.c_int32), ("pad0", C.c_int32),
         ("t_stride", C.c_int64), ("env_id_offset", C.c_int64), ("seed", C.c_uint64),
         ("fee", C.c_double), ("rate", C.c_double), ("v0", C.c_double), ("done_ratio", C.c_double),
+        ("reward_scale", C.c_double), ("reward_lo", C.c_double), ("reward_hi", C.c_double),
         ("positions", C.c_void_p), ("features", C.c_void_p), ("price", C.c_void_p), ("lengths", C.c_void_p),
         ("asset", C.c_void_p), ("fiat", C.c_void_p), ("interest_asset", C.c_void_p),
         ("interest_fiat", C.c_void_p), ("prev_val", C.c_void_p),
@@ -125,7 +127,8 @@ class OracleVecEnv:
                  trading_fees=0.0, borrow_interest_rate=0.0, portfolio_initial_value=1000.0,
                  initial_position="random", max_episode_duration="max", dynamic_features=True,
                  done_ratio=0.7, seed=0, env_id_offset=0, plan=None, multi_dataset=False,
-                 episodes_between_dataset_switch=1, dyn_mode=1, threads=1):
+                 episodes_between_dataset_switch=1, dyn_mode=1, threads=1,
+                 reward_kind=0, reward_scale=1.0, reward_clip=(-np.inf, np.inf)):
         features = np.ascontiguousarray(features, dtype=np.float32)
         price = np.ascontiguousarray(price, dtype=np.float64)
         if features.ndim == 2:
@@ -165,6 +168,8 @@ class OracleVecEnv:
         e.t_stride, e.env_id_offset, e.seed = t_stride, int(env_id_offset), int(seed)
         e.fee, e.rate = float(trading_fees), float(borrow_interest_rate)
         e.v0, e.done_ratio = float(portfolio_initial_value), float(done_ratio)
+        e.reward_kind, e.reward_scale = int(reward_kind), float(reward_scale)
+        e.reward_lo, e.reward_hi = float(reward_clip[0]), float(reward_clip[1])
         e.positions, e.features, e.price, e.lengths = _p(self.positions), _p(features), _p(price), _p(self.lengths)
         e.asset, e.fiat = _p(self.asset), _p(self.fiat)
         e.interest_asset, e.interest_fiat, e.prev_val = _p(self.interest_asset), _p(self.interest_fiat), _p(self.prev_val)

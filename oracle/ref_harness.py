@@ -66,7 +66,8 @@ def _zero_dyn(env):
 def run_lockstep(dfs, n_envs, actions, *, positions, windows, trading_fees, borrow_interest_rate,
                  portfolio_initial_value, initial_position, max_episode_duration,
                  dynamic_features=True, normalize_dyn=True, np_seed=0,
-                 multi_dataset=False, episodes_between_dataset_switch=1, max_episodes=None):
+                 multi_dataset=False, episodes_between_dataset_switch=1, max_episodes=None,
+                 reward_function=None):
     """Run N reference envs for K lockstep iterations; return a dict of recorded arrays.
 
     dfs: list of DataFrames (one unless multi_dataset).  actions: int64 [K, N]; a negative
@@ -81,6 +82,8 @@ def run_lockstep(dfs, n_envs, actions, *, positions, windows, trading_fees, borr
                   max_episode_duration=max_episode_duration, verbose=0)
     if not dynamic_features:
         kwargs["dynamic_feature_functions"] = []
+    if reward_function is not None:
+        kwargs["reward_function"] = reward_function       # a caller-style Python callback over History
 
     np.random.seed(np_seed)
     tmpdir = None

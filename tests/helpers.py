@@ -41,6 +41,11 @@ def make_oracle(g, dyn_mode=None, plan=True, **over):
     kw.update(num_envs=p["n_envs"], dynamic_features=p.get("dynamic_features", True),
               plan=g["plan"] if plan else None, multi_dataset=p.get("multi_dataset", False),
               episodes_between_dataset_switch=p.get("episodes_between_dataset_switch", 1), dyn_mode=dyn_mode)
+    if "reward" in p:
+        r = p["reward"]
+        clip = r["reward_clip"]
+        kw.update(reward_kind=r["reward_kind"], reward_scale=r["reward_scale"],
+                  reward_clip=(-np.inf if clip[0] is None else clip[0], np.inf if clip[1] is None else clip[1]))
     kw.update(over)
     return orc.OracleVecEnv(g["features"], g["price"], g["lengths"], **kw)
 
@@ -62,6 +67,10 @@ def make_device_env(g, plan=True, **over):
     kw.update(num_envs=p["n_envs"], reset_plan=g["plan"] if plan else None, verbose=0, debug_outputs=True)
     if not p.get("dynamic_features", True):
         kw["dynamic_feature_functions"] = []
+    if "reward" in p:
+        r = p["reward"]
+        kw["reward_function"] = gte.DeviceReward("simple_return" if r["reward_kind"] == 1 else "log_return",
+                                                 r["reward_scale"], tuple(r["reward_clip"]))
     kw.update(over)
     series = series_from_golden(g)
     if p.get("multi_dataset", False):

@@ -244,3 +244,16 @@ def test_step_obs_pipelined_graph_and_hybrid_modes_match_oracle(mode):
         np.testing.assert_allclose(m[6], o.metrics[6], rtol=1e-9, atol=1e-11)
     assert int(dev._tick_dev.item()) == 2 + 130
     dev.check_errors()
+
+
+def test_reward_catalogue_rejects_python_callbacks_and_accepts_device_functors():
+    import gym_trading_env_b200 as gte
+    arr = gte.frame_to_arrays(gte.make_gbm_ohlcv(500, seed=0))
+    with pytest.raises(NotImplementedError):
+        gte.TradingVectorEnv(arr, reward_function=lambda h: 0.0, num_envs=2)
+    with pytest.raises(ValueError):
+        gte.DeviceReward("sharpe")
+    env = gte.TradingVectorEnv(arr, reward_function=gte.log_return_reward(scale=100.0, clip=(-0.2, 0.5)), num_envs=8, verbose=0)
+    env.reset()
+    _, rew, *_ = env.step(np.ones(8, dtype=np.int64))
+    assert float(rew.max()) <= 0.5 and float(rew.min()) >= -0.2
