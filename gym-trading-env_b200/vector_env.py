@@ -262,6 +262,7 @@ class TradingVectorEnv:
         self.n_chunks = int(n_chunks)
         self._graph = None
         self._copy_in = self._copy_out = None
+        self._track_ids = None
         self._obs_variant = _cabi.OBS_VARIANTS[obs_variant]
         self._multi = bool(_multi_dataset)
         self._k_switch = int(_episodes_between_dataset_switch)
@@ -504,6 +505,8 @@ class TradingVectorEnv:
                 mask_ptr = C.c_void_p(keep.data_ptr())
             self._launch_reset(mask_ptr, first=False)
             self._launch_obs()
+            if self._track_ids is not None:
+                self._track_append(after_reset=True)
             return self._emit_obs(), self.infos
 
     def step(self, actions):
@@ -537,39 +540,47 @@ class TradingVectorEnv:
                 if act.dtype != torch.int64 or not act.is_contiguous() or act.shape != (self.num_envs,) \
                         or act.device != self.device:
                     act = act.to(device=self.device, dtype=torch.int64).contiguous().view(self.num_envs)
-            if self.output == "hybrid":
-                # reward / flags leave for the host right after the step kernel, beside the gather
-                hb = self._host_buffers()
-                self._launch_step(C.c_void_p(act.data_ptr()))
-                self._copy_out.wait_stream(main)
-                with torch.cuda.stream(self._copy_out):
-                    for k, t in (("reward", self._reward), ("terminated", self._terminated),
-                                 ("truncated", self._truncated), ("error_flag", self._error_flag)):
-                        hb[k].copy_(t, non_blocking=True)
-                self._launch_obs()
-                self._copy_out.synchronize()
-                self._raise_on_flag(int(hb["error_flag"][0]))
-                return (self._obs, hb["reward"].numpy(), hb["terminated"].numpy().view(np.bool_),
-                        hb["truncated"].numpy().view(np.bool_), self.infos)
-            if self.cuda_graph:
-                if act.data_ptr() != self._actions_dev.data_ptr():
-                    self._actions_dev.copy_(act, non_blocking=True)
-                if self._graph is None:
-                    self._capture_graph()
-                self._tick += 1
-                self._graph.replay()
-            else:
-                self._launch_step_obs(C.c_void_p(act.data_ptr()))
-            if self.output == "numpy":
-                h = self._host_buffers()
-                for k, t in (("obs", self._obs), ("reward", self._reward), ("terminated", self._terminated),
+            if self._track_ids is not None:
+                self._track_pre = (self._pos_idx[self._track_ids].clone(), self._dataset_idx[self._track_ids].clone())
+            ret = self._step_launch(act, main)
+            if self._track_ids is not None:
+                self._track_append(after_reset=False, actions=act)
+            return ret
+
+    def _step_launch(self, act, main):
+        if self.output == "hybrid":
+            # reward / flags leave for the host right after the step kernel, beside the gather
+            hb = self._host_buffers()
+            self._launch_step(C.c_void_p(act.data_ptr()))
+            self._copy_out.wait_stream(main)
+            with torch.cuda.stream(self._copy_out):
+                for k, t in (("reward", self._reward), ("terminated", self._terminated),
                              ("truncated", self._truncated), ("error_flag", self._error_flag)):
-                    h[k].copy_(t, non_blocking=True)
-                main.synchronize()
-                self._raise_on_flag(int(h["error_flag"][0]))
-                return (h["obs"].numpy(), h["reward"].numpy(), h["terminated"].numpy().view(np.bool_),
-                        h["truncated"].numpy().view(np.bool_), self.infos)
-            return self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), self.infos
+                    hb[k].copy_(t, non_blocking=True)
+            self._launch_obs()
+            self._copy_out.synchronize()
+            self._raise_on_flag(int(hb["error_flag"][0]))
+            return (self._obs, hb["reward"].numpy(), hb["terminated"].numpy().view(np.bool_),
+                    hb["truncated"].numpy().view(np.bool_), self.infos)
+        if self.cuda_graph:
+            if act.data_ptr() != self._actions_dev.data_ptr():
+                self._actions_dev.copy_(act, non_blocking=True)
+            if self._graph is None:
+                self._capture_graph()
+            self._tick += 1
+            self._graph.replay()
+        else:
+            self._launch_step_obs(C.c_void_p(act.data_ptr()))
+        if self.output == "numpy":
+            h = self._host_buffers()
+            for k, t in (("obs", self._obs), ("reward", self._reward), ("terminated", self._terminated),
+                         ("truncated", self._truncated), ("error_flag", self._error_flag)):
+                h[k].copy_(t, non_blocking=True)
+            main.synchronize()
+            self._raise_on_flag(int(h["error_flag"][0]))
+            return (h["obs"].numpy(), h["reward"].numpy(), h["terminated"].numpy().view(np.bool_),
+                    h["truncated"].numpy().view(np.bool_), self.infos)
+        return self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), self.infos
 
     def _emit_obs(self):
         if self.output == "numpy":
@@ -582,6 +593,94 @@ class TradingVectorEnv:
     def close(self):
         self._host = None
         self._graph = None
+
+    # ------------------------------------------------------------------ History of tracked envs (utils/history.py)
+    def track(self, env_indices, max_steps=100_000):
+        """Keep a device-side per-step log — the reference's ``History`` rows (environments.py:186-197,
+        253-264) — for a FEW selected envs (rendering / debugging; needs ``debug_outputs=True``).
+        Rows are appended on the device after every reset()/step() with no host synchronisation."""
+        if not self.debug_outputs:
+            raise ValueError("track() needs debug_outputs=True (the terminal-step info columns)")
+        ids = torch.as_tensor(list(env_indices), dtype=torch.int64, device=self.device)
+        if ids.numel() == 0 or int(ids.min()) < 0 or int(ids.max()) >= self.num_envs:
+            raise ValueError("env_indices out of range")
+        self._track_ids = ids
+        self._track_log = torch.zeros(int(max_steps), ids.numel(), len(self._TRACK_COLS), dtype=torch.float64,
+                                      device=self.device)
+        self._track_len = 0
+
+    _TRACK_COLS = ["idx", "step", "position_index", "position", "real_position", "portfolio_valuation",
+                   "portfolio_distribution_asset", "portfolio_distribution_fiat",
+                   "portfolio_distribution_borrowed_asset", "portfolio_distribution_borrowed_fiat",
+                   "portfolio_distribution_interest_asset", "portfolio_distribution_interest_fiat",
+                   "reward", "terminated", "truncated", "dataset_idx", "new_episode",
+                   # state after the in-place auto-reset (used to rebuild the reset() row of the next episode)
+                   "_post_idx", "_post_pos_idx", "_post_asset", "_post_fiat", "_post_ds"]
+
+    def _track_append(self, after_reset, actions=None):
+        if self._track_ids is None or self._track_len >= self._track_log.shape[0]:
+            return
+        i = self._track_ids
+        z = torch.zeros(i.numel(), dtype=torch.float64, device=self.device)
+        pos_tab = torch.tensor(self.positions, dtype=torch.float64, device=self.device)
+        if after_reset:       # the row reset() writes (environments.py:186-197)
+            pidx = self._pos_idx[i].long()
+            pos = pos_tab[pidx]
+            a, f = self._asset[i], self._fiat[i]
+            cols = [(self._ep_start[i] + self._step[i]).double(), self._step[i].double(), pidx.double(), pos, pos,
+                    torch.full_like(z, self.portfolio_initial_value), a.clamp(min=0), f.clamp(min=0),
+                    (-a).clamp(min=0), (-f).clamp(min=0), self._interest_asset[i], self._interest_fiat[i],
+                    z, z, z, self._dataset_idx[i].double(), z + 1, z, z, z, z, z]
+        else:                 # the row step() adds (:253-264): terminal values where the episode ended
+            pf = self._pre_reset_portfolio[:, i]
+            a, f = pf[0], pf[1]
+            a_i = actions[i]
+            pre_pos, pre_ds = self._track_pre
+            # position after the step (before any auto-reset) = target of the action unless it was a hold
+            pos = torch.where(a_i >= 0, pos_tab[a_i.clamp(min=0)], pos_tab[pre_pos.long()])
+            cols = [self._info_idx[i].double(), self._info_step[i].double(), a_i.double(), pos, self._real_position[i],
+                    self._valuation[i], a.clamp(min=0), f.clamp(min=0), (-a).clamp(min=0), (-f).clamp(min=0), pf[2], pf[3],
+                    self._reward[i], self._terminated[i].double(), self._truncated[i].double(),
+                    pre_ds.double(), z,
+                    (self._ep_start[i] + self._step[i]).double(), self._pos_idx[i].double(), self._asset[i], self._fiat[i],
+                    self._dataset_idx[i].double()]
+        self._track_log[self._track_len] = torch.stack(cols, dim=1)
+        self._track_len += 1
+
+    def tracked_history(self, which=0):
+        """The log of tracked env number `which` as a pandas DataFrame with the reference's History
+        column names (+ terminated / truncated / new_episode / date / data_close when known)."""
+        import pandas as pd
+        if self._track_ids is None:
+            raise ValueError("no env is tracked: call track([...]) first")
+        rows = self._track_log[:self._track_len, which].cpu().numpy()
+        cols = self._TRACK_COLS
+        c = {n: k for k, n in enumerate(cols)}
+        out = []
+        for r in rows:
+            out.append(r)
+            if not r[c["new_episode"]] and (r[c["terminated"]] or r[c["truncated"]]) and self.autoreset:
+                # the row reset() writes for the episode the auto-reset started (environments.py:186-197)
+                n = np.zeros(len(cols))
+                pos = float(self.positions[int(r[c["_post_pos_idx"]])])
+                a, f = r[c["_post_asset"]], r[c["_post_fiat"]]
+                n[c["idx"]], n[c["position_index"]], n[c["position"]], n[c["real_position"]] = r[c["_post_idx"]], r[c["_post_pos_idx"]], pos, pos
+                n[c["portfolio_valuation"]] = self.portfolio_initial_value
+                n[c["portfolio_distribution_asset"]], n[c["portfolio_distribution_fiat"]] = max(a, 0.0), max(f, 0.0)
+                n[c["portfolio_distribution_borrowed_asset"]], n[c["portfolio_distribution_borrowed_fiat"]] = max(-a, 0.0), max(-f, 0.0)
+                n[c["dataset_idx"]], n[c["new_episode"]] = r[c["_post_ds"]], 1.0
+                out.append(n)
+        df = pd.DataFrame(np.array(out).reshape(-1, len(cols)), columns=cols)
+        df = df[[n for n in cols if not n.startswith("_")]]
+        for c in ("idx", "step", "position_index", "dataset_idx"):
+            df[c] = df[c].astype(np.int64)
+        for c in ("terminated", "truncated", "new_episode"):
+            df[c] = df[c].astype(bool)
+        ds, idx = df["dataset_idx"].to_numpy(), df["idx"].to_numpy()
+        df["data_close"] = np.array([self._series[d].price[i] for d, i in zip(ds, idx)])
+        if all(s.index is not None for s in self._series):
+            df["date"] = np.array([self._series[d].index[i] for d, i in zip(ds, idx)])
+        return df
 
     # ------------------------------------------------------------------ metrics / errors / state
     def get_metrics(self, total=True):

@@ -257,3 +257,33 @@ def test_reward_catalogue_rejects_python_callbacks_and_accepts_device_functors()
     env.reset()
     _, rew, *_ = env.step(np.ones(8, dtype=np.int64))
     assert float(rew.max()) <= 0.5 and float(rew.min()) >= -0.2
+
+
+def test_tracked_history_reproduces_the_reference_history_rows():
+    """The device-side History log of a tracked env against the golden C1 run:
+    the rows step() adds and the rows reset() writes, including across an end-of-data truncation."""
+    g = H.load_golden("c1_single_nowindow")
+    env = H.make_device_env(g)
+    env.track([0], max_steps=4000)
+    env.reset()
+    import torch
+    K = g["actions"].shape[0]
+    for k in range(K):
+        env.step(torch.as_tensor(g["actions"][k], device=env.device))
+    df = env.tracked_history(0)
+    steps = df[~df["new_episode"]].reset_index(drop=True)
+    assert len(steps) == K and int(df["new_episode"].sum()) == g["plan"].shape[1]
+    H.assert_bits(steps["idx"].to_numpy(np.int32), g["idx"][:, 0], "history idx")
+    H.assert_bits(steps["step"].to_numpy(np.int32), g["step"][:, 0], "history step")
+    H.assert_bits(steps["portfolio_valuation"].to_numpy(), g["valuation"][:, 0], "history valuation")
+    H.assert_bits(steps["position"].to_numpy(), g["position"][:, 0], "history position")
+    H.assert_bits(steps["real_position"].to_numpy(), g["real_position"][:, 0], "history real_position")
+    H.assert_bits(steps["position_index"].to_numpy(), g["actions"][:, 0], "history position_index (raw action)")
+    H.assert_close64(steps["reward"].to_numpy(), g["reward"][:, 0], "history reward")
+    a, f = g["asset"][:, 0], g["fiat"][:, 0]
+    H.assert_bits(steps["portfolio_distribution_asset"].to_numpy(), np.maximum(a, 0) + 0.0, "distribution asset")
+    H.assert_bits(steps["portfolio_distribution_borrowed_fiat"].to_numpy(), np.maximum(-f, 0) + 0.0, "distribution borrowed fiat")
+    H.assert_bits(steps["data_close"].to_numpy(), g["price"][0][g["idx"][:, 0]], "data_close")
+    starts = df[df["new_episode"]]
+    assert (starts["portfolio_valuation"] == 1000.0).all() and (starts["step"] == 0).all()
+    assert starts["idx"].tolist() == g["plan"][0, :, 0].tolist()
