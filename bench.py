@@ -301,7 +301,7 @@ def main():
     # C4: the 1.28 GB feature table is not L2-resident, so the static window read is HBM traffic too
     # (SURVEY.md §8d "5 218 B" accounting) — reported beside the conservative figure
     a_static = (wl["windows"] or 1) * 8 * 4 if wl["n_datasets"] > 1 else 0
-    roofline = {"bound": "hbm", "kernel": f"obs_{env.obs_variant}_kernel", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": {"tma": "obs_tma_coop_kernel", "vec": "obs_vec_kernel", "generic": "obs_generic_kernel"}[env.obs_variant], "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_env": a_obs, "kernel_ms": obs_ms_avg,
                 "step_kernel_ms": step_ms_avg,
