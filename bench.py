@@ -132,6 +132,74 @@ def cpu_port_rate(wl, n_sample, seconds, threads, seed=0):
     return n_sample * iters / dt, iters, dt
 
 
+
+# ---- the UNMODIFIED Python reference, when the driver-style install under baseline/_ref is present -------------
+def _pyref_worker(args):
+    """One host process: n reference TradingEnv objects stepped in a sync-style lockstep loop for `seconds`."""
+    n_envs, seconds, wl, seed = args
+    import warnings
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+    try:
+        import gymnasium  # noqa: F401
+    except Exception:  # noqa: BLE001
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "gymnasium_stub"))     # 4-name stand-in (see its docstring)
+    import gym_trading_env_b200 as gte
+    from gym_trading_env.environments import TradingEnv
+    warnings.resetwarnings()
+    df = gte.make_gbm_ohlcv(min(wl["rows"], 100_000), seed=0)
+    np.random.seed(seed)
+    envs = [TradingEnv(df=df, positions=wl["positions"], windows=wl["windows"], trading_fees=FEE,
+                       borrow_interest_rate=RATE, portfolio_initial_value=V0,
+                       max_episode_duration=wl["duration"], verbose=0) for _ in range(n_envs)]
+    obs = [e.reset()[0] for e in envs]
+    rng = np.random.default_rng(seed)
+    n_pos = len(wl["positions"])
+    steps = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        acts = rng.integers(0, n_pos, size=n_envs)
+        for i, e in enumerate(envs):                      # what gymnasium's SyncVectorEnv does
+            o, r, term, trunc, info = e.step(int(acts[i]))
+            if term or trunc:
+                o, info = e.reset()
+            obs[i] = o
+        np.stack(obs)
+        steps += n_envs
+    return steps, time.perf_counter() - t0
+
+
+def python_reference_rate(wl, workload_name, seconds=6.0):
+    """env-steps/s of the unmodified reference (pip-installed into baseline/_ref) on this box's host cores:
+    one sync-style loop on one core, and one such loop per core (separate processes, hard time-outs).
+    None when the install is absent."""
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "gym_trading_env")):
+        return None
+    cores = len(os.sched_getaffinity(0))
+    out = {"driver": "sync-style lockstep loop over reference TradingEnv objects (gymnasium is not installed: "
+                     "4-name stub from oracle/gymnasium_stub)", "envs_per_process": 8, "cores": cores}
+
+    def run(n_proc):
+        cmd = [sys.executable, os.path.abspath(__file__), "--workload", workload_name, "--pyref-worker", str(seconds)]
+        procs = [subprocess.Popen(cmd + ["--pyref-seed", str(k)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                  text=True) for k in range(n_proc)]
+        res = []
+        for p in procs:
+            try:
+                o, _ = p.communicate(timeout=seconds + 180)
+                res.append(json.loads(o.strip().splitlines()[-1]))
+            except Exception:  # noqa: BLE001
+                p.kill()
+        if len(res) != n_proc:
+            raise RuntimeError(f"{n_proc - len(res)} of {n_proc} reference workers failed")
+        return sum(r["steps"] for r in res) / max(r["seconds"] for r in res)
+    try:
+        out["one_core"] = run(1)
+        out["all_cores"] = run(cores)
+    except Exception as e:  # noqa: BLE001
+        out["error"] = repr(e)[:200]
+    return out
+
+
 def run_reference_arm(args, wl, rank):
     """`--impl reference`: the reference algorithm's CPU port (oracle/gte_oracle.c, scalar C, faithful
     per-env private dynamic-feature columns) on all host cores.  Rank 0 only."""
@@ -162,7 +230,8 @@ def run_reference_arm(args, wl, rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["label"], "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "python_reference": python_reference_rate(wl, args.workload)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
@@ -180,12 +249,18 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--cuda-graph", action="store_true", help="replay one captured lockstep iteration (small N)")
+    ap.add_argument("--pyref-worker", type=float, default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--pyref-seed", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.envs_per_gpu:
         wl["envs"] = args.envs_per_gpu
+    if args.pyref_worker is not None:                      # internal: one reference worker process
+        st, dt = _pyref_worker((8, args.pyref_worker, wl, args.pyref_seed))
+        print(json.dumps({"steps": st, "seconds": dt}), flush=True)
+        return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -363,7 +438,8 @@ def main():
         v_one, _, _ = cpu_port_rate(wl, 256, 3.0, 1)
         cpu = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n_sample} envs x {iters} lockstep iterations ({dt:.1f} s), same dataset/config, "
-                         f"oracle/gte_oracle.c on {cores} threads", "single_core_value": v_one}
+                         f"oracle/gte_oracle.c on {cores} threads", "single_core_value": v_one,
+               "python_reference": python_reference_rate(wl, args.workload)}
 
     if rank == 0:
         out = {
