@@ -1,0 +1,94 @@
+"""GPU: edge shapes of the path against the oracle — single env, env counts that are not multiples of the
+tile / group / CTA sizes, tiny and odd windows (every gather variant and the fallbacks), one static
+feature, the maximum number of positions and datasets, a dataset barely longer than one episode."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(series_list, n_envs, K, *, positions, windows, duration, multi=False, k_switch=1, dyn=True, variant="auto", seed=5):
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    kw = dict(positions=positions, windows=windows, trading_fees=1e-4, borrow_interest_rate=3e-6,
+              portfolio_initial_value=1000, max_episode_duration=duration)
+    tmax = max(s.length for s in series_list)
+    ns = series_list[0].features.shape[1]
+    feats = np.zeros((len(series_list), tmax, ns), np.float32)
+    price = np.ones((len(series_list), tmax))
+    for k, s in enumerate(series_list):
+        feats[k, :s.length], price[k, :s.length] = s.features, s.price
+    lens = np.array([s.length for s in series_list])
+    dkw = dict(kw, num_envs=n_envs, seed=seed, verbose=0, obs_variant=variant, debug_outputs=True)
+    if not dyn:
+        dkw["dynamic_feature_functions"] = []
+    if multi:
+        dev = gte.MultiDatasetTradingVectorEnv(datasets=series_list, episodes_between_dataset_switch=k_switch, **dkw)
+    else:
+        dev = gte.TradingVectorEnv(series_list[0], **dkw)
+    o = orc.OracleVecEnv(feats, price, lens, num_envs=n_envs, seed=seed, multi_dataset=multi,
+                         episodes_between_dataset_switch=k_switch, dynamic_features=dyn, **kw)
+    obs, _ = dev.reset()
+    H.assert_bits(obs.cpu().numpy(), o.reset(), "reset obs")
+    rng = np.random.default_rng(seed)
+    for k in range(K):
+        a = rng.integers(-1, len(positions), size=n_envs)          # -1 = hold
+        dev.step(torch.as_tensor(a, device=dev.device))
+        o.step(a)
+        H.assert_bits(dev._obs.cpu().numpy(), o.obs, f"step {k} obs")
+        H.assert_bits(dev._valuation.cpu().numpy(), o.valuation, f"step {k} valuation")
+        H.assert_bits(dev._terminated.cpu().numpy(), o.terminated, f"step {k} terminated")
+        H.assert_bits(dev._truncated.cpu().numpy(), o.truncated, f"step {k} truncated")
+        H.assert_bits(dev._ep_start.cpu().numpy(), o.ep_start, f"step {k} ep_start")
+        H.assert_bits(dev._dataset_idx.cpu().numpy(), o.dataset_idx, f"step {k} dataset")
+        H.assert_close64(dev._reward.cpu().numpy(), o.reward, f"step {k} reward")
+        assert dev._metrics_step[0].item() == o.metrics[0]
+    dev.check_errors()
+    return dev
+
+
+def _series(T, seed, n_features=8):
+    import gym_trading_env_b200 as gte
+    s = gte.frame_to_arrays(gte.make_gbm_ohlcv(T, seed=seed))
+    if n_features != 8:
+        s = gte.SeriesArrays(np.ascontiguousarray(s.features[:, :n_features]), s.price, s.feature_names[:n_features], {}, None)
+    return s
+
+
+@pytest.mark.parametrize("n_envs", [1, 3, 31, 33, 127, 257, 1000])
+def test_env_counts_off_the_tile_sizes(n_envs):
+    dev = _run([_series(900, 1)], n_envs, 70, positions=[-1, 0, 1, 2], windows=16, duration=20)
+    assert dev.obs_variant == "tma"
+
+
+@pytest.mark.parametrize("windows,n_features,variant", [
+    (2, 8, "auto"), (2, 8, "generic"), (4, 2, "vec"), (6, 8, "tma"),      # tiny windows
+    (5, 5, "auto"), (7, 3, "auto"), (9, 8, "auto"),                        # odd windows / row sizes -> vec or generic
+    (128, 8, "auto"), (200, 8, "auto"), (1, 8, "auto"),                    # long windows (smaller TMA groups), W=1
+    (64, 1, "auto"), (64, 14, "auto"),                                     # 1 and 14 static features
+])
+def test_window_and_feature_shapes(windows, n_features, variant):
+    _run([_series(1200, 2, n_features)], 300, 45, positions=[-2, 0, 0.5, 2], windows=windows, duration=30, variant=variant)
+
+
+def test_no_dynamic_features_all_variants():
+    for variant in ("tma", "vec", "generic"):
+        _run([_series(800, 3)], 200, 50, positions=[0, 1], windows=8, duration=25, dyn=False, variant=variant)
+
+
+def test_maximum_positions_and_datasets():
+    pos = [round(-3 + 6 * i / 63, 6) for i in range(64)]                   # GTE_MAX_POSITIONS
+    _run([_series(700, 4)], 150, 40, positions=pos, windows=8, duration=20)
+    many = [_series(260 + 7 * k, 100 + k) for k in range(64)]              # GTE_MAX_DATASETS, ragged lengths
+    dev = _run(many, 256, 90, positions=[-1, 0, 1], windows=4, duration=12, multi=True, k_switch=1)
+    assert len(set(dev._dataset_idx.cpu().numpy().tolist())) > 30
+
+
+def test_dataset_barely_longer_than_an_episode_and_max_duration():
+    # T - D - 2(W-1) = 1: every episode starts at the same row; 'max': episodes run to the end of the data
+    _run([_series(60, 6)], 64, 80, positions=[0, 1], windows=8, duration=45)
+    _run([_series(80, 7)], 64, 200, positions=[-1, 1], windows=8, duration="max")
+    _run([_series(50, 8)], 17, 120, positions=[-1, 1], windows=None, duration="max")
