@@ -92,3 +92,41 @@ def test_dataset_barely_longer_than_an_episode_and_max_duration():
     _run([_series(60, 6)], 64, 80, positions=[0, 1], windows=8, duration=45)
     _run([_series(80, 7)], 64, 200, positions=[-1, 1], windows=8, duration="max")
     _run([_series(50, 8)], 17, 120, positions=[-1, 1], windows=None, duration="max")
+
+
+@pytest.mark.parametrize("variant,n_envs", [("tma", 1000), ("tma", 37), ("vec", 333), ("generic", 333), ("nowindow", 333)])
+def test_no_write_lands_outside_the_output_and_state_buffers(variant, n_envs):
+    """Every buffer the kernels write is re-homed between 4 KiB guard bands filled with a byte pattern;
+    after resets and steps with auto-resets the bands must be untouched (compute-sanitizer is closed on
+    this GPU pool, so this is the out-of-bounds check)."""
+    import gym_trading_env_b200 as gte
+    windows = None if variant == "nowindow" else 16
+    env = gte.TradingVectorEnv(_series(700, 11), positions=[-1, 0, 1, 2], windows=windows, trading_fees=1e-4,
+                               borrow_interest_rate=3e-6, max_episode_duration=15, num_envs=n_envs, seed=3, verbose=0,
+                               debug_outputs=True, obs_variant="auto" if variant == "nowindow" else variant)
+    GUARD = 4096
+    bands = []
+    names = ["_obs", "_dyn_ring", "_reward", "_terminated", "_truncated", "_valuation", "_real_position", "_info_idx",
+             "_info_step", "_pre_reset_portfolio", "_asset", "_fiat", "_interest_asset", "_interest_fiat", "_pos_idx",
+             "_step", "_ep_start", "_dataset_idx", "_plan_cursor", "_ds_used", "_ds_episodes", "_metrics_step",
+             "_metrics_total", "_metric_partials", "_error_flag", "_tick_dev", "_block_counter"]
+    for name in names:
+        t = getattr(env, name)
+        nbytes = t.numel() * t.element_size()
+        pad = (-nbytes) % 16
+        big = torch.full((GUARD + nbytes + pad + GUARD,), 0xA5, dtype=torch.uint8, device=env.device)
+        view = big[GUARD:GUARD + nbytes].view(t.dtype).view(t.shape)
+        view.copy_(t)
+        setattr(env, name, view)
+        bands.append((name, big, nbytes))
+    env._build_structs()
+    env.reset()
+    rng = np.random.default_rng(0)
+    for _ in range(60):
+        env.step(torch.as_tensor(rng.integers(0, 4, size=n_envs), device=env.device))
+    env.infos["portfolio_valuation"]
+    torch.cuda.synchronize()
+    assert float(env.get_metrics()["episodes"].item()) > n_envs          # auto-resets happened
+    for name, big, nbytes in bands:
+        assert bool((big[:GUARD] == 0xA5).all()), f"write below {name}"
+        assert bool((big[GUARD + nbytes:] == 0xA5).all()), f"write above {name}"
