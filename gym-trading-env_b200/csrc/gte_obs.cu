@@ -290,6 +290,14 @@ static ObsKernelFn tma_kernel(const TmaConfig& c) {
         case 31202: return obs_tma_coop_kernel<3, 12, 2>;
         case 31204: return obs_tma_coop_kernel<3, 12, 4>;
         case 41204: return obs_tma_coop_kernel<4, 12, 4>;
+        case 40604: return obs_tma_coop_kernel<4, 6, 4>;
+        case 40704: return obs_tma_coop_kernel<4, 7, 4>;
+        case 50604: return obs_tma_coop_kernel<5, 6, 4>;
+        case 50804: return obs_tma_coop_kernel<5, 8, 4>;
+        case 60802: return obs_tma_coop_kernel<6, 8, 2>;
+        case 61202: return obs_tma_coop_kernel<6, 12, 2>;
+        case 81202: return obs_tma_coop_kernel<8, 12, 2>;
+        case 30604: return obs_tma_coop_kernel<3, 6, 4>;
         case 40404: return obs_tma_coop_kernel<4, 4, 4>;
         case 30808: return obs_tma_coop_kernel<3, 8, 8>;
         case 20608: return obs_tma_coop_kernel<2, 6, 8>;
@@ -384,8 +392,12 @@ cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteStat
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 2048 / threads) per_sm = 2048 / threads;
         if (per_sm > 32) per_sm = 32;
-        const int64_t need = ((int64_t)n_envs + 31) / 32;          // work unit = one 32-env tile per CTA
-        const int grid = (int)(need < (int64_t)sms * per_sm ? need : (int64_t)sms * per_sm);
+        // work unit = one 32-env tile; persistent grid of <= SMs x per_sm CTAs, sized so that every CTA gets
+        // the same number of tiles (no straggler wave at mid-size N)
+        const int64_t need = ((int64_t)n_envs + 31) / 32;
+        const int64_t cap = (int64_t)sms * per_sm;
+        const int64_t waves = (need + cap - 1) / cap;
+        const int grid = (int)((need + waves - 1) / waves);
         kern<<<grid, threads, smem, stream>>>(P, D, S, obs, sh, env_begin, env_end);
         return cudaGetLastError();
     }
