@@ -27,3 +27,15 @@ def __getattr__(name):          # torch / the CUDA library are only imported whe
         from ._cabi import build
         return build
     raise AttributeError(name)
+
+
+def register():
+    """Register the batched envs with gymnasium (ids ``TradingEnv-B200-v0`` / ``MultiDatasetTradingEnv-B200-v0``,
+    vector entry points), mirroring the reference's registration (src/gym_trading_env/__init__.py:3-14).
+    Raises ImportError when gymnasium is not installed (it is not part of this image)."""
+    from gymnasium.envs.registration import register as _register
+    _register(id="TradingEnv-B200-v0", vector_entry_point="gym_trading_env_b200.vector_env:TradingVectorEnv",
+              disable_env_checker=True, order_enforce=False)
+    _register(id="MultiDatasetTradingEnv-B200-v0",
+              vector_entry_point="gym_trading_env_b200.vector_env:MultiDatasetTradingVectorEnv",
+              disable_env_checker=True, order_enforce=False)

@@ -177,8 +177,9 @@ class TradingVectorEnv:
     truncated on the host, observations stay device-resident for an on-device policy; the copies
     run on side streams beside the gather kernel); ``autoreset`` (True = in-place); ``cuda_graph``
     (capture one lockstep iteration and replay it: removes the launch overhead at small N; actions
-    are then read from the env's own buffer); ``n_chunks`` (0 = auto: env ranges whose step kernel
-    is pipelined beside the previous range's gather);
+    are then read from the env's own buffer); ``n_chunks`` (0 = library default = 1; k > 1 cuts the envs
+    into k ranges and runs the step kernel of range c+1 beside the gather of range c on a side stream —
+    measured: no gain on B200, kept as an option);
     ``debug_outputs`` (also write the terminal step's idx/step/real_position/portfolio, +48 B/env).
 
     ``reward_function`` must be :func:`basic_reward_function` or a :class:`DeviceReward` from the fused
