@@ -531,7 +531,10 @@ class TradingVectorEnv:
                 # H2D on its own stream: it may run beside the previous iteration's gather.  Out-of-range
                 # actions are flagged by the kernel (positions[position_index] would raise, :234) and the
                 # flag rides back with the results in the host-output modes.
-                self._copy_in.wait_stream(main)
+                if self.output != "hybrid":
+                    self._copy_in.wait_stream(main)          # the last step kernel may still be reading the buffer
+                # (hybrid: step() returned only after the last step kernel's results had reached the host, so the
+                #  buffer is free and the copy may run beside the previous iteration's gather)
                 with torch.cuda.stream(self._copy_in):
                     self._actions_dev.copy_(src, non_blocking=True)
                 main.wait_stream(self._copy_in)
