@@ -448,7 +448,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["label"], "envs_per_gpu": N, "obs_variant": env.obs_variant, "chunks": env.chunks, "cuda_graph": bool(args.cuda_graph),
                        "l2_policy": "inputs larger than L2 (obs %.0f MB + state/ring %.0f MB per step vs 126 MB L2)"
-                                    % (env._obs.numel() * 4 / 1e6, (N * 44 + env._dyn_ring.numel() * 4) / 1e6),
+                                    % (env._obs.numel() * 4 / 1e6, (N * 44 + env._dyn_ring.numel()) / 1e6),
                        "parallelism": f"env-sharded x{world}, dataset replicated, NCCL allreduce of 8 fp64 metrics per iteration"},
             "clocks": clocks, "e2e": e2e, "e2e_full_obs_to_host": e2e_full,
             "gpu_launches": (1 if wl["windows"] is None else 2 * env.chunks) * args.steps, "roofline": roofline, "cpu_baseline": cpu,

@@ -83,7 +83,7 @@ static int check_variant(const char* fn, const GteParams* params, const GteData*
     if (variant == GTE_OBS_VEC && !gte::obs_vec_supported(*params, *data))
         return fail_arg(fn, "GTE_OBS_VEC needs windows>0, 16-byte-multiple windows and window tables");
     if (variant == GTE_OBS_TMA && !gte::obs_tma_supported(*params, *data))
-        return fail_arg(fn, "GTE_OBS_TMA needs the GTE_OBS_VEC conditions, an even window and stage buffers that fit in shared memory");
+        return fail_arg(fn, "GTE_OBS_TMA needs the GTE_OBS_VEC conditions and stage buffers that fit in shared memory");
     return GTE_OK;
 }
 

@@ -127,6 +127,15 @@ __device__ __forceinline__ int next_dataset(const GteParams& P, const GteState& 
     return ds;
 }
 
+// dyn_ring of env i: W f32 real_position values then W u8 position indices (GTE_RING_STRIDE(W) bytes)
+__device__ __forceinline__ void ring_store(const GteParams& P, const GteState& S, int i, int row, float rp, int pos_idx) {
+    const int W = P.windows > 0 ? P.windows : 1;
+    uint8_t* ring = S.dyn_ring + (int64_t)i * GTE_RING_STRIDE(W);
+    const int slot = row % W;
+    reinterpret_cast<float*>(ring)[slot] = rp;
+    ring[4 * W + slot] = (uint8_t)pos_idx;
+}
+
 struct EnvRegs {          // the per-env state a step keeps in registers
     Portfolio pf;
     int pos_idx, step, ep_start, ds;
@@ -173,12 +182,8 @@ __device__ __forceinline__ void reset_env(const GteParams& P, const GteData& D, 
     const double position = P.positions[e.pos_idx];
     const double price = D.price[(int64_t)e.ds * P.t_stride + start];
     e.pf = target_portfolio(position, P.v0, price);                          // :179-183
-    if (P.n_dyn > 0) {                                                       // first obs row: (position, position) :191-192
-        const int W = P.windows > 0 ? P.windows : 1;
-        float2* ring = reinterpret_cast<float2*>(S.dyn_ring) + (int64_t)i * W + (start % W);
-        const float fp = (float)position;
-        *ring = make_float2(fp, fp);
-    }
+    if (P.n_dyn > 0)                                                         // first obs row: (position, position) :191-192
+        ring_store(P, S, i, start, (float)position, e.pos_idx);
 }
 
 }  // namespace gte

@@ -32,7 +32,7 @@ obs_generic_kernel(const GteParams P, const GteData D, const GteState S, float* 
         const int ds = S.dataset_idx[env];
         const int r0 = idx + 1 - sh.W;
         const float* __restrict__ feat = D.features + ((int64_t)ds * P.t_stride + r0) * sh.ns;
-        const float* __restrict__ ring = S.dyn_ring + env * sh.W * 2;
+        const uint8_t* __restrict__ ring = S.dyn_ring + env * (int64_t)GTE_RING_STRIDE(sh.W);
         float* __restrict__ out = obs + env * per_env;
         for (int e = lane; e < per_env; e += G) {
             const int w = e / sh.F, c = e - w * sh.F;
@@ -41,7 +41,9 @@ obs_generic_kernel(const GteParams P, const GteData D, const GteState S, float* 
                 v = __ldg(feat + (int64_t)w * sh.ns + c);
             } else {
                 const int r = r0 + w;
-                v = (r >= ep_start) ? ring[(r % sh.W) * 2 + (c - sh.ns)] : 0.0f;
+                const int slot = r % sh.W;
+                v = (r < ep_start) ? 0.0f
+                  : (c == sh.ns ? (float)P.positions[ring[4 * sh.W + slot]] : reinterpret_cast<const float*>(ring)[slot]);
             }
             out[e] = v;
         }
@@ -75,7 +77,8 @@ obs_vec_kernel(const GteParams P, const GteData D, const GteState S, float* __re
         const int r0 = idx + 1 - sh.W;
         const int s0 = ((r0 % sh.W) + sh.W) % sh.W;            // ring slot of window row 0
         const char* __restrict__ src = window_src(D, sh, ds, r0);
-        const float2* __restrict__ ring = reinterpret_cast<const float2*>(S.dyn_ring) + env * sh.W;
+        const uint8_t* __restrict__ ring = S.dyn_ring + env * (int64_t)GTE_RING_STRIDE(sh.W);
+        const float* __restrict__ ring_rp = reinterpret_cast<const float*>(ring);
         char* __restrict__ dst = reinterpret_cast<char*>(obs) + env * (int64_t)sh.win_bytes;
         for (int j = lane; j < sh.n_vec; j += 32) {
             float4 v = ld_nc_v4(src + 16 * j);
@@ -91,12 +94,12 @@ obs_vec_kernel(const GteParams P, const GteData D, const GteState S, float* __re
                         int slot = s0 + w;
                         if (slot >= sh.W) slot -= sh.W;
                         if (PAIR) {
-                            const float2 d = (r >= ep_start) ? __ldg(ring + slot) : make_float2(0.f, 0.f);
-                            pv[k] = d.x;
-                            pv[k + 1] = d.y;
+                            const bool live = r >= ep_start;
+                            pv[k] = live ? (float)P.positions[__ldg(ring + 4 * sh.W + slot)] : 0.0f;
+                            pv[k + 1] = live ? __ldg(ring_rp + slot) : 0.0f;
                         } else {
-                            const float* rf = reinterpret_cast<const float*>(ring + slot);
-                            pv[k] = (r >= ep_start) ? __ldg(rf + (c - sh.ns)) : 0.0f;
+                            pv[k] = (r < ep_start) ? 0.0f
+                                  : (c == sh.ns ? (float)P.positions[__ldg(ring + 4 * sh.W + slot)] : __ldg(ring_rp + slot));
                         }
                     }
                 }
@@ -151,7 +154,7 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
     __shared__ int4 meta[2][32];                                 // per tile parity: {r0, s0, ep_start, -}
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t win_bytes = (uint32_t)sh.win_bytes;
-    const uint32_t ring_bytes = sh.nd > 0 ? (uint32_t)sh.W * 8u : 0u;
+    const uint32_t ring_bytes = sh.nd > 0 ? (uint32_t)GTE_RING_STRIDE(sh.W) : 0u;   // W f32 real_position + W u8 position idx
     const uint32_t wstage_bytes = win_bytes * G, rstage_bytes = ring_bytes * G;
     unsigned char* wbase = smem_raw;
     unsigned char* rbase = smem_raw + (size_t)WS * wstage_bytes;
@@ -194,7 +197,7 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
                 const int stage = qr % RS, use = qr / RS;
                 if (use > 0) mbar_wait(&empty_r[stage], (uint32_t)(use - 1) & 1u);
                 mbar_expect_tx(&full_r[stage], (uint32_t)nv * ring_bytes);
-                bulk_g2s(rbase + (size_t)stage * rstage_bytes, S.dyn_ring + group_env0(qr) * (int64_t)sh.W * 2,
+                bulk_g2s(rbase + (size_t)stage * rstage_bytes, S.dyn_ring + group_env0(qr) * (int64_t)ring_bytes,
                          (uint32_t)nv * ring_bytes, &full_r[stage]);
             }
         };
@@ -244,15 +247,15 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
                         const int4 m = meta[k & 1][gi * G + g];
                         const int r0 = m.x, s0 = m.y, ep_start = m.z;
                         float* fbuf = reinterpret_cast<float*>(sbuf + (size_t)g * win_bytes);
-                        const float2* rbuf = reinterpret_cast<const float2*>(rbase + (size_t)rs * rstage_bytes + (size_t)g * ring_bytes);
+                        const unsigned char* rbuf = rbase + (size_t)rs * rstage_bytes + (size_t)g * ring_bytes;
+                        const float* rbuf_rp = reinterpret_cast<const float*>(rbuf);
                         for (int s = t; s < sh.W; s += TPE) {
                             int w = s - s0;
                             if (w < 0) w += sh.W;
                             if (r0 + w >= ep_start) {            // rows before the episode start stay zero
-                                const float2 d = rbuf[s];
                                 float* qd = fbuf + w * sh.F + sh.ns;
-                                qd[0] = d.x;
-                                qd[1] = d.y;
+                                qd[0] = (float)P.positions[rbuf[4 * sh.W + s]];     // fp64 -> fp32 as numpy casts (:154)
+                                qd[1] = rbuf_rp[s];
                             }
                         }
                     }
@@ -279,7 +282,7 @@ using ObsKernelFn = void (*)(const GteParams, const GteData, const GteState, flo
 struct TmaConfig { int wstages, rstages, group; };
 
 static size_t tma_smem_bytes(const ObsShape& sh, const TmaConfig& c) {
-    const size_t ring = sh.nd > 0 ? (size_t)sh.W * 8 : 0;
+    const size_t ring = sh.nd > 0 ? (size_t)GTE_RING_STRIDE(sh.W) : 0;
     return (size_t)c.group * ((size_t)c.wstages * sh.win_bytes + (size_t)c.rstages * ring);
 }
 
@@ -298,6 +301,9 @@ static ObsKernelFn tma_kernel(const TmaConfig& c) {
         case 61202: return obs_tma_coop_kernel<6, 12, 2>;
         case 81202: return obs_tma_coop_kernel<8, 12, 2>;
         case 30604: return obs_tma_coop_kernel<3, 6, 4>;
+        case 30804: return obs_tma_coop_kernel<3, 8, 4>;
+        case 31004: return obs_tma_coop_kernel<3, 10, 4>;
+        case 31604: return obs_tma_coop_kernel<3, 16, 4>;
         case 40404: return obs_tma_coop_kernel<4, 4, 4>;
         case 30808: return obs_tma_coop_kernel<3, 8, 8>;
         case 20608: return obs_tma_coop_kernel<2, 6, 8>;
@@ -336,9 +342,7 @@ bool obs_vec_supported(const GteParams& P, const GteData& D) {
 bool obs_tma_supported(const GteParams& P, const GteData& D) {
     if (!obs_vec_supported(P, D)) return false;
     const ObsShape sh = make_shape(P);
-    // the ring of one env (W*8 bytes) must itself be a 16-byte multiple for cp.async.bulk
-    return (sh.nd == 0 || (sh.W * 8) % 16 == 0) && (sh.nd == 0 || sh.nd == 2) &&
-           tma_smem_bytes(sh, tma_config(sh)) <= 200 * 1024;
+    return (sh.nd == 0 || sh.nd == 2) && tma_smem_bytes(sh, tma_config(sh)) <= 200 * 1024;
 }
 
 cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteState& S, float* obs, int variant,

@@ -91,11 +91,7 @@ __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteD
         O.pre_reset_portfolio[3 * N + i] = e.pf.ifi;
     }
     float dyn_pos = (float)P.positions[e.pos_idx], dyn_rp = (float)rp;        // fp64 -> fp32 as numpy casts (:154)
-    if (P.n_dyn > 0) {                                                       // _get_obs write-back (:153-154)
-        const int W = P.windows > 0 ? P.windows : 1;
-        float2* ring = reinterpret_cast<float2*>(S.dyn_ring) + (int64_t)i * W + (idx % W);
-        *ring = make_float2(dyn_pos, dyn_rp);
-    }
+    if (P.n_dyn > 0) ring_store(P, S, i, idx, dyn_rp, e.pos_idx);             // _get_obs write-back (:153-154)
     acc.sum_rew = dadd(acc.sum_rew, rew);
     if (done || trunc) {                                                     // :269-271 calculate_metrics
         acc.episodes += 1;

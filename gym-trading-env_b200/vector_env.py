@@ -351,7 +351,7 @@ class TradingVectorEnv:
         self._pos_idx, self._step, self._ep_start, self._dataset_idx = i32(N), i32(N), i32(N), i32(N)
         self._plan_cursor, self._ds_episodes = i32(N), i32(N)
         self._ds_used = torch.zeros(N, dtype=torch.int64, device=dev)
-        self._dyn_ring = torch.zeros(N, W, 2, dtype=torch.float32, device=dev)
+        self._dyn_ring = torch.zeros(N, ((W * 5 + 15) // 16) * 16, dtype=torch.uint8, device=dev)   # GTE_RING_STRIDE(W)
         self._error_flag = i32(1)
         self._tick_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self._reset_plan = None

@@ -29,10 +29,11 @@
 extern "C" {
 #endif
 
-#define GTE_VERSION 101            /* 0.1.1 */
+#define GTE_VERSION 102            /* 0.1.2 */
 #define GTE_MAX_POSITIONS 64
 #define GTE_MAX_DATASETS 64        /* least-used rotation keeps a 64-bit "used this round" mask per env */
 #define GTE_N_METRICS 8
+#define GTE_RING_STRIDE(W) ((((W) * 5) + 15) / 16 * 16)   /* bytes of dyn_ring per env */
 #define GTE_STEP_THREADS 256       /* envs per CTA of the step kernel; metric_partials has ceil(N/256) rows */
 
 #define GTE_OK 0
@@ -119,8 +120,10 @@ typedef struct GteState {
     int32_t* step;                   /* i32 [N]  TradingEnv._step                                      */
     int32_t* ep_start;               /* i32 [N]  _idx at reset (episode start row)                     */
     int32_t* dataset_idx;            /* i32 [N]  which dataset the env is on                           */
-    float* dyn_ring;                 /* f32 [N, max(windows,1), 2]: (position, real_position) of row r
-                                        at slot r % W; rows before ep_start read as zero               */
+    uint8_t* dyn_ring;               /* u8 [N, GTE_RING_STRIDE(W)], W = max(windows,1).  Per env: W f32
+                                        real_position values, then W u8 position INDICES (the dynamic
+                                        feature "position" is float32(positions[index])), padded to 16 B;
+                                        row r lives at slot r % W, rows before ep_start read as zero   */
     int32_t* plan_cursor;            /* i32 [N]  next episode slot of reset_plan                       */
     uint64_t* ds_used;               /* u64 [N]  datasets used in the current rotation round (:383)    */
     int32_t* ds_episodes;            /* i32 [N]  _episodes_on_this_dataset (:381,394)                  */
