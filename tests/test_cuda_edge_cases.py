@@ -130,3 +130,39 @@ def test_no_write_lands_outside_the_output_and_state_buffers(variant, n_envs):
     for name, big, nbytes in bands:
         assert bool((big[:GUARD] == 0xA5).all()), f"write below {name}"
         assert bool((big[GUARD + nbytes:] == 0xA5).all()), f"write above {name}"
+
+
+def test_long_soak_against_the_oracle_with_every_episode_end_kind():
+    """1 500 lockstep iterations of 2 048 envs on a volatile series with extreme leverage: thousands of
+    valuation stops, duration truncations and end-of-data truncations, every one followed by an in-kernel
+    Philox reset — compared with the oracle every 25 iterations (state bit-exact implies the steps between)."""
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    arr = gte.frame_to_arrays(gte.make_gbm_ohlcv(2500, seed=21, sigma=0.02))
+    pos = [-4, -1, 0, 1, 4]
+    kw = dict(positions=pos, windows=16, trading_fees=5e-4, borrow_interest_rate=5e-5,
+              portfolio_initial_value=1000, max_episode_duration="max")
+    N, K = 2048, 1500
+    dev = gte.TradingVectorEnv(arr, num_envs=N, seed=17, verbose=0, **kw)
+    o = orc.OracleVecEnv(arr.features, arr.price, num_envs=N, seed=17, **kw)
+    dev.reset()
+    o.reset()
+    g = torch.Generator(device=dev.device)
+    g.manual_seed(5)
+    acts = torch.randint(0, len(pos), (K, N), generator=g, device=dev.device, dtype=torch.int64)
+    acts_h = acts.cpu().numpy()
+    c = lambda t: t.cpu().numpy()   # noqa: E731
+    for k in range(K):
+        dev.step(acts[k])
+        o.step(acts_h[k], want_obs=(k % 25 == 24))
+        if k % 25 == 24:
+            H.assert_bits(c(dev._obs), o.obs, f"step {k} obs")
+            for nm in ("asset", "fiat", "interest_asset", "interest_fiat"):
+                H.assert_bits(c(getattr(dev, "_" + nm)), getattr(o, nm), f"step {k} {nm}")
+            H.assert_bits(c(dev._ep_start), o.ep_start, f"step {k} ep_start")
+            H.assert_bits(c(dev._step), o.step_, f"step {k} step")
+            H.assert_bits(c(dev._pos_idx), o.pos_idx, f"step {k} pos_idx")
+            H.assert_bits(c(dev._valuation), o.valuation, f"step {k} valuation")
+    m = c(dev._metrics_total)
+    assert m[1] > 1000 and m[2] > 100 and m[0] <= m[1] + m[2]   # valuation stops and truncations both occurred
+    dev.check_errors()
