@@ -19,13 +19,18 @@ __global__ void __launch_bounds__(kStepThreads, MIN_CTAS)
 step_kernel(const GteParams P, const GteData D, const GteState S, const int64_t* __restrict__ actions,
             const GteStepOut O, int autoreset, int tiles_per_cta, int env_begin, int env_end, int chunk_flags,
             float* __restrict__ obs_rows) {
+    // the positions table in shared memory: a per-lane index into the kernel-parameter constant bank would be
+    // replayed once per distinct address
+    __shared__ double s_pos[GTE_MAX_POSITIONS];
+    if (threadIdx.x < GTE_MAX_POSITIONS) s_pos[threadIdx.x] = P.positions[threadIdx.x];
+    __syncthreads();
     MetricAcc acc;
     const uint64_t tick = *S.tick;
     const int64_t base0 = (int64_t)env_begin + (int64_t)blockIdx.x * tiles_per_cta * kStepThreads;
     for (int t = 0; t < tiles_per_cta; ++t) {
         const int64_t i = base0 + (int64_t)t * kStepThreads + threadIdx.x;
         if (i < env_end) {
-            const StepThreadOut r = step_env(P, D, S, actions, O, tick, autoreset, (int)i, acc);
+            const StepThreadOut r = step_env(P, D, S, actions, O, tick, autoreset, (int)i, acc, s_pos);
             if (obs_rows != nullptr) {
                 // windows=None (environments.py:156-157): the observation is the single row idx, written by the
                 // env's own thread -> one launch per lockstep iteration at small N

@@ -22,7 +22,7 @@ struct MetricAcc {           // per-thread accumulators (deterministic: fixed ti
 __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteData& D, const GteState& S,
                                                   const int64_t* __restrict__ actions,
                                                   const GteStepOut& O, uint64_t tick, int autoreset,
-                                                  int i, MetricAcc& acc) {
+                                                  int i, MetricAcc& acc, const double* __restrict__ pos_tab) {
     EnvRegs e;
     e.pf.asset = S.asset[i];
     e.pf.fiat = S.fiat[i];
@@ -52,8 +52,8 @@ __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteD
     const double prev_val = (e.step == 0) ? P.v0 : val0;
 
     if (a >= 0) {                                                            // :234 (None = hold)
-        const double target = P.positions[a];
-        if (target != P.positions[e.pos_idx]) {                              // :213-215 value compare
+        const double target = pos_tab[a];
+        if (target != pos_tab[e.pos_idx]) {                              // :213-215 value compare
             trade_to_position(e.pf, target, p0, P.fee, val0);                // :204-211
             e.pos_idx = (int)a;
         }
@@ -90,7 +90,7 @@ __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteD
         O.pre_reset_portfolio[2 * N + i] = e.pf.ia;
         O.pre_reset_portfolio[3 * N + i] = e.pf.ifi;
     }
-    float dyn_pos = (float)P.positions[e.pos_idx], dyn_rp = (float)rp;        // fp64 -> fp32 as numpy casts (:154)
+    float dyn_pos = (float)pos_tab[e.pos_idx], dyn_rp = (float)rp;        // fp64 -> fp32 as numpy casts (:154)
     if (P.n_dyn > 0) ring_store(P, S, i, idx, dyn_rp, e.pos_idx);             // _get_obs write-back (:153-154)
     acc.sum_rew = dadd(acc.sum_rew, rew);
     if (done || trunc) {                                                     // :269-271 calculate_metrics
@@ -103,7 +103,7 @@ __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteD
         if (autoreset) {
             reset_env(P, D, S, i, tick, e);                                  // in-place auto-reset
             idx = e.ep_start;
-            dyn_pos = dyn_rp = (float)P.positions[e.pos_idx];                // first row: (position, position) :191-192
+            dyn_pos = dyn_rp = (float)pos_tab[e.pos_idx];                // first row: (position, position) :191-192
             if (P.n_datasets > 1) S.dataset_idx[i] = e.ds;
         }
     }
