@@ -64,3 +64,25 @@ def test_product_package_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "gte_oracle" not in text and "libgte_oracle" not in text, f
+
+
+def test_built_library_is_sm100a_and_uses_tma_and_mbarriers():
+    """SASS evidence (B200_PROFILING.md): the gather kernel moves its windows with TMA bulk copies (UBLKCP)
+    tracked by mbarriers (SYNCS), the library is built for sm_100a only, and the fp64 money math is not
+    contracted into FMA in the transition kernel's portfolio arithmetic (DMUL/DADD present)."""
+    import shutil
+    import subprocess
+    from gym_trading_env_b200 import _cabi
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    if not os.path.exists(_cabi.LIB_PATH):
+        _cabi.build()
+    elf = subprocess.run([cuobjdump, "-lelf", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf and "sm_90" not in elf and "sm_80" not in elf
+    sass = subprocess.run([cuobjdump, "-sass", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    gather = sass[sass.index("obs_tma_coop_kernel"):]
+    assert "UBLKCP" in gather                      # cp.async.bulk (TMA 1-D) global<->shared
+    assert "SYNCS" in gather                       # mbarrier arrive/expect_tx/try_wait
+    step = sass[sass.index("step_kernel"):]
+    assert "DMUL" in step and "DADD" in step and "MUFU.RCP64H" in step   # fp64 multiply/add kept separate, IEEE divide
