@@ -180,7 +180,10 @@ class TradingVectorEnv:
     are then read from the env's own buffer); ``n_chunks`` (0 = library default = 1; k > 1 cuts the envs
     into k ranges and runs the step kernel of range c+1 beside the gather of range c on a side stream —
     measured: no gain on B200, kept as an option);
-    ``debug_outputs`` (also write the terminal step's idx/step/real_position/portfolio, +48 B/env).
+    ``debug_outputs`` (also write the terminal step's idx/step/real_position/portfolio, +48 B/env);
+    ``final_obs`` (gymnasium's SAME_STEP ``final_obs``: ``env.final_obs`` keeps, for every env whose episode
+    ended in this step, the observation ``step()`` itself returned before the in-place reset
+    (environments.py:272); costs a second gather, off by default).
 
     ``reward_function`` must be :func:`basic_reward_function` or a :class:`DeviceReward` from the fused
     catalogue (log / simple return with scale and clip), and ``dynamic_feature_functions`` the two
@@ -198,7 +201,7 @@ class TradingVectorEnv:
                  max_episode_duration="max", verbose=1, name="Stock", render_mode="logs", *,
                  num_envs=1, device=None, seed=0, env_id_offset=0, done_valuation_ratio=0.7,
                  reset_plan=None, obs_variant="auto", output="torch", autoreset=True,
-                 debug_outputs=False, cuda_graph=False, n_chunks=0, _multi_dataset=False, _episodes_between_dataset_switch=1):
+                 debug_outputs=False, cuda_graph=False, n_chunks=0, final_obs=False, _multi_dataset=False, _episodes_between_dataset_switch=1):
         self._lib = _cabi.load()                      # fails loudly when the CUDA library is missing
         if not torch.cuda.is_available():
             raise RuntimeError("gym_trading_env_b200 needs a CUDA device (no CPU fallback)")
@@ -261,6 +264,8 @@ class TradingVectorEnv:
         self.debug_outputs = bool(debug_outputs)
         self.cuda_graph = bool(cuda_graph)
         self.n_chunks = int(n_chunks)
+        self.keep_final_obs = bool(final_obs)
+        self.final_obs = None
         self._graph = None
         self._copy_in = self._copy_out = None
         self._track_ids = None
@@ -552,6 +557,20 @@ class TradingVectorEnv:
             return ret
 
     def _step_launch(self, act, main):
+        if self.keep_final_obs and self.autoreset:
+            # step without the in-kernel reset, gather the terminal observations, keep those of the ended envs,
+            # then reset exactly those envs and gather again (what a SAME_STEP vector env returns)
+            if self.final_obs is None:
+                self.final_obs = torch.zeros_like(self._obs)
+            self._launch_step(C.c_void_p(act.data_ptr()), autoreset=False)
+            self._launch_obs()
+            ended = (self._terminated | self._truncated)
+            shape = (self.num_envs,) + (1,) * (self._obs.dim() - 1)
+            torch.where(ended.view(shape).bool(), self._obs, self.final_obs, out=self.final_obs)
+            self._launch_reset(C.c_void_p(ended.data_ptr()), first=False)
+            self._tick -= 1                                 # one public call = one info version
+            self._launch_obs()
+            return self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), self.infos
         if self.output == "hybrid":
             # reward / flags leave for the host right after the step kernel, beside the gather
             hb = self._host_buffers()

@@ -287,3 +287,25 @@ def test_tracked_history_reproduces_the_reference_history_rows():
     starts = df[df["new_episode"]]
     assert (starts["portfolio_valuation"] == 1000.0).all() and (starts["step"] == 0).all()
     assert starts["idx"].tolist() == g["plan"][0, :, 0].tolist()
+
+
+def test_final_obs_mode_keeps_the_terminal_observation():
+    """gymnasium SAME_STEP semantics (hazard H8): with final_obs=True the observation step() itself returned
+    for an ended episode (golden `step_obs`) is kept in env.final_obs, obs is the reset observation."""
+    import torch
+    g = H.load_golden("c3_windows_leveraged")
+    env = H.make_device_env(g, final_obs=True)
+    obs, _ = env.reset()
+    H.assert_bits(obs.cpu().numpy(), g["obs0"], "reset obs")
+    seen = 0
+    for k in range(g["actions"].shape[0]):
+        obs, rew, term, trunc, _ = env.step(torch.as_tensor(g["actions"][k], device=env.device))
+        H.assert_bits(obs.cpu().numpy(), g["obs"][k], f"step {k} obs (post-reset)")
+        ended = (g["terminated"][k] | g["truncated"][k]).astype(bool)
+        H.assert_bits(term.cpu().numpy() | trunc.cpu().numpy(), ended, f"step {k} ended")
+        if ended.any():
+            H.assert_bits(env.final_obs.cpu().numpy()[ended], g["step_obs"][k][ended], f"step {k} final_obs")
+            seen += int(ended.sum())
+        H.assert_bits(env._valuation.cpu().numpy(), g["valuation"][k], f"step {k} valuation")
+        H.assert_bits(env.idx.cpu().numpy(), g["post_idx"][k], f"step {k} post idx")
+    assert seen >= 30
