@@ -6,9 +6,10 @@
 //   vec     : one warp per env; 128-bit ld.global.nc from the 16-byte-aligned window table (rows in the
 //             reference's own [t, F] layout, dynamic columns zero), dynamic columns patched in
 //             registers from the per-env ring, 128-bit coalesced st.global.  No shared memory.
-//   tma     : one warp per env per pipeline stage; cp.async.bulk (TMA, 1-D) pulls the whole window
-//             global->shared, lanes patch the dynamic columns in shared memory, cp.async.bulk pushes
-//             the finished window shared->global.  The LSU only touches the 8-byte ring entries.
+//   tma     : warp-specialised producer/consumer pipeline: cp.async.bulk (TMA, 1-D) pulls whole windows and
+//             the envs' dynamic-feature rings global->shared, consumer warps patch the dynamic columns in
+//             shared memory, cp.async.bulk pushes groups of finished windows shared->global.  The LSU only
+//             touches 12 bytes of per-env metadata.
 #include <cstdlib>
 
 #include "gte_tma.cuh"
