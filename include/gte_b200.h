@@ -15,6 +15,8 @@
  *    duration of the call (the caller owns every buffer; outputs are overwritten in place).
  *  - calls only enqueue work on `stream` (a cudaStream_t passed as void*; NULL = default stream)
  *    and return without synchronising.
+ *  - the library keeps a few process-wide caches (SM count, kernel attributes, side stream): make the calls
+ *    from one host thread at a time.
  *  - return value: 0 = success, GTE_ERR_ARG (-1) = bad argument, GTE_ERR_CUDA (-2) = CUDA error;
  *    gte_last_error() returns a thread-local message for the last failing call.
  *  - all money math is IEEE fp64 round-to-nearest in the reference's exact operation order with
