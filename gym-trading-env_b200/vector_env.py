@@ -617,6 +617,36 @@ class TradingVectorEnv:
         self._host = None
         self._graph = None
 
+    def rollout(self, actions, keep_obs=False):
+        """Advance K lockstep iterations from a device tensor of actions ``[K, N]`` (int64) without touching the
+        host between them; returns dict of device tensors ``reward [K, N]`` (f64), ``terminated`` / ``truncated``
+        ``[K, N]`` (bool), ``valuation [K, N]`` (terminal-step valuation) and, with ``keep_obs``, ``obs [K, N, ...]``.
+        The open-loop driver for pre-computed action streams (replay, random-policy baselines, benchmarks)."""
+        if not (isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dim() == 2
+                and actions.shape[1] == self.num_envs):
+            raise ValueError("rollout() needs a CUDA int64 tensor of shape [K, num_envs]")
+        actions = actions.to(torch.int64).contiguous()
+        K, N, dev = actions.shape[0], self.num_envs, self.device
+        out = {"reward": torch.empty(K, N, dtype=torch.float64, device=dev),
+               "terminated": torch.empty(K, N, dtype=torch.bool, device=dev),
+               "truncated": torch.empty(K, N, dtype=torch.bool, device=dev),
+               "valuation": torch.empty(K, N, dtype=torch.float64, device=dev)}
+        if keep_obs:
+            out["obs"] = torch.empty((K,) + tuple(self._obs.shape), dtype=torch.float32, device=dev)
+        saved, self.output = self.output, "torch"
+        try:
+            for k in range(K):
+                obs, rew, term, trunc, _ = self.step(actions[k])
+                out["reward"][k].copy_(rew)
+                out["terminated"][k].copy_(term)
+                out["truncated"][k].copy_(trunc)
+                out["valuation"][k].copy_(self._valuation)
+                if keep_obs:
+                    out["obs"][k].copy_(obs)
+        finally:
+            self.output = saved
+        return out
+
     # ------------------------------------------------------------------ History of tracked envs (utils/history.py)
     def track(self, env_indices, max_steps=100_000):
         """Keep a device-side per-step log — the reference's ``History`` rows (environments.py:186-197,

@@ -309,3 +309,20 @@ def test_final_obs_mode_keeps_the_terminal_observation():
         H.assert_bits(env._valuation.cpu().numpy(), g["valuation"][k], f"step {k} valuation")
         H.assert_bits(env.idx.cpu().numpy(), g["post_idx"][k], f"step {k} post idx")
     assert seen >= 30
+
+
+def test_rollout_equals_stepping_one_by_one():
+    import torch
+    import gym_trading_env_b200 as gte
+    arr = gte.frame_to_arrays(gte.make_gbm_ohlcv(1500, seed=4))
+    kw = dict(positions=[-1, 0, 1], windows=8, trading_fees=1e-4, max_episode_duration=30, num_envs=500, seed=2, verbose=0)
+    a, b = gte.TradingVectorEnv(arr, **kw), gte.TradingVectorEnv(arr, **kw)
+    a.reset(); b.reset()
+    g = torch.Generator(device=a.device); g.manual_seed(0)
+    acts = torch.randint(0, 3, (40, 500), generator=g, device=a.device)
+    out = a.rollout(acts, keep_obs=True)
+    for k in range(40):
+        obs, rew, term, trunc, _ = b.step(acts[k])
+        assert torch.equal(out["obs"][k].view(torch.int32), obs.view(torch.int32))
+        assert torch.equal(out["reward"][k], rew) and torch.equal(out["terminated"][k], term) and torch.equal(out["truncated"][k], trunc)
+    assert torch.equal(a._metrics_total, b._metrics_total)
