@@ -216,7 +216,7 @@ def run_reference_arm(args, wl, rank):
     env.reset()
     rng = np.random.default_rng(1234)
     acts = rng.integers(0, len(wl["positions"]), size=(16, n_sample))
-    inner = 200                                   # lockstep iterations per bench "step" (bounded sample)
+    inner = 1000                                  # lockstep iterations per bench "step" (bounded sample, ~50 ms)
     for _ in range(args.warmup):
         env.rollout(acts, inner)
     t0 = time.perf_counter()
