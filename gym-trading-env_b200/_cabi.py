@@ -35,6 +35,7 @@ class GteParams(C.Structure):
         ("n_datasets", C.c_int32), ("initial_position_idx", C.c_int32),
         ("episodes_between_switch", C.c_int32), ("plan_episodes", C.c_int32),
         ("multi_dataset", C.c_int32), ("reward_kind", C.c_int32),
+        ("n_limit_positions", C.c_int32), ("reserved0", C.c_int32),
         ("t_stride", C.c_int64), ("env_id_offset", C.c_int64), ("seed", C.c_uint64),
         ("fee", C.c_double), ("rate", C.c_double), ("v0", C.c_double), ("done_ratio", C.c_double),
         ("reward_scale", C.c_double), ("reward_lo", C.c_double), ("reward_hi", C.c_double),
@@ -45,6 +46,7 @@ class GteParams(C.Structure):
 class GteData(C.Structure):
     _fields_ = [
         ("features", C.c_void_p), ("price", C.c_void_p), ("lengths", C.c_void_p),
+        ("high", C.c_void_p), ("low", C.c_void_p),
         ("window_table", C.c_void_p * 4), ("window_table_ds_stride", C.c_int64),
     ]
 
@@ -55,7 +57,8 @@ class GteState(C.Structure):
         ("interest_fiat", C.c_void_p), ("pos_idx", C.c_void_p), ("step", C.c_void_p),
         ("ep_start", C.c_void_p), ("dataset_idx", C.c_void_p), ("dyn_ring", C.c_void_p),
         ("plan_cursor", C.c_void_p), ("ds_used", C.c_void_p), ("ds_episodes", C.c_void_p),
-        ("reset_plan", C.c_void_p), ("error_flag", C.c_void_p), ("tick", C.c_void_p),
+        ("reset_plan", C.c_void_p), ("limit_price", C.c_void_p), ("limit_seq", C.c_void_p),
+        ("error_flag", C.c_void_p), ("tick", C.c_void_p),
     ]
 
 

@@ -45,6 +45,8 @@ int check_common(const char* fn, const GteParams* p, const GteData* d, const Gte
     GTE_REQUIRE(fn, p->n_dyn == 0 || s->dyn_ring != nullptr);
     GTE_REQUIRE(fn, s->plan_cursor && s->ds_used && s->ds_episodes && s->error_flag && s->tick);
     GTE_REQUIRE(fn, p->plan_episodes == 0 || s->reset_plan != nullptr);
+    GTE_REQUIRE(fn, p->n_limit_positions >= 0 && p->n_limit_positions <= p->n_positions);
+    GTE_REQUIRE(fn, p->n_limit_positions == 0 || (s->limit_price && s->limit_seq && d->high && d->low));
     return GTE_OK;
 }
 

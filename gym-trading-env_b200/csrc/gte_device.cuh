@@ -182,6 +182,8 @@ __device__ __forceinline__ void reset_env(const GteParams& P, const GteData& D, 
     const double position = P.positions[e.pos_idx];
     const double price = D.price[(int64_t)e.ds * P.t_stride + start];
     e.pf = target_portfolio(position, P.v0, price);                          // :179-183
+    for (int k = 0; k < P.n_limit_positions; ++k)                            // self._limit_orders = {} (:168)
+        S.limit_price[(int64_t)i * P.n_positions + S.limit_seq[k]] = __longlong_as_double(0x7ff8000000000000ll);
     if (P.n_dyn > 0)                                                         // first obs row: (position, position) :191-192
         ring_store(P, S, i, start, (float)position, e.pos_idx);
 }

@@ -60,6 +60,18 @@ __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteD
     }
     idx += 1;                                                                // :235
     e.step += 1;                                                             // :236
+    if (P.n_limit_positions > 0) {                                           // _take_action_order_limit (:217-223)
+        const double hi = __ldg(D.high + (int64_t)e.ds * P.t_stride + idx);
+        const double lo = __ldg(D.low + (int64_t)e.ds * P.t_stride + idx);
+        for (int k = 0; k < P.n_limit_positions; ++k) {                      // dict insertion order (:220)
+            const int pk = S.limit_seq[k];
+            const double lim = S.limit_price[(int64_t)i * P.n_positions + pk];
+            if (lim == lim && pos_tab[pk] != pos_tab[e.pos_idx] && lim <= hi && lim >= lo) {   // :221
+                trade_to_position(e.pf, pos_tab[pk], lim, P.fee, valorisation(e.pf, lim));       // :222 price = limit
+                e.pos_idx = pk;
+            }
+        }
+    }
     update_interest(e.pf, P.rate);                                           // :240
     const double val = valorisation(e.pf, p1);                               // :241
     const bool done = ddiv(val, P.v0) <= P.done_ratio;                       // :246

@@ -269,6 +269,7 @@ class TradingVectorEnv:
         self._graph = None
         self._copy_in = self._copy_out = None
         self._track_ids = None
+        self._limit_price = None
         self._obs_variant = _cabi.OBS_VARIANTS[obs_variant]
         self._multi = bool(_multi_dataset)
         self._k_switch = int(_episodes_between_dataset_switch)
@@ -616,6 +617,49 @@ class TradingVectorEnv:
     def close(self):
         self._host = None
         self._graph = None
+
+    def add_limit_order(self, position, limit, persistent=False, env_ids=None):
+        """``TradingEnv.add_limit_order(position, limit, persistent)`` (environments.py:227-231) for every env, or
+        for ``env_ids``: at each following step, after the index has advanced, an env whose position differs from
+        ``position`` and whose bar contains the price (``low <= limit <= high``) rebalances to ``position`` AT THE
+        LIMIT PRICE (:217-223).  ``limit`` is a scalar or one value per selected env.  Orders are tried in the order
+        in which their positions first received one (the reference iterates its dict in insertion order) and are
+        cleared by reset() and by the in-kernel auto-reset, like ``self._limit_orders = {}`` (:168) — re-add them
+        for the envs whose episode ended.  Only ``persistent=True`` is supported: the reference's non-persistent
+        branch deletes from the dict it is iterating and raises RuntimeError as soon as such an order executes."""
+        if not persistent:
+            raise NotImplementedError(
+                "persistent=False is not supported: in the reference a non-persistent order raises RuntimeError "
+                "('dictionary changed size during iteration', environments.py:220-223) when it executes")
+        if position not in self.positions:
+            raise ValueError("position must be one of `positions`")
+        if any("high" not in srs.info or "low" not in srs.info for srs in self._series):
+            raise ValueError("limit orders need 'high' and 'low' columns in every dataset (environments.py:221)")
+        N, P, dev = self.num_envs, len(self.positions), self.device
+        if self._limit_price is None:
+            hi = np.ones((self._n_ds, self._t_stride), dtype=np.float64)
+            lo = np.ones((self._n_ds, self._t_stride), dtype=np.float64)
+            for k, srs in enumerate(self._series):
+                hi[k, :srs.length], lo[k, :srs.length] = srs.info["high"], srs.info["low"]
+            self._high, self._low = torch.from_numpy(hi).to(dev), torch.from_numpy(lo).to(dev)
+            self._limit_price = torch.full((N, P), float("nan"), dtype=torch.float64, device=dev)
+            self._limit_seq_host = []
+            self._limit_seq = torch.zeros(P, dtype=torch.int32, device=dev)
+            self._D.high, self._D.low = self._high.data_ptr(), self._low.data_ptr()
+            self._S.limit_price, self._S.limit_seq = self._limit_price.data_ptr(), self._limit_seq.data_ptr()
+            self._graph = None                                   # kernel arguments changed: re-capture
+        pk = self.positions.index(position)
+        if pk not in self._limit_seq_host:
+            self._limit_seq_host.append(pk)
+            self._limit_seq[:len(self._limit_seq_host)] = torch.tensor(self._limit_seq_host, dtype=torch.int32, device=dev)
+            self._P.n_limit_positions = len(self._limit_seq_host)
+            self._graph = None
+        lim = torch.as_tensor(limit, dtype=torch.float64, device=dev)
+        if env_ids is None:
+            self._limit_price[:, pk] = lim
+        else:
+            ids = torch.as_tensor(np.asarray(env_ids), dtype=torch.int64, device=dev)
+            self._limit_price[ids, pk] = lim
 
     def rollout(self, actions, keep_obs=False):
         """Advance K lockstep iterations from a device tensor of actions ``[K, N]`` (int64) without touching the

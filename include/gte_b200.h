@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GTE_VERSION 102            /* 0.1.2 */
+#define GTE_VERSION 103            /* 0.1.3 */
 #define GTE_MAX_POSITIONS 64
 #define GTE_MAX_DATASETS 64        /* least-used rotation keeps a 64-bit "used this round" mask per env */
 #define GTE_N_METRICS 8
@@ -86,6 +86,8 @@ typedef struct GteParams {
     int32_t plan_episodes;           /* E of reset_plan[N,E,3]; 0 = draw resets from Philox            */
     int32_t multi_dataset;           /* 1 = MultiDatasetTradingEnv.reset semantics (:393-400)          */
     int32_t reward_kind;             /* enum GteRewardKind: which fused reward functor (:50-51 `reward_function`) */
+    int32_t n_limit_positions;       /* how many positions carry limit orders (0 = feature off, :217-231)          */
+    int32_t reserved0;
     int64_t t_stride;                /* rows allocated per dataset in `price` / `features`             */
     int64_t env_id_offset;           /* global index of env 0 (multi-GPU sharding; keys the RNG)       */
     uint64_t seed;                   /* Philox key                                                     */
@@ -104,6 +106,8 @@ typedef struct GteData {
     const float* features;           /* f32 [n_datasets, t_stride, n_static]  (_obs_array static part, :141) */
     const double* price;             /* f64 [n_datasets, t_stride]            (_price_array, :143)            */
     const int32_t* lengths;          /* i32 [n_datasets]  len(df) of each dataset                              */
+    const double* high;              /* f64 [n_datasets, t_stride] "high" column, or NULL (only limit orders read it, :221) */
+    const double* low;               /* f64 [n_datasets, t_stride] "low" column, or NULL                                   */
     /* 16-byte-aligned window tables for the vector/TMA gather: copy c holds rows in the reference's
      * own [t, n_static+n_dyn] layout (dynamic columns zero) shifted so that a window starting at row
      * r0 with (r0*row_bytes) % 16 == 4*c starts on a 16-byte boundary.  NULL where unused. */
@@ -130,6 +134,10 @@ typedef struct GteState {
     uint64_t* ds_used;               /* u64 [N]  datasets used in the current rotation round (:383)    */
     int32_t* ds_episodes;            /* i32 [N]  _episodes_on_this_dataset (:381,394)                  */
     const int32_t* reset_plan;       /* i32 [N, E, 3] (start row, position idx, dataset idx) or NULL   */
+    double* limit_price;             /* f64 [N, n_positions]: persistent limit order per target position
+                                        (TradingEnv.add_limit_order :227-231), NaN = none; cleared at reset (:168) */
+    const int32_t* limit_seq;        /* i32 [n_limit_positions]: position indices in the order the orders are tried
+                                        (the reference iterates its dict in insertion order, :220)              */
     int32_t* error_flag;             /* i32 [1]  bit 0: action out of range seen (treated as hold);
                                                  bit 1: an env was stepped past the end of its data    */
     uint64_t* tick;                  /* u64 [1]  event counter keying the Philox draws; every gte_reset /

@@ -42,7 +42,7 @@ typedef struct OrcEnv {
     int32_t plan_episodes;           /* E of plan[N,E,3]; 0 = no plan -> Philox */
     int32_t multi_dataset;           /* 1 = MultiDatasetTradingEnv semantics (:393-400) */
     int32_t reward_kind;             /* 0 = log-return (basic_reward_function :17-18), 1 = simple return */
-    int32_t pad0;
+    int32_t n_limit_positions;       /* positions carrying persistent limit orders (:217-231), 0 = none */
     int64_t t_stride;                /* rows allocated per dataset */
     int64_t env_id_offset;           /* global id of env 0 (multi-GPU sharding) */
     uint64_t seed;
@@ -62,6 +62,9 @@ typedef struct OrcEnv {
     float* dyn_cols;                 /* [N, t_stride, n_dyn]: each env's private dynamic columns (:135-138,153-154) */
     int32_t* touched_lo; int32_t* touched_hi;   /* rows of dyn_cols written since the last zeroing */
     const int32_t* plan;             /* [N, E, 3] (start idx, position idx, dataset idx) or NULL */
+    const double* high; const double* low;   /* [n_datasets, t_stride] "high"/"low" columns (limit orders, :221) */
+    double* limit_price;             /* [N, P] limit per target position, NaN = none (add_limit_order :227-231) */
+    const int32_t* limit_seq;        /* [n_limit_positions] position indices in dict insertion order (:220) */
 } OrcEnv;
 
 /* ------------------------------------------------------------------ Portfolio (utils/portfolio.py) */
@@ -268,6 +271,8 @@ void orc_reset_env(OrcEnv* e, int i, uint64_t tick) {
     orc_target_portfolio(s, position, e->v0, price);                     /* :179-183 */
     e->asset[i] = s[0]; e->fiat[i] = s[1]; e->interest_asset[i] = s[2]; e->interest_fiat[i] = s[3];
     e->prev_val[i] = e->v0;                                              /* :194 */
+    for (int k = 0; k < e->n_limit_positions; ++k)                       /* self._limit_orders = {} (:168) */
+        e->limit_price[(int64_t)i * e->n_positions + e->limit_seq[k]] = NAN;
     orc_write_dyn(e, i, start, (float)position, (float)position);        /* :191-192 + :153-154 */
 }
 
@@ -308,6 +313,17 @@ void orc_step_range(OrcEnv* e, int lo, int hi, const int64_t* actions, uint64_t 
         }
         idx += 1;                                                        /* :235 */
         int step = e->step[i] + 1;                                       /* :236 */
+        if (e->n_limit_positions > 0) {                                  /* _take_action_order_limit, :217-223 */
+            double hi = e->high[(int64_t)ds * e->t_stride + idx], lo = e->low[(int64_t)ds * e->t_stride + idx];
+            for (int k = 0; k < e->n_limit_positions; ++k) {
+                int pk = e->limit_seq[k];
+                double lim = e->limit_price[(int64_t)i * e->n_positions + pk];
+                if (lim == lim && e->positions[pk] != e->positions[e->pos_idx[i]] && lim <= hi && lim >= lo) {  /* :221 */
+                    orc_trade_to_position(s, e->positions[pk], lim, e->fee);   /* :222 _trade(position, price=limit) */
+                    e->pos_idx[i] = pk;
+                }
+            }
+        }
         double p = price[idx];                                           /* :239 */
         orc_update_interest(s, e->rate);                                 /* :240 */
         double val = orc_valorisation(s[0], s[1], s[2], s[3], p);        /* :241 */

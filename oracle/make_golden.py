@@ -33,7 +33,7 @@ RECORD_KEYS = ["obs0", "obs", "step_obs", "idx", "step", "position", "real_posit
                "terminated", "truncated", "asset", "fiat", "interest_asset", "interest_fiat",
                "market_return", "portfolio_return", "post_idx", "post_step", "post_pos_idx",
                "post_dataset", "post_asset", "post_fiat", "post_interest_asset",
-               "post_interest_fiat", "plan", "init_asset", "init_fiat"]
+               "post_interest_fiat", "plan", "init_asset", "init_fiat", "limit_plan"]
 
 
 def btc_frame(rows=2500):
@@ -96,6 +96,11 @@ def make_case(name, dfs, *, n_envs, n_steps, action_seed, hold_fraction=0.0, rew
     params.update(n_envs=n_envs, n_steps=n_steps, action_seed=action_seed, name=name,
                   reference="ten2net/Gym-Trading-Env src/gym_trading_env (unmodified), numpy %s" % np.__version__)
     out = {k: rec[k] for k in RECORD_KEYS}
+    tmax = feats.shape[1]
+    hi, lo = np.ones((len(dfs), tmax)), np.ones((len(dfs), tmax))
+    for k_, d_ in enumerate(dfs):
+        hi[k_, :len(d_)], lo[k_, :len(d_)] = d_["high"].to_numpy(), d_["low"].to_numpy()
+    out.update(high=hi, low=lo)
     out.update(features=feats, price=price, lengths=lengths, actions=actions,
                positions=np.array(positions, np.float64), params=np.array(json.dumps(params)))
     path = os.path.join(OUT, name + ".npz")
@@ -155,6 +160,11 @@ def main():
         make_case("reward_" + rname, [vol], n_envs=6, n_steps=160, action_seed=30, reward=rname,
                   positions=[-2, -1, 0, 1, 2], windows=None, initial_position="random",
                   max_episode_duration=60, max_episodes=16, **common)
+    # persistent limit orders (add_limit_order, environments.py:217-231), re-added after every reset; a hold-heavy
+    # action stream so that the orders, not the actions, move the position most of the time
+    make_case("limit_orders_persistent", [vol], n_envs=6, n_steps=200, action_seed=31, hold_fraction=0.7,
+              positions=[-1, 0, 1, 2], windows=4, initial_position="random", max_episode_duration=60, max_episodes=16,
+              limit_orders=[(2, 0.99), (-1, 1.012), (0, 1.003)], **common)
     # MultiDatasetTradingEnv: ragged datasets, least-used rotation, switch every episode / every 3 episodes
     multi = [gte.make_gbm_ohlcv(T, seed=20 + k) for k, T in enumerate([300, 420, 360, 500])]
     make_case("multi_dataset_k1", multi, n_envs=6, n_steps=260, action_seed=20,

@@ -38,7 +38,7 @@ class _OrcEnv(C.Structure):
         ("n_datasets", C.c_int32), ("initial_position_idx", C.c_int32),
         ("episodes_between_switch", C.c_int32), ("dyn_mode", C.c_int32),
         ("plan_episodes", C.c_int32), ("multi_dataset", C.c_int32),
-        ("reward_kind", C.c_int32), ("pad0", C.c_int32),
+        ("reward_kind", C.c_int32), ("n_limit_positions", C.c_int32),
         ("t_stride", C.c_int64), ("env_id_offset", C.c_int64), ("seed", C.c_uint64),
         ("fee", C.c_double), ("rate", C.c_double), ("v0", C.c_double), ("done_ratio", C.c_double),
         ("reward_scale", C.c_double), ("reward_lo", C.c_double), ("reward_hi", C.c_double),
@@ -49,6 +49,7 @@ class _OrcEnv(C.Structure):
         ("plan_cursor", C.c_void_p), ("ds_used", C.c_void_p), ("ds_episodes", C.c_void_p),
         ("dyn_cols", C.c_void_p), ("touched_lo", C.c_void_p), ("touched_hi", C.c_void_p),
         ("plan", C.c_void_p),
+        ("high", C.c_void_p), ("low", C.c_void_p), ("limit_price", C.c_void_p), ("limit_seq", C.c_void_p),
     ]
 
 
@@ -128,7 +129,7 @@ class OracleVecEnv:
                  initial_position="random", max_episode_duration="max", dynamic_features=True,
                  done_ratio=0.7, seed=0, env_id_offset=0, plan=None, multi_dataset=False,
                  episodes_between_dataset_switch=1, dyn_mode=1, threads=1,
-                 reward_kind=0, reward_scale=1.0, reward_clip=(-np.inf, np.inf)):
+                 reward_kind=0, reward_scale=1.0, reward_clip=(-np.inf, np.inf), high=None, low=None):
         features = np.ascontiguousarray(features, dtype=np.float32)
         price = np.ascontiguousarray(price, dtype=np.float64)
         if features.ndim == 2:
@@ -177,6 +178,13 @@ class OracleVecEnv:
         e.plan_cursor, e.ds_used, e.ds_episodes = _p(self.plan_cursor), _p(self.ds_used), _p(self.ds_episodes)
         e.dyn_cols, e.touched_lo, e.touched_hi = _p(self.dyn_cols), _p(self.touched_lo), _p(self.touched_hi)
         e.plan = _p(self.plan)
+        # limit orders (environments.py:217-231): needs the high / low columns
+        self.high = None if high is None else np.ascontiguousarray(np.asarray(high, np.float64).reshape(n_ds, t_stride))
+        self.low = None if low is None else np.ascontiguousarray(np.asarray(low, np.float64).reshape(n_ds, t_stride))
+        self.limit_price = np.full((N, len(self.positions)), np.nan, np.float64)
+        self.limit_seq = np.zeros(len(self.positions), np.int32)
+        e.high, e.low, e.limit_price, e.limit_seq = _p(self.high), _p(self.low), _p(self.limit_price), _p(self.limit_seq)
+        e.n_limit_positions = 0
         self._e = e
         self._lib = lib()
         self._lib.orc_init_datasets(C.byref(e), self._next_tick())
@@ -197,6 +205,18 @@ class OracleVecEnv:
     @property
     def idx(self):
         return self.ep_start + self.step_
+
+    def add_limit_order(self, position, limit, persistent=True, env_ids=None):
+        """TradingEnv.add_limit_order (environments.py:227-231) for the given envs (default: all)."""
+        assert persistent, "the reference's non-persistent branch raises RuntimeError when it executes (:223)"
+        assert self.high is not None and self.low is not None, "limit orders need the high / low columns"
+        pk = list(self.positions).index(position)
+        n = self._e.n_limit_positions
+        if pk not in self.limit_seq[:n]:
+            self.limit_seq[n] = pk
+            self._e.n_limit_positions = n + 1
+        ids = slice(None) if env_ids is None else np.asarray(env_ids)
+        self.limit_price[ids, pk] = limit
 
     def reset(self, mask=None):
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)

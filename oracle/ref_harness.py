@@ -67,11 +67,14 @@ def run_lockstep(dfs, n_envs, actions, *, positions, windows, trading_fees, borr
                  portfolio_initial_value, initial_position, max_episode_duration,
                  dynamic_features=True, normalize_dyn=True, np_seed=0,
                  multi_dataset=False, episodes_between_dataset_switch=1, max_episodes=None,
-                 reward_function=None):
+                 reward_function=None, limit_orders=None):
     """Run N reference envs for K lockstep iterations; return a dict of recorded arrays.
 
     dfs: list of DataFrames (one unless multi_dataset).  actions: int64 [K, N]; a negative
     action is passed to the reference as ``None`` (= hold, environments.py:234).
+    limit_orders: list of (position, factor): after EVERY reset (which clears the env's orders, :168)
+    ``env.add_limit_order(position, factor * close[start], persistent=True)`` is called in that order; the
+    limits are returned as ``limit_plan[N, E, n_orders]``.
     """
     envmod = import_reference()
     K, N = actions.shape
@@ -112,6 +115,7 @@ def run_lockstep(dfs, n_envs, actions, *, positions, windows, trading_fees, borr
     obs_shape = envs[0].observation_space.shape
     E = max_episodes or 64
     plan = np.full((N, E, 3), -1, dtype=np.int32)
+    limit_plan = np.full((N, E, len(limit_orders or [])), np.nan, dtype=np.float64)
     cursor = np.zeros(N, dtype=np.int64)
 
     def do_reset(i):
@@ -123,6 +127,10 @@ def run_lockstep(dfs, n_envs, actions, *, positions, windows, trading_fees, borr
         if e >= E:
             raise RuntimeError(f"env {i} needs more than max_episodes={E} plan slots")
         plan[i, e] = (env._idx, pos_index(env), ds_of(env))
+        for j, (lpos, factor) in enumerate(limit_orders or []):
+            limit = float(factor * env._price_array[env._idx])
+            env.add_limit_order(lpos, limit, persistent=True)          # environments.py:227-231
+            limit_plan[i, e, j] = limit
         cursor[i] += 1
         return np.array(obs, dtype=np.float32, copy=True), info
 
@@ -178,6 +186,7 @@ def run_lockstep(dfs, n_envs, actions, *, positions, windows, trading_fees, borr
             rec["post_interest_fiat"][k, i] = pf.interest_fiat
 
     rec["plan"] = plan[:, :int(cursor.max())].copy()
+    rec["limit_plan"] = limit_plan[:, :int(cursor.max())].copy()
     rec["init_asset"] = init_state["asset"]; rec["init_fiat"] = init_state["fiat"]
     if tmpdir is not None:
         tmpdir.cleanup()

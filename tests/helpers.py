@@ -46,6 +46,8 @@ def make_oracle(g, dyn_mode=None, plan=True, **over):
         clip = r["reward_clip"]
         kw.update(reward_kind=r["reward_kind"], reward_scale=r["reward_scale"],
                   reward_clip=(-np.inf if clip[0] is None else clip[0], np.inf if clip[1] is None else clip[1]))
+    if p.get("limit_orders"):
+        kw.update(high=g["high"], low=g["low"])
     kw.update(over)
     return orc.OracleVecEnv(g["features"], g["price"], g["lengths"], **kw)
 
@@ -54,9 +56,12 @@ def series_from_golden(g):
     import gym_trading_env_b200 as gte
     out = []
     for k, T in enumerate(g["lengths"]):
+        info = {}
+        if "high" in g:
+            info = {"high": np.ascontiguousarray(g["high"][k, :T]), "low": np.ascontiguousarray(g["low"][k, :T])}
         out.append(gte.SeriesArrays(np.ascontiguousarray(g["features"][k, :T]),
                                     np.ascontiguousarray(g["price"][k, :T]),
-                                    [f"feature_{j}" for j in range(g["features"].shape[2])], {}, None))
+                                    [f"feature_{j}" for j in range(g["features"].shape[2])], info, None))
     return out
 
 
@@ -142,9 +147,23 @@ def assert_close64(a, b, what):
         raise AssertionError(f"{what}: |{a.flat[i]!r} - {b.flat[i]!r}| = {err.flat[i]:.3e} > {tol.flat[i]:.3e}")
 
 
+def _add_planned_orders(adapter, g, env_ids, cursor):
+    """Re-add the golden's limit orders for the envs that were just reset (a reset clears them, :168)."""
+    orders = g["params"].get("limit_orders") or []
+    for j, (lpos, _factor) in enumerate(orders):
+        limits = np.array([g["limit_plan"][i, cursor[i], j] for i in env_ids])
+        adapter.e.add_limit_order(float(lpos), limits, persistent=True, env_ids=np.asarray(env_ids))
+    for i in env_ids:
+        cursor[i] += 1
+
+
 def replay_golden(adapter, g, *, exact_money=True, check_final_obs=False, max_steps=None):
     """Replay the golden action stream and compare every recorded quantity, step by step."""
     obs0 = adapter.reset()
+    has_orders = bool(g["params"].get("limit_orders"))
+    order_cursor = np.zeros(g["actions"].shape[1], dtype=np.int64)
+    if has_orders:
+        _add_planned_orders(adapter, g, list(range(g["actions"].shape[1])), order_cursor)
     assert_bits(obs0, g["obs0"], "reset obs")
     K = g["actions"].shape[0] if max_steps is None else min(max_steps, g["actions"].shape[0])
     money = assert_bits if exact_money else assert_close64
@@ -178,6 +197,8 @@ def replay_golden(adapter, g, *, exact_money=True, check_final_obs=False, max_st
         np.testing.assert_allclose(m[4], np.nansum(g["market_return"][k]), rtol=1e-10, atol=1e-12)
         assert m[5] == g["step"][k][ended].sum(), f"{w} episode length metric"
         np.testing.assert_allclose(m[6], g["reward"][k].sum(), rtol=1e-9, atol=1e-12)
+        if has_orders and ended.any():
+            _add_planned_orders(adapter, g, np.flatnonzero(ended).tolist(), order_cursor)
         stats["reward_bit_mismatch"] += int((r["reward"] != g["reward"][k]).sum())
         stats["episodes"] += int(ended.sum())
         stats["steps"] += g["actions"].shape[1]

@@ -326,3 +326,18 @@ def test_rollout_equals_stepping_one_by_one():
         assert torch.equal(out["obs"][k].view(torch.int32), obs.view(torch.int32))
         assert torch.equal(out["reward"][k], rew) and torch.equal(out["terminated"][k], term) and torch.equal(out["truncated"][k], trunc)
     assert torch.equal(a._metrics_total, b._metrics_total)
+
+
+def test_limit_order_api_validation():
+    import gym_trading_env_b200 as gte
+    env = gte.TradingVectorEnv(gte.make_gbm_ohlcv(400, seed=1), positions=[0, 1], num_envs=8, verbose=0)
+    env.reset()
+    with pytest.raises(NotImplementedError):
+        env.add_limit_order(1, 100.0)                    # persistent=False: the reference itself raises when it executes
+    with pytest.raises(ValueError):
+        env.add_limit_order(0.5, 100.0, persistent=True)
+    close0 = float(env.infos["data_close"][0])
+    env.add_limit_order(1, close0, persistent=True)      # at the money: executes on the next bars
+    for _ in range(5):
+        env.step(np.full(8, -1))                         # hold: only the order can move the position
+    assert int((env._pos_idx == 1).sum()) > 0

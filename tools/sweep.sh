@@ -1,5 +1,5 @@
 # tuning helper: one line per configuration given as "ENV=VAL ..." strings
-for cfg in "X=0" "X=1"; do
+for cfg in "X=0"; do
   env $cfg python bench.py --no-e2e --no-cpu --steps 50 --warmup 3 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
