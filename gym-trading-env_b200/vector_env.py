@@ -270,6 +270,8 @@ class TradingVectorEnv:
         self._copy_in = self._copy_out = None
         self._track_ids = None
         self._limit_price = None
+        self._kernel_events = None           # bench.py: list collecting (start, after step, after gather) CUDA events
+        self._kernel_events_every = 1        # ... on every k-th iteration
         self._obs_variant = _cabi.OBS_VARIANTS[obs_variant]
         self._multi = bool(_multi_dataset)
         self._k_switch = int(_episodes_between_dataset_switch)
@@ -593,6 +595,16 @@ class TradingVectorEnv:
                 self._capture_graph()
             self._tick += 1
             self._graph.replay()
+        elif self._kernel_events is not None and self.windows is not None and self._tick % self._kernel_events_every == 0:
+            # (bench.py, every k-th iteration) the same two kernels as gte_step_obs, issued as two calls so that
+            # CUDA events can bracket each of them without perturbing the other iterations
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            self._launch_step(C.c_void_p(act.data_ptr()))
+            ev[1].record()
+            self._launch_obs()
+            ev[2].record()
+            self._kernel_events.append(ev)
         else:
             self._launch_step_obs(C.c_void_p(act.data_ptr()))
         if self.output == "numpy":
