@@ -55,7 +55,8 @@ class GteState(C.Structure):
     _fields_ = [
         ("asset", C.c_void_p), ("fiat", C.c_void_p), ("interest_asset", C.c_void_p),
         ("interest_fiat", C.c_void_p), ("pos_idx", C.c_void_p), ("step", C.c_void_p),
-        ("ep_start", C.c_void_p), ("dataset_idx", C.c_void_p), ("dyn_ring", C.c_void_p),
+        ("ep_start", C.c_void_p), ("dataset_idx", C.c_void_p),
+        ("dyn_ring", C.c_void_p), ("ring_clock", C.c_void_p),
         ("plan_cursor", C.c_void_p), ("ds_used", C.c_void_p), ("ds_episodes", C.c_void_p),
         ("reset_plan", C.c_void_p), ("limit_price", C.c_void_p), ("limit_seq", C.c_void_p),
         ("error_flag", C.c_void_p), ("tick", C.c_void_p),

@@ -42,7 +42,8 @@ int check_common(const char* fn, const GteParams* p, const GteData* d, const Gte
     GTE_REQUIRE(fn, p->n_static == 0 || d->features != nullptr);
     GTE_REQUIRE(fn, s->asset && s->fiat && s->interest_asset && s->interest_fiat);
     GTE_REQUIRE(fn, s->pos_idx && s->step && s->ep_start && s->dataset_idx);
-    GTE_REQUIRE(fn, p->n_dyn == 0 || s->dyn_ring != nullptr);
+    GTE_REQUIRE(fn, s->ring_clock != nullptr);
+    GTE_REQUIRE(fn, p->n_dyn == 0 || (s->dyn_ring != nullptr && (reinterpret_cast<uintptr_t>(s->dyn_ring) & 15u) == 0));
     GTE_REQUIRE(fn, s->plan_cursor && s->ds_used && s->ds_episodes && s->error_flag && s->tick);
     GTE_REQUIRE(fn, p->plan_episodes == 0 || s->reset_plan != nullptr);
     GTE_REQUIRE(fn, p->n_limit_positions >= 0 && p->n_limit_positions <= p->n_positions);

@@ -127,13 +127,22 @@ __device__ __forceinline__ int next_dataset(const GteParams& P, const GteState& 
     return ds;
 }
 
-// dyn_ring of env i: W f32 real_position values then W u8 position indices (GTE_RING_STRIDE(W) bytes)
-__device__ __forceinline__ void ring_store(const GteParams& P, const GteState& S, int i, int row, float rp, int pos_idx) {
+// Dynamic-feature ring (time-indexed, one block per 32-env tile: include/gte_b200.h): the row env i observes at
+// lockstep iteration c lives in slot c % W.  All envs write the same slot in one iteration: a warp stores one
+// full 128-byte line of real_position values and one full 32-byte sector of position indices.
+__device__ __forceinline__ int ring_slot_of(const GteParams& P, uint64_t clock) {
     const int W = P.windows > 0 ? P.windows : 1;
-    uint8_t* ring = S.dyn_ring + (int64_t)i * GTE_RING_STRIDE(W);
-    const int slot = row % W;
-    reinterpret_cast<float*>(ring)[slot] = rp;
-    ring[4 * W + slot] = (uint8_t)pos_idx;
+    return (int)(clock % (uint64_t)W);
+}
+__device__ __forceinline__ const uint8_t* ring_tile(const GteState& S, int W, int64_t env) {
+    return S.dyn_ring + (env >> 5) * (int64_t)GTE_RING_TILE_BYTES(W);
+}
+__device__ __forceinline__ void ring_store(const GteParams& P, const GteState& S, int i, int slot, float rp, int pos_idx) {
+    const int W = P.windows > 0 ? P.windows : 1;
+    const int e = i & 31;
+    uint8_t* tile = S.dyn_ring + (int64_t)(i >> 5) * GTE_RING_TILE_BYTES(W);
+    *reinterpret_cast<float*>(tile + GTE_RING_RP_OFFSET(slot, e)) = rp;
+    tile[GTE_RING_POS_OFFSET(W, slot, e)] = (uint8_t)pos_idx;
 }
 
 struct EnvRegs {          // the per-env state a step keeps in registers
@@ -144,7 +153,7 @@ struct EnvRegs {          // the per-env state a step keeps in registers
 // TradingEnv.reset (environments.py:163-199) preceded by MultiDatasetTradingEnv.reset (:393-400).
 // Rare path (once per episode): plan/rotation bookkeeping goes straight to global memory.
 __device__ __forceinline__ void reset_env(const GteParams& P, const GteData& D, const GteState& S,
-                                       int i, uint64_t tick, EnvRegs& e) {
+                                       int i, uint64_t tick, int ring_slot, EnvRegs& e) {
     uint32_t r[4];
     philox_draw(P.seed, tick, (uint64_t)(P.env_id_offset + i), r);
     const bool have_plan = P.plan_episodes > 0 && S.reset_plan != nullptr;
@@ -185,7 +194,7 @@ __device__ __forceinline__ void reset_env(const GteParams& P, const GteData& D, 
     for (int k = 0; k < P.n_limit_positions; ++k)                            // self._limit_orders = {} (:168)
         S.limit_price[(int64_t)i * P.n_positions + S.limit_seq[k]] = __longlong_as_double(0x7ff8000000000000ll);
     if (P.n_dyn > 0)                                                         // first obs row: (position, position) :191-192
-        ring_store(P, S, i, start, (float)position, e.pos_idx);
+        ring_store(P, S, i, ring_slot, (float)position, e.pos_idx);
 }
 
 }  // namespace gte

@@ -7,9 +7,9 @@
 //             reference's own [t, F] layout, dynamic columns zero), dynamic columns patched in
 //             registers from the per-env ring, 128-bit coalesced st.global.  No shared memory.
 //   tma     : warp-specialised producer/consumer pipeline: cp.async.bulk (TMA, 1-D) pulls whole windows and
-//             the envs' dynamic-feature rings global->shared, consumer warps patch the dynamic columns in
-//             shared memory, cp.async.bulk pushes groups of finished windows shared->global.  The LSU only
-//             touches 12 bytes of per-env metadata.
+//             the dynamic-feature ring block of each 32-env tile global->shared, consumer warps patch the
+//             dynamic columns in shared memory, cp.async.bulk pushes groups of finished windows shared->global.
+//             The LSU only touches 12 bytes of per-env metadata.
 #include <cstdlib>
 
 #include "gte_tma.cuh"
@@ -26,6 +26,7 @@ obs_generic_kernel(const GteParams P, const GteData D, const GteState S, float* 
     const int lane = threadIdx.x % G;
     const int64_t n_groups = (int64_t)gridDim.x * groups_per_block;
     const int per_env = sh.W * sh.F;
+    const int s0 = sh.nd > 0 ? (int)((*S.ring_clock + 1ull) % (uint64_t)sh.W) : 0;    // ring slot of window row 0
     for (int64_t env = env_begin + (int64_t)blockIdx.x * groups_per_block + threadIdx.x / G; env < env_end;
          env += n_groups) {
         const int ep_start = S.ep_start[env];
@@ -33,7 +34,6 @@ obs_generic_kernel(const GteParams P, const GteData D, const GteState S, float* 
         const int ds = S.dataset_idx[env];
         const int r0 = idx + 1 - sh.W;
         const float* __restrict__ feat = D.features + ((int64_t)ds * P.t_stride + r0) * sh.ns;
-        const uint8_t* __restrict__ ring = S.dyn_ring + env * (int64_t)GTE_RING_STRIDE(sh.W);
         float* __restrict__ out = obs + env * per_env;
         for (int e = lane; e < per_env; e += G) {
             const int w = e / sh.F, c = e - w * sh.F;
@@ -42,9 +42,13 @@ obs_generic_kernel(const GteParams P, const GteData D, const GteState S, float* 
                 v = __ldg(feat + (int64_t)w * sh.ns + c);
             } else {
                 const int r = r0 + w;
-                const int slot = r % sh.W;
+                int slot = s0 + w;
+                if (slot >= sh.W) slot -= sh.W;
+                const uint8_t* __restrict__ ring = ring_tile(S, sh.W, env);
+                const int e32 = (int)(env & 31);
                 v = (r < ep_start) ? 0.0f
-                  : (c == sh.ns ? (float)P.positions[ring[4 * sh.W + slot]] : reinterpret_cast<const float*>(ring)[slot]);
+                  : (c == sh.ns ? (float)P.positions[ring[GTE_RING_POS_OFFSET(sh.W, slot, e32)]]
+                                : *reinterpret_cast<const float*>(ring + GTE_RING_RP_OFFSET(slot, e32)));
             }
             out[e] = v;
         }
@@ -70,16 +74,16 @@ obs_vec_kernel(const GteParams P, const GteData D, const GteState S, float* __re
                const ObsShape sh, const int env_begin, const int env_end) {
     const int lane = threadIdx.x & 31;
     const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int s0 = sh.nd > 0 ? (int)((*S.ring_clock + 1ull) % (uint64_t)sh.W) : 0;    // ring slot of window row 0
     for (int64_t env = env_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); env < env_end;
          env += n_warps) {
         const int ep_start = S.ep_start[env];
         const int idx = ep_start + S.step[env];
         const int ds = S.dataset_idx[env];
         const int r0 = idx + 1 - sh.W;
-        const int s0 = ((r0 % sh.W) + sh.W) % sh.W;            // ring slot of window row 0
         const char* __restrict__ src = window_src(D, sh, ds, r0);
-        const uint8_t* __restrict__ ring = S.dyn_ring + env * (int64_t)GTE_RING_STRIDE(sh.W);
-        const float* __restrict__ ring_rp = reinterpret_cast<const float*>(ring);
+        const uint8_t* __restrict__ ring = ring_tile(S, sh.W, env);
+        const int e32 = (int)(env & 31);
         char* __restrict__ dst = reinterpret_cast<char*>(obs) + env * (int64_t)sh.win_bytes;
         for (int j = lane; j < sh.n_vec; j += 32) {
             float4 v = ld_nc_v4(src + 16 * j);
@@ -94,13 +98,15 @@ obs_vec_kernel(const GteParams P, const GteData D, const GteState S, float* __re
                         const int r = r0 + w;
                         int slot = s0 + w;
                         if (slot >= sh.W) slot -= sh.W;
+                        const uint8_t* rpos = ring + GTE_RING_POS_OFFSET(sh.W, slot, e32);
+                        const float* rrp = reinterpret_cast<const float*>(ring + GTE_RING_RP_OFFSET(slot, e32));
                         if (PAIR) {
                             const bool live = r >= ep_start;
-                            pv[k] = live ? (float)P.positions[__ldg(ring + 4 * sh.W + slot)] : 0.0f;
-                            pv[k + 1] = live ? __ldg(ring_rp + slot) : 0.0f;
+                            pv[k] = live ? (float)P.positions[__ldg(rpos)] : 0.0f;
+                            pv[k + 1] = live ? __ldg(rrp) : 0.0f;
                         } else {
                             pv[k] = (r < ep_start) ? 0.0f
-                                  : (c == sh.ns ? (float)P.positions[__ldg(ring + 4 * sh.W + slot)] : __ldg(ring_rp + slot));
+                                  : (c == sh.ns ? (float)P.positions[__ldg(rpos)] : __ldg(rrp));
                         }
                     }
                 }
@@ -111,23 +117,26 @@ obs_vec_kernel(const GteParams P, const GteData D, const GteState S, float* __re
 }
 
 // ---- TMA gather: warp-specialised producer / consumer pipeline -----------------------------------------
-// One CTA = 4 consumer warps + 1 producer warp working on ONE pipeline of groups of G consecutive envs
-// (a 32-env tile = 32/G groups; tiles strided over the grid):
-//   producer warp : owns the metadata of the next 32-env tile (one env per lane, one coalesced load per
-//                   array a whole tile ahead), turns it ONCE per env into the window address / ring slot,
-//                   waits for a free stage (empty mbarrier), publishes (r0, s0, ep_start) to shared memory
-//                   and issues the group's TMA loads: G cp.async.bulk window copies from the L2-resident
-//                   window table onto the window stage's full mbarrier, and ONE cp.async.bulk for the G
-//                   contiguous rings (HBM) onto the ring stage's full mbarrier;
-//   consumer warps: wait on both full mbarriers, patch the dynamic columns smem->smem with a thread-per-row
-//                   mapping (128 threads = G envs x 128/G threads; rows before the episode start stay
-//                   zero), fence.proxy.async, meet on a named barrier; one thread then hands the ring stage
-//                   back, issues the SINGLE bulk store of the G contiguous windows and, once the PREVIOUS
-//                   group's store has finished reading shared memory, hands that window stage back.
+// One CTA = 4 consumer warps + 1 producer warp working on ONE pipeline over 32-env tiles (strided over the grid),
+// each tile cut into groups of G consecutive envs:
+//   producer warp : owns the metadata of the next tile (one env per lane, one coalesced load per array a whole
+//                   tile ahead), turns it ONCE per env into the window address and the first live window row,
+//                   waits for a free window stage (empty mbarrier), publishes the first live rows to shared
+//                   memory and issues the group's G cp.async.bulk window copies from the L2-resident window
+//                   table onto the stage's full mbarrier.  One tile ahead it issues the ONE cp.async.bulk of the
+//                   tile's dynamic-feature ring block (HBM, W x 160 contiguous bytes: real_position rows whose
+//                   16-byte chunks are XOR-swizzled so the consumers' column reads spread over the banks, then
+//                   position-index rows);
+//   consumer warps: wait on both full mbarriers, patch the dynamic columns smem->smem (128 threads = G envs x
+//                   128/G slots per pass; rows before the episode start stay zero), fence.proxy.async, meet on
+//                   a named barrier; one thread then issues the SINGLE bulk store of the G contiguous windows,
+//                   hands the ring tile back after the tile's last group and, once the PREVIOUS group's store
+//                   has finished reading shared memory, hands that window stage back.
 // Evidence for this shape is in profiles/r01_tuning.md (per-warp pipelines were bound by the instruction
 // chain of too few resident warps; consumers of a unified pipeline mostly waited on the HBM ring loads).
 constexpr int kCoopConsumerWarps = 4;
 constexpr int kCoopThreads = (kCoopConsumerWarps + 1) * 32;
+constexpr int kTileEnvs = 32;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -135,36 +144,36 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void consumer_barrier() {
     asm volatile("bar.sync 1, %0;" :: "n"(kCoopConsumerWarps * 32) : "memory");
 }
-
-// WS window stages and RS >= WS ring stages per CTA, G envs per stage.  The rings come from HBM (slow under a
-// saturating write stream) and only need the env index, the windows come from L2 and need the env's
-// metadata: the ring pipeline runs RS-WS groups further ahead, so the big window buffers are only held
-// for an L2 round trip + patch + store drain.
-template <int WS, int RS, int G>
+// WS window stages of G envs and RT ring-tile stages per CTA.  The ring tiles come from HBM (slow under a
+// saturating write stream) and only need the tile index, the windows come from L2 and need the envs'
+// metadata: ring tiles are requested a whole tile ahead, the big window buffers are only held for an L2
+// round trip + patch + store drain.
+template <int WS, int RT, int G>
 __global__ void __launch_bounds__(kCoopThreads)
 obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float* __restrict__ obs,
                     const ObsShape sh, const int env_begin, const int env_end) {
-    static_assert(RS >= WS, "the ring pipeline is at least as deep as the window pipeline");
-    constexpr int GROUPS = 32 / G;                               // groups per 32-env tile
+    static_assert(RT >= 2, "a ring tile is requested while the previous one is being consumed");
+    constexpr int GROUPS = kTileEnvs / G;                        // groups per tile
     constexpr int NCONS = kCoopConsumerWarps * 32;
-    constexpr int TPE = NCONS / G;                               // consumer threads per env
-    constexpr int LEAD = RS - WS;                                // extra groups the ring loads run ahead
+    constexpr int SPP = NCONS / G;                               // ring slots patched per pass
+    constexpr int RING_AT = WS < GROUPS - 1 ? WS : GROUPS - 1;   // group at which the tile RT-1 ahead is requested:
+                                                                 // by then the stage it reuses has been handed back
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_w[WS], empty_w[WS], full_r[RS], empty_r[RS];
-    __shared__ int4 meta[2][32];                                 // per tile parity: {r0, s0, ep_start, -}
+    __shared__ __align__(8) uint64_t full_w[WS], empty_w[WS], full_r[RT], empty_r[RT];
+    __shared__ int first_live[2][kTileEnvs];                     // per tile parity: first window row of the episode
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool ring = sh.nd > 0;
     const uint32_t win_bytes = (uint32_t)sh.win_bytes;
-    const uint32_t ring_bytes = sh.nd > 0 ? (uint32_t)GTE_RING_STRIDE(sh.W) : 0u;   // W f32 real_position + W u8 position idx
-    const uint32_t wstage_bytes = win_bytes * G, rstage_bytes = ring_bytes * G;
-    unsigned char* wbase = smem_raw;
-    unsigned char* rbase = smem_raw + (size_t)WS * wstage_bytes;
+    const uint32_t wstage_bytes = win_bytes * G, rstride = (uint32_t)GTE_RING_TILE_BYTES(sh.W);
+    unsigned char* rbase = smem_raw;
+    unsigned char* wbase = rbase + (ring ? (size_t)RT * rstride : 0);
 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < WS; ++s) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], 1); }
 #pragma unroll
-        for (int s = 0; s < RS; ++s) { mbar_init(&full_r[s], 1); mbar_init(&empty_r[s], 1); }
+        for (int s = 0; s < RT; ++s) { mbar_init(&full_r[s], 1); mbar_init(&empty_r[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -179,47 +188,44 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
 
     if (warp == kCoopConsumerWarps) {
         // ------------------------------------------------------------------ producer warp
+        struct TilePre { unsigned long long src; int first_live; };
         auto load_tile = [&](int k) {
-            EnvPre p;
-            p.src = 0ull; p.r0 = 0; p.s0 = 0; p.ep_start = 0;
+            TilePre p;
+            p.src = 0ull; p.first_live = 0;
             const int64_t env = tile_env0(k) + lane;
             if (env < env_end) {
                 const int ep = __ldg(S.ep_start + env), st = __ldg(S.step + env), ds = __ldg(S.dataset_idx + env);
-                p.ep_start = ep;
-                p.r0 = ep + st + 1 - sh.W;
-                p.s0 = sh.w_mask >= 0 ? (p.r0 & sh.w_mask) : (((p.r0 % sh.W) + sh.W) % sh.W);
-                p.src = (unsigned long long)window_src(D, sh, ds, p.r0);
+                p.first_live = sh.W - 1 - st;                    // window row of ep_start (<= 0: the whole window is live)
+                p.src = (unsigned long long)window_src(D, sh, ds, ep + st + 1 - sh.W);
             }
             return p;
         };
-        auto issue_ring = [&](int qr) {                          // lane 0; needs nothing but the env index
-            const int nv = group_valid(qr);
-            if (nv > 0 && ring_bytes) {
-                const int stage = qr % RS, use = qr / RS;
+        auto issue_ring = [&](int k) {                           // lane 0; needs nothing but the tile index
+            if (ring && tile_env0(k) < env_end) {
+                const int stage = k % RT, use = k / RT;
                 if (use > 0) mbar_wait(&empty_r[stage], (uint32_t)(use - 1) & 1u);
-                mbar_expect_tx(&full_r[stage], (uint32_t)nv * ring_bytes);
-                bulk_g2s(rbase + (size_t)stage * rstage_bytes, S.dyn_ring + group_env0(qr) * (int64_t)ring_bytes,
-                         (uint32_t)nv * ring_bytes, &full_r[stage]);
+                mbar_expect_tx(&full_r[stage], rstride);
+                bulk_g2s(rbase + (size_t)stage * rstride, ring_tile(S, sh.W, tile_env0(k)), rstride, &full_r[stage]);
             }
         };
-        EnvPre pc = load_tile(0), pn = load_tile(1);
+        TilePre pc = load_tile(0), pn = load_tile(1);
         if (lane == 0)
-            for (int qr = 0; qr < LEAD; ++qr) issue_ring(qr);
+            for (int k = 0; k < RT - 1; ++k) issue_ring(k);
         int q = 0;
         for (int k = 0; tile_env0(k) < env_end; ++k) {
             for (int gi = 0; gi < GROUPS; ++gi, ++q) {
                 const int n_valid = group_valid(q);
                 if (n_valid == 0) break;
-                if (lane == 0) issue_ring(q + LEAD);
+                if (lane == 0 && gi == RING_AT) issue_ring(k + RT - 1);
                 __syncwarp();
                 const int stage = q % WS, use = q / WS;
                 if (use > 0) mbar_wait(&empty_w[stage], (uint32_t)(use - 1) & 1u);     // stage handed back
                 if (gi == 0) {                                   // after the wait: tile k-2 is fully consumed
-                    meta[k & 1][lane] = make_int4(pc.r0, pc.s0, pc.ep_start, 0);
+                    first_live[k & 1][lane] = pc.first_live;
                     __syncwarp();
                 }
                 unsigned char* sbuf = wbase + (size_t)stage * wstage_bytes;
-                if (lane == 0) mbar_expect_tx(&full_w[stage], (uint32_t)n_valid * win_bytes);   // release: publishes meta
+                if (lane == 0) mbar_expect_tx(&full_w[stage], (uint32_t)n_valid * win_bytes);   // release: publishes first_live
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     const unsigned long long src = __shfl_sync(FULL, pc.src, gi * G + g);
@@ -232,31 +238,34 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
         }
     } else {
         // ------------------------------------------------------------------ consumer warps
-        const int g = tid / TPE, t = tid % TPE;
+        // thread -> (env g of the group, slot t of the pass): the G lanes sharing a slot read one 16-byte chunk of
+        // the swizzled real_position row, lanes of different slots hit different chunks (banks)
+        const int g = tid % G, t = tid / G;
+        const int s0 = ring ? (int)((*S.ring_clock + 1ull) % (uint64_t)sh.W) : 0;      // ring slot of window row 0
         int q = 0;
         for (int k = 0; tile_env0(k) < env_end; ++k) {
+            const int rs = k % RT;
             for (int gi = 0; gi < GROUPS; ++gi, ++q) {
                 const int n_valid = group_valid(q);
                 if (n_valid == 0) break;
                 const int64_t env0 = group_env0(q);
-                const int ws = q % WS, rs = q % RS;
+                const int ws = q % WS;
                 unsigned char* sbuf = wbase + (size_t)ws * wstage_bytes;
-                mbar_wait(&full_w[ws], (uint32_t)(q / WS) & 1u);             // windows landed (acquire: meta too)
-                if (ring_bytes) {
-                    mbar_wait(&full_r[rs], (uint32_t)(q / RS) & 1u);         // rings landed
+                mbar_wait(&full_w[ws], (uint32_t)(q / WS) & 1u);             // windows landed (acquire: first_live too)
+                if (ring) {
+                    mbar_wait(&full_r[rs], (uint32_t)(k / RT) & 1u);         // the tile's ring slots landed
                     if (g < n_valid) {
-                        const int4 m = meta[k & 1][gi * G + g];
-                        const int r0 = m.x, s0 = m.y, ep_start = m.z;
+                        const int e = gi * G + g;                            // env within the tile
+                        const int live0 = first_live[k & 1][e];
                         float* fbuf = reinterpret_cast<float*>(sbuf + (size_t)g * win_bytes);
-                        const unsigned char* rbuf = rbase + (size_t)rs * rstage_bytes + (size_t)g * ring_bytes;
-                        const float* rbuf_rp = reinterpret_cast<const float*>(rbuf);
-                        for (int s = t; s < sh.W; s += TPE) {
+                        const unsigned char* rtile = rbase + (size_t)rs * rstride;
+                        for (int s = t; s < sh.W; s += SPP) {
                             int w = s - s0;
                             if (w < 0) w += sh.W;
-                            if (r0 + w >= ep_start) {            // rows before the episode start stay zero
+                            if (w >= live0) {                    // rows before the episode start stay zero
                                 float* qd = fbuf + w * sh.F + sh.ns;
-                                qd[0] = (float)P.positions[rbuf[4 * sh.W + s]];     // fp64 -> fp32 as numpy casts (:154)
-                                qd[1] = rbuf_rp[s];
+                                qd[0] = (float)P.positions[rtile[GTE_RING_POS_OFFSET(sh.W, s, e)]];   // fp64 -> fp32 as numpy casts (:154)
+                                qd[1] = *reinterpret_cast<const float*>(rtile + GTE_RING_RP_OFFSET(s, e));
                             }
                         }
                     }
@@ -264,7 +273,7 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
                 }
                 consumer_barrier();
                 if (tid == 0) {
-                    if (ring_bytes) mbar_arrive(&empty_r[rs]);   // the rings of this group are consumed
+                    if (ring && gi == GROUPS - 1) mbar_arrive(&empty_r[rs]);  // the tile's ring slots are consumed
                     bulk_s2g(reinterpret_cast<char*>(obs) + env0 * (int64_t)win_bytes, sbuf, (uint32_t)n_valid * win_bytes);
                     bulk_commit();
                     if (q > 0) {
@@ -280,50 +289,43 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
 
 using ObsKernelFn = void (*)(const GteParams, const GteData, const GteState, float*, const ObsShape, int, int);
 
-struct TmaConfig { int wstages, rstages, group; };
+struct TmaConfig { int wstages, rtiles, group; };
 
 static size_t tma_smem_bytes(const ObsShape& sh, const TmaConfig& c) {
-    const size_t ring = sh.nd > 0 ? (size_t)GTE_RING_STRIDE(sh.W) : 0;
-    return (size_t)c.group * ((size_t)c.wstages * sh.win_bytes + (size_t)c.rstages * ring);
+    const size_t ring = sh.nd > 0 ? (size_t)c.rtiles * GTE_RING_TILE_BYTES(sh.W) : 0;
+    return (size_t)c.group * c.wstages * sh.win_bytes + ring;
 }
 
 static ObsKernelFn tma_kernel(const TmaConfig& c) {
-    // (window stages, ring stages, envs per group) combinations compiled in
-    switch (c.wstages * 10000 + c.rstages * 100 + c.group) {
-        case 31201: return obs_tma_coop_kernel<3, 12, 1>;
-        case 31202: return obs_tma_coop_kernel<3, 12, 2>;
-        case 31204: return obs_tma_coop_kernel<3, 12, 4>;
-        case 41204: return obs_tma_coop_kernel<4, 12, 4>;
-        case 40604: return obs_tma_coop_kernel<4, 6, 4>;
-        case 40704: return obs_tma_coop_kernel<4, 7, 4>;
-        case 50604: return obs_tma_coop_kernel<5, 6, 4>;
-        case 50804: return obs_tma_coop_kernel<5, 8, 4>;
-        case 60802: return obs_tma_coop_kernel<6, 8, 2>;
-        case 61202: return obs_tma_coop_kernel<6, 12, 2>;
-        case 81202: return obs_tma_coop_kernel<8, 12, 2>;
-        case 30604: return obs_tma_coop_kernel<3, 6, 4>;
-        case 30804: return obs_tma_coop_kernel<3, 8, 4>;
-        case 31004: return obs_tma_coop_kernel<3, 10, 4>;
-        case 31604: return obs_tma_coop_kernel<3, 16, 4>;
-        case 40404: return obs_tma_coop_kernel<4, 4, 4>;
-        case 30808: return obs_tma_coop_kernel<3, 8, 8>;
-        case 20608: return obs_tma_coop_kernel<2, 6, 8>;
-        case 40408: return obs_tma_coop_kernel<4, 4, 8>;
+    // (window stages, ring-tile stages, envs per group) combinations compiled in
+    switch (c.wstages * 10000 + c.rtiles * 100 + c.group) {
+        case 30201: return obs_tma_coop_kernel<3, 2, 1>;
+        case 30202: return obs_tma_coop_kernel<3, 2, 2>;
+        case 30204: return obs_tma_coop_kernel<3, 2, 4>;
+        case 30208: return obs_tma_coop_kernel<3, 2, 8>;
+        case 30304: return obs_tma_coop_kernel<3, 3, 4>;
+        case 40204: return obs_tma_coop_kernel<4, 2, 4>;
+        case 40304: return obs_tma_coop_kernel<4, 3, 4>;
+        case 20204: return obs_tma_coop_kernel<2, 2, 4>;
+        case 40202: return obs_tma_coop_kernel<4, 2, 2>;
+        case 60202: return obs_tma_coop_kernel<6, 2, 2>;
+        case 60302: return obs_tma_coop_kernel<6, 3, 2>;
+        case 20208: return obs_tma_coop_kernel<2, 2, 8>;
         default: return nullptr;
     }
 }
 
-// Pipeline shape: 3 window stages + 12 ring stages of the largest group (4, 2, 1 envs) that still leaves
-// two CTAs per SM; GTE_TMA_STAGES / GTE_TMA_RSTAGES / GTE_TMA_GROUP override it for tuning runs.
+// Pipeline shape: 3 window stages of the largest group (4, 2, 1 envs) + 2 ring tiles that still leave two CTAs per
+// SM; GTE_TMA_STAGES / GTE_TMA_RTILES / GTE_TMA_GROUP override it for tuning runs.
 static TmaConfig tma_config(const ObsShape& sh) {
     static const int ws = [] { const char* e = getenv("GTE_TMA_STAGES"); return e ? atoi(e) : 0; }();
-    static const int rs = [] { const char* e = getenv("GTE_TMA_RSTAGES"); return e ? atoi(e) : 0; }();
+    static const int rt = [] { const char* e = getenv("GTE_TMA_RTILES"); return e ? atoi(e) : 0; }();
     static const int g = [] { const char* e = getenv("GTE_TMA_GROUP"); return e ? atoi(e) : 0; }();
-    if (ws > 0 && rs > 0 && g > 0) {
-        const TmaConfig c{ws, rs, g};
+    if (ws > 0 && rt > 0 && g > 0) {
+        const TmaConfig c{ws, rt, g};
         if (tma_kernel(c) != nullptr) return c;
     }
-    TmaConfig c{3, 12, 4};
+    TmaConfig c{3, 2, 4};
     while (c.group > 1 && tma_smem_bytes(sh, c) > 100 * 1024) c.group /= 2;
     return c;
 }

@@ -26,11 +26,13 @@ step_kernel(const GteParams P, const GteData D, const GteState S, const int64_t*
     __syncthreads();
     MetricAcc acc;
     const uint64_t tick = *S.tick;
+    // the slot this iteration's row goes to: the first env range of an iteration still sees the old clock
+    const int ring_slot = ring_slot_of(P, *S.ring_clock + ((chunk_flags & kChunkFirst) ? 1ull : 0ull));
     const int64_t base0 = (int64_t)env_begin + (int64_t)blockIdx.x * tiles_per_cta * kStepThreads;
     for (int t = 0; t < tiles_per_cta; ++t) {
         const int64_t i = base0 + (int64_t)t * kStepThreads + threadIdx.x;
         if (i < env_end) {
-            const StepThreadOut r = step_env(P, D, S, actions, O, tick, autoreset, (int)i, acc, s_pos);
+            const StepThreadOut r = step_env(P, D, S, actions, O, tick, ring_slot, autoreset, (int)i, acc, s_pos);
             if (obs_rows != nullptr) {
                 // windows=None (environments.py:156-157): the observation is the single row idx, written by the
                 // env's own thread -> one launch per lockstep iteration at small N
@@ -69,7 +71,7 @@ reset_kernel(const GteParams P, const GteData D, const GteState S, const uint8_t
     if (mask != nullptr && mask[i] == 0) return;
     EnvRegs e;
     e.ds = S.dataset_idx[i];
-    reset_env(P, D, S, i, tick, e);
+    reset_env(P, D, S, i, tick, ring_slot_of(P, *S.ring_clock), e);    // the row currently observed
     S.asset[i] = e.pf.asset;
     S.fiat[i] = e.pf.fiat;
     S.interest_asset[i] = e.pf.ia;

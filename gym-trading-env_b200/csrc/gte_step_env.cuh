@@ -21,7 +21,7 @@ struct MetricAcc {           // per-thread accumulators (deterministic: fixed ti
 // The transition of ONE env (the reference's step(), line by line).
 __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteData& D, const GteState& S,
                                                   const int64_t* __restrict__ actions,
-                                                  const GteStepOut& O, uint64_t tick, int autoreset,
+                                                  const GteStepOut& O, uint64_t tick, int ring_slot, int autoreset,
                                                   int i, MetricAcc& acc, const double* __restrict__ pos_tab) {
     EnvRegs e;
     e.pf.asset = S.asset[i];
@@ -103,7 +103,8 @@ __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteD
         O.pre_reset_portfolio[3 * N + i] = e.pf.ifi;
     }
     float dyn_pos = (float)pos_tab[e.pos_idx], dyn_rp = (float)rp;        // fp64 -> fp32 as numpy casts (:154)
-    if (P.n_dyn > 0) ring_store(P, S, i, idx, dyn_rp, e.pos_idx);             // _get_obs write-back (:153-154)
+    // _get_obs write-back (:153-154); an auto-reset below overwrites the same slot with the new episode's first row
+    if (P.n_dyn > 0) ring_store(P, S, i, ring_slot, dyn_rp, e.pos_idx);
     acc.sum_rew = dadd(acc.sum_rew, rew);
     if (done || trunc) {                                                     // :269-271 calculate_metrics
         acc.episodes += 1;
@@ -113,7 +114,7 @@ __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteD
         acc.sum_pr = dadd(acc.sum_pr, dsub(ddiv(val, P.v0), 1.0));           // :282
         acc.sum_mr = dadd(acc.sum_mr, dsub(ddiv(p1, __ldg(price + e.ep_start)), 1.0));   // :281
         if (autoreset) {
-            reset_env(P, D, S, i, tick, e);                                  // in-place auto-reset
+            reset_env(P, D, S, i, tick, ring_slot, e);                       // in-place auto-reset
             idx = e.ep_start;
             dyn_pos = dyn_rp = (float)pos_tab[e.pos_idx];                // first row: (position, position) :191-192
             if (P.n_datasets > 1) S.dataset_idx[i] = e.ds;
@@ -196,8 +197,11 @@ static __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O,
     }
     if (threadIdx.x == 0) {
         *O.block_counter = 0u;                           // self-resetting for the next launch
-        // every CTA of this iteration has read the tick by now: advance the Philox event counter
+        // every CTA of this launch has read the tick / ring clock by now.  The Philox event counter advances with
+        // the LAST env range of an iteration; the ring clock with the FIRST one, so that the later ranges and
+        // every gather of the iteration (all stream-ordered behind this launch) read the new value
         if (chunk_flags & kChunkLast) *S.tick = *S.tick + 1ull;
+        if (chunk_flags & kChunkFirst) *S.ring_clock = *S.ring_clock + 1ull;
     }
 }
 

@@ -76,14 +76,4 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// What the gather needs to know about one env, computed ONCE per env by the lane that owns it in the
-// current 32-env block (in parallel across lanes) and then broadcast with shuffles: the per-env loop
-// of a warp is a latency chain, so nothing expensive (64-bit address math, modulo) stays inside it.
-struct EnvPre {
-    unsigned long long src;      // 16-byte-aligned address of the env's window in the window table
-    int r0;                      // absolute row of window row 0
-    int s0;                      // ring slot of window row 0
-    int ep_start;                // rows before it read as zero
-};
-
 }  // namespace gte

@@ -359,7 +359,10 @@ class TradingVectorEnv:
         self._pos_idx, self._step, self._ep_start, self._dataset_idx = i32(N), i32(N), i32(N), i32(N)
         self._plan_cursor, self._ds_episodes = i32(N), i32(N)
         self._ds_used = torch.zeros(N, dtype=torch.int64, device=dev)
-        self._dyn_ring = torch.zeros(N, ((W * 5 + 15) // 16) * 16, dtype=torch.uint8, device=dev)   # GTE_RING_STRIDE(W)
+        # dynamic-feature ring: one GTE_RING_TILE_BYTES(W) block per tile of 32 envs, slots indexed by the
+        # device-resident iteration clock (layout: include/gte_b200.h)
+        self._dyn_ring = torch.zeros((N + 31) // 32, W * 160, dtype=torch.uint8, device=dev)
+        self._ring_clock = torch.zeros(1, dtype=torch.int64, device=dev)
         self._error_flag = i32(1)
         self._tick_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self._reset_plan = None
@@ -415,7 +418,8 @@ class TradingVectorEnv:
         s.asset, s.fiat = self._asset.data_ptr(), self._fiat.data_ptr()
         s.interest_asset, s.interest_fiat = self._interest_asset.data_ptr(), self._interest_fiat.data_ptr()
         s.pos_idx, s.step, s.ep_start = self._pos_idx.data_ptr(), self._step.data_ptr(), self._ep_start.data_ptr()
-        s.dataset_idx, s.dyn_ring = self._dataset_idx.data_ptr(), self._dyn_ring.data_ptr()
+        s.dataset_idx = self._dataset_idx.data_ptr()
+        s.dyn_ring, s.ring_clock = self._dyn_ring.data_ptr(), self._ring_clock.data_ptr()
         s.plan_cursor, s.ds_used, s.ds_episodes = self._plan_cursor.data_ptr(), self._ds_used.data_ptr(), self._ds_episodes.data_ptr()
         s.reset_plan = None if self._reset_plan is None else self._reset_plan.data_ptr()
         s.error_flag = self._error_flag.data_ptr()
@@ -824,7 +828,8 @@ class TradingVectorEnv:
     def state_dict(self):
         """Env state as tensors (checkpoint/resume: SURVEY.md §5)."""
         names = ["asset", "fiat", "interest_asset", "interest_fiat", "pos_idx", "step", "ep_start", "dataset_idx",
-                 "dyn_ring", "plan_cursor", "ds_used", "ds_episodes", "metrics_total", "tick_dev"]
+                 "dyn_ring", "ring_clock", "plan_cursor", "ds_used", "ds_episodes",
+                 "metrics_total", "tick_dev"]
         return {n: getattr(self, "_" + n).clone() for n in names}
 
     def load_state_dict(self, d):

@@ -31,11 +31,16 @@
 extern "C" {
 #endif
 
-#define GTE_VERSION 103            /* 0.1.3 */
+#define GTE_VERSION 104            /* 0.1.4 */
 #define GTE_MAX_POSITIONS 64
 #define GTE_MAX_DATASETS 64        /* least-used rotation keeps a 64-bit "used this round" mask per env */
 #define GTE_N_METRICS 8
-#define GTE_RING_STRIDE(W) ((((W) * 5) + 15) / 16 * 16)   /* bytes of dyn_ring per env */
+/* dynamic-feature ring: one block per tile of 32 consecutive envs (layout at GteState.dyn_ring) */
+#define GTE_RING_TILE_ENVS 32
+#define GTE_RING_TILE_BYTES(W) ((W) * 160)
+#define GTE_RING_BYTES(N, W) ((((int64_t)(N) + 31) / 32) * GTE_RING_TILE_BYTES(W))
+#define GTE_RING_RP_OFFSET(s, e) ((s) * 128 + (((((e) >> 2) ^ ((s) & 7))) << 4) + (((e) & 3) << 2))
+#define GTE_RING_POS_OFFSET(W, s, e) ((W) * 128 + (s) * 32 + (e))
 #define GTE_STEP_THREADS 256       /* envs per CTA of the step kernel; metric_partials has ceil(N/256) rows */
 
 #define GTE_OK 0
@@ -126,10 +131,17 @@ typedef struct GteState {
     int32_t* step;                   /* i32 [N]  TradingEnv._step                                      */
     int32_t* ep_start;               /* i32 [N]  _idx at reset (episode start row)                     */
     int32_t* dataset_idx;            /* i32 [N]  which dataset the env is on                           */
-    uint8_t* dyn_ring;               /* u8 [N, GTE_RING_STRIDE(W)], W = max(windows,1).  Per env: W f32
-                                        real_position values, then W u8 position INDICES (the dynamic
-                                        feature "position" is float32(positions[index])), padded to 16 B;
-                                        row r lives at slot r % W, rows before ep_start read as zero   */
+    /* Dynamic-feature ring, indexed by TIME: the row an env observed at lockstep iteration c (c = *ring_clock,
+     * advanced by every gte_step / gte_step_obs call) lives in slot c % W, W = max(windows,1); a window reads slots
+     * c-W+1 .. c, and its rows before ep_start read as zero (the env was reset less than W iterations ago).
+     * Memory: one contiguous block of GTE_RING_TILE_BYTES(W) per tile of 32 consecutive envs, so that the gather
+     * fetches a tile's whole ring with one bulk copy while one iteration's stores are a full 128-byte line + a
+     * full 32-byte sector per warp.  Inside a block: W rows of 32 f32 real_position values (:24) — env lane e of
+     * slot s at GTE_RING_RP_OFFSET(s, e), 16-byte chunks XOR-swizzled by the slot so that column reads from
+     * shared memory spread over the banks — then W rows of 32 u8 position INDICES at GTE_RING_POS_OFFSET(W, s, e)
+     * (the dynamic feature "position" is float32(positions[index]), :20-21). */
+    uint8_t* dyn_ring;               /* u8 [GTE_RING_BYTES(N, W)], 16-byte aligned                               */
+    uint64_t* ring_clock;            /* u64 [1]  lockstep iterations so far, advanced ON THE DEVICE              */
     int32_t* plan_cursor;            /* i32 [N]  next episode slot of reset_plan                       */
     uint64_t* ds_used;               /* u64 [N]  datasets used in the current rotation round (:383)    */
     int32_t* ds_episodes;            /* i32 [N]  _episodes_on_this_dataset (:381,394)                  */
@@ -193,7 +205,7 @@ int gte_step(const GteParams* params, const GteData* data, const GteState* state
 
 /* Replaces TradingEnv._get_obs (environments.py:152-160): obs f32 [N, F] (windows=None) or
  * [N, W, F], F = n_static + n_dyn; static columns gathered from the device-resident tables,
- * dynamic columns from dyn_ring. */
+ * dynamic columns from the dynamic-feature ring. */
 int gte_gather_obs(const GteParams* params, const GteData* data, const GteState* state,
                    float* obs, int variant, void* stream);
 

@@ -106,7 +106,7 @@ def test_no_write_lands_outside_the_output_and_state_buffers(variant, n_envs):
                                debug_outputs=True, obs_variant="auto" if variant == "nowindow" else variant)
     GUARD = 4096
     bands = []
-    names = ["_obs", "_dyn_ring", "_reward", "_terminated", "_truncated", "_valuation", "_real_position", "_info_idx",
+    names = ["_obs", "_dyn_ring", "_ring_clock", "_reward", "_terminated", "_truncated", "_valuation", "_real_position", "_info_idx",
              "_info_step", "_pre_reset_portfolio", "_asset", "_fiat", "_interest_asset", "_interest_fiat", "_pos_idx",
              "_step", "_ep_start", "_dataset_idx", "_plan_cursor", "_ds_used", "_ds_episodes", "_metrics_step",
              "_metrics_total", "_metric_partials", "_error_flag", "_tick_dev", "_block_counter"]

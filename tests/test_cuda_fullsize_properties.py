@@ -98,11 +98,12 @@ def test_full_size_properties(series, n_envs, n_steps):
     idx0 = (env._ep_start + env._step).clone()
     step0 = env._step.clone()
     # P4/P5/P6 companions start from the same (modified) state
-    lo, n_slice = 12_345, 4_096
+    lo, n_slice = 12_352, 4_096         # a multiple of 32: the ring is stored per 32-env tile
     sl = gte.TradingVectorEnv(series, num_envs=n_slice, seed=7, env_id_offset=lo, verbose=0, debug_outputs=True, **KW)
     sl.reset()
-    for name in ("asset", "fiat", "interest_asset", "interest_fiat", "pos_idx", "step", "ep_start", "dyn_ring"):
+    for name in ("asset", "fiat", "interest_asset", "interest_fiat", "pos_idx", "step", "ep_start"):
         getattr(sl, "_" + name).copy_(getattr(env, "_" + name)[lo:lo + n_slice])
+    sl._dyn_ring.copy_(env._dyn_ring[lo // 32:(lo + n_slice) // 32])       # one ring block per tile of 32 envs
 
     prev_idx, prev_step = idx0, step0
     total_eps = 0
