@@ -23,7 +23,18 @@ struct Portfolio {        // signed state of utils/portfolio.py:2-6
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+// IEEE division.  The inline fast path of the fp64 divide hands a ZERO numerator to a ~250-instruction subroutine,
+// and zero numerators are everyday values here (a flat position: asset = 0, target = 0), so one flat env per warp
+// would send the whole warp there several times per step.  0 / b for a finite non-zero b is a zero whose sign is
+// the XOR of the operand signs: answer that directly and divide 1 / b instead (result discarded) — bit-identical.
+__device__ __forceinline__ double ddiv(double a, double b) {
+    const bool zero_num = (a == 0.0) && (b != 0.0) && (fabs(b) <= 1.7976931348623157e308);   // false for NaN / inf / 0
+    double num = zero_num ? 1.0 : a;
+    asm("" : "+d"(num));      // opaque: otherwise the compiler divides the original (zero) numerator, whose quotient is dead
+    const double q = __ddiv_rn(num, b);
+    const double z = __longlong_as_double((__double_as_longlong(a) ^ __double_as_longlong(b)) & (long long)0x8000000000000000ull);
+    return zero_num ? z : q;
+}
 
 // Portfolio.valorisation (portfolio.py:7-13): sum([asset*price, fiat, -ia*price, -if]) left to right.
 __device__ __forceinline__ double valorisation(const Portfolio& s, double price) {

@@ -117,7 +117,7 @@ obs_vec_kernel(const GteParams P, const GteData D, const GteState S, float* __re
 }
 
 // ---- TMA gather: warp-specialised producer / consumer pipeline -----------------------------------------
-// One CTA = 4 consumer warps + 1 producer warp working on ONE pipeline over 32-env tiles (strided over the grid),
+// One CTA = 4 consumer warps + 1 producer warp + 1 store warp working on ONE pipeline over 32-env tiles (strided over the grid),
 // each tile cut into groups of G consecutive envs:
 //   producer warp : owns the metadata of the next tile (one env per lane, one coalesced load per array a whole
 //                   tile ahead), turns it ONCE per env into the window address and the first live window row,
@@ -128,22 +128,22 @@ obs_vec_kernel(const GteParams P, const GteData D, const GteState S, float* __re
 //                   16-byte chunks are XOR-swizzled so the consumers' column reads spread over the banks, then
 //                   position-index rows);
 //   consumer warps: wait on both full mbarriers, patch the dynamic columns smem->smem (128 threads = G envs x
-//                   128/G slots per pass; rows before the episode start stay zero), fence.proxy.async, meet on
-//                   a named barrier; one thread then issues the SINGLE bulk store of the G contiguous windows,
-//                   hands the ring tile back after the tile's last group and, once the PREVIOUS group's store
-//                   has finished reading shared memory, hands that window stage back.
+//                   128/G slots per pass; rows before the episode start stay zero), fence.proxy.async, and each
+//                   warp arrives on the stage's ready mbarrier (and, after the tile's last group, hands the ring
+//                   block back) without ever meeting the other warps;
+//   store warp    : one thread waits for a ready stage, issues the SINGLE bulk store of the G contiguous windows
+//                   and, once the PREVIOUS group's store has finished reading shared memory, hands that window
+//                   stage back to the producer — the store drain never blocks the consumers.
 // Evidence for this shape is in profiles/r01_tuning.md (per-warp pipelines were bound by the instruction
 // chain of too few resident warps; consumers of a unified pipeline mostly waited on the HBM ring loads).
 constexpr int kCoopConsumerWarps = 4;
-constexpr int kCoopThreads = (kCoopConsumerWarps + 1) * 32;
+constexpr int kCoopThreads = (kCoopConsumerWarps + 2) * 32;       // + producer warp + store warp
 constexpr int kTileEnvs = 32;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void consumer_barrier() {
-    asm volatile("bar.sync 1, %0;" :: "n"(kCoopConsumerWarps * 32) : "memory");
-}
+
 // WS window stages of G envs and RT ring-tile stages per CTA.  The ring tiles come from HBM (slow under a
 // saturating write stream) and only need the tile index, the windows come from L2 and need the envs'
 // metadata: ring tiles are requested a whole tile ahead, the big window buffers are only held for an L2
@@ -160,7 +160,7 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
                                                                  // by then the stage it reuses has been handed back
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_w[WS], empty_w[WS], full_r[RT], empty_r[RT];
+    __shared__ __align__(8) uint64_t full_w[WS], ready_w[WS], empty_w[WS], full_r[RT], empty_r[RT];
     __shared__ int first_live[2][kTileEnvs];                     // per tile parity: first window row of the episode
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool ring = sh.nd > 0;
@@ -171,9 +171,11 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < WS; ++s) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], 1); }
+        for (int s = 0; s < WS; ++s) {
+            mbar_init(&full_w[s], 1); mbar_init(&ready_w[s], kCoopConsumerWarps); mbar_init(&empty_w[s], 1);
+        }
 #pragma unroll
-        for (int s = 0; s < RT; ++s) { mbar_init(&full_r[s], 1); mbar_init(&empty_r[s], 1); }
+        for (int s = 0; s < RT; ++s) { mbar_init(&full_r[s], 1); mbar_init(&empty_r[s], kCoopConsumerWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -236,10 +238,32 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
             pc = pn;
             pn = load_tile(k + 2);
         }
+    } else if (warp == kCoopConsumerWarps + 1) {
+        // ------------------------------------------------------------------ store warp (one thread)
+        if (lane == 0) {
+            int q = 0;
+            for (int k = 0; tile_env0(k) < env_end; ++k) {
+                for (int gi = 0; gi < GROUPS; ++gi, ++q) {
+                    const int n_valid = group_valid(q);
+                    if (n_valid == 0) break;
+                    const int ws = q % WS;
+                    mbar_wait(&ready_w[ws], (uint32_t)(q / WS) & 1u);        // every consumer warp has patched the group
+                    bulk_s2g(reinterpret_cast<char*>(obs) + group_env0(q) * (int64_t)win_bytes,
+                             wbase + (size_t)ws * wstage_bytes, (uint32_t)n_valid * win_bytes);
+                    bulk_commit();
+                    if (q > 0) {
+                        bulk_wait_read<1>();                     // the previous group's store has left smem
+                        mbar_arrive(&empty_w[(q - 1) % WS]);
+                    }
+                }
+            }
+            bulk_wait_read<0>();                                 // smem must outlive the last store's reads
+        }
     } else {
         // ------------------------------------------------------------------ consumer warps
         // thread -> (env g of the group, slot t of the pass): the G lanes sharing a slot read one 16-byte chunk of
-        // the swizzled real_position row, lanes of different slots hit different chunks (banks)
+        // the swizzled real_position row, lanes of different slots hit different chunks (banks).  The warps never
+        // meet: each one signals the store warp (and, after a tile's last group, the producer) on its own.
         const int g = tid % G, t = tid / G;
         const int s0 = ring ? (int)((*S.ring_clock + 1ull) % (uint64_t)sh.W) : 0;      // ring slot of window row 0
         int q = 0;
@@ -248,12 +272,11 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
             for (int gi = 0; gi < GROUPS; ++gi, ++q) {
                 const int n_valid = group_valid(q);
                 if (n_valid == 0) break;
-                const int64_t env0 = group_env0(q);
                 const int ws = q % WS;
                 unsigned char* sbuf = wbase + (size_t)ws * wstage_bytes;
                 mbar_wait(&full_w[ws], (uint32_t)(q / WS) & 1u);             // windows landed (acquire: first_live too)
                 if (ring) {
-                    mbar_wait(&full_r[rs], (uint32_t)(k / RT) & 1u);         // the tile's ring slots landed
+                    mbar_wait(&full_r[rs], (uint32_t)(k / RT) & 1u);         // the tile's ring block landed
                     if (g < n_valid) {
                         const int e = gi * G + g;                            // env within the tile
                         const int live0 = first_live[k & 1][e];
@@ -271,19 +294,13 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
                     }
                     fence_proxy_async();                         // generic-proxy smem writes -> visible to TMA
                 }
-                consumer_barrier();
-                if (tid == 0) {
-                    if (ring && gi == GROUPS - 1) mbar_arrive(&empty_r[rs]);  // the tile's ring slots are consumed
-                    bulk_s2g(reinterpret_cast<char*>(obs) + env0 * (int64_t)win_bytes, sbuf, (uint32_t)n_valid * win_bytes);
-                    bulk_commit();
-                    if (q > 0) {
-                        bulk_wait_read<1>();                     // the previous group's store has left smem
-                        mbar_arrive(&empty_w[(q - 1) % WS]);
-                    }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&ready_w[ws]);                   // release: this warp's share of the group is patched
+                    if (ring && gi == GROUPS - 1) mbar_arrive(&empty_r[rs]);  // ... and its reads of the ring block are done
                 }
             }
         }
-        if (tid == 0) bulk_wait_read<0>();                       // smem must outlive the last store's reads
     }
 }
 
