@@ -84,20 +84,29 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t_end = time.time() + 2.0                 # wait for the first row: nvidia-smi needs tens of ms to start
+            while not self.rows and time.time() < t_end:
+                time.sleep(0.005)
         except Exception:  # noqa: BLE001
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Rows sampled inside [t0, t1] (host clock; one sampling period of slack on both sides); when the timed
+        region is shorter than the sampler's period, the rows taken under the same load since start()."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.05)
         self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 is None or (t0 - 0.025 <= t <= t1 + 0.025)]
+        window = "timed region"
+        if not rows:
+            rows, window = [r for _, r in self.rows], "warm-up + timed region (timed region shorter than the 20 ms sampling period)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:  # noqa: BLE001
@@ -106,7 +115,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def cpu_port_rate(wl, n_sample, seconds, threads, seed=0):
@@ -240,7 +249,9 @@ def run_reference_arm(args, wl, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None,
+                    help="timed iterations (default 200; 2000 / 5000 for the small c3 / c2 workloads, whose "
+                         "iterations take tens of microseconds, so that the clocks can be sampled during the timed region)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5", choices=list(WORKLOADS))
@@ -254,6 +265,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = {"c3": 2000, "c2": 5000}.get(args.workload, 200) if args.impl == "b200" else 200
     wl = dict(WORKLOADS[args.workload])
     if args.envs_per_gpu:
         wl["envs"] = args.envs_per_gpu
@@ -320,12 +333,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                      # already running (and past its start-up) when the timed region begins
     for k in range(max(args.warmup, 3)):
         lockstep(k)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     # per-kernel CUDA events INSIDE the timed region: on every 8th iteration env.step() issues its two kernels as
     # two calls (the very kernels gte_step_obs launches) with events on the launching stream around each
     env._kernel_events = [] if wl["windows"] is not None else None
@@ -333,6 +346,7 @@ def main():
     env._kernel_events_every = 1 if (wl["envs"] >= 2 ** 20 or args.steps < 64) else 8
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.time()
     e0.record()
     for k in range(args.steps):
         lockstep(k)
@@ -340,7 +354,7 @@ def main():
         torch.cuda.current_stream().wait_stream(side)
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_host0, time.time()) if rank == 0 else None
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
