@@ -23,6 +23,9 @@ def __getattr__(name):          # torch / the CUDA library are only imported whe
     if name in _LAZY:
         from . import vector_env
         return getattr(vector_env, name)
+    if name == "SB3VecEnv":
+        from .sb3_adapter import SB3VecEnv
+        return SB3VecEnv
     if name == "build":
         from ._cabi import build
         return build

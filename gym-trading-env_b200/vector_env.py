@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import glob as _glob
+import os
 from collections.abc import Mapping
 from pathlib import Path
 
@@ -794,6 +795,38 @@ class TradingVectorEnv:
         if all(s.index is not None for s in self._series):
             df["date"] = np.array([self._series[d].index[i] for d, i in zip(ds, idx)])
         return df
+
+    def save_for_render(self, dir="render_logs", which=0, episode=-1):
+        """``TradingEnv.save_for_render`` (environments.py:296-307) for tracked env number `which`: the History rows of
+        one episode joined with the market frame on the date index, pickled to ``{dir}/{name}_{timestamp}.pkl`` — the
+        file the reference's ``Renderer`` (renderer.py:51-58) loads.  `episode` indexes the FINISHED episodes of the
+        log (-1 = the latest; the reference object only ever holds its current episode), falling back to the running
+        episode when none has finished.  Returns the path."""
+        import datetime
+        import pandas as pd
+        h = self.tracked_history(which)
+        starts = list(np.flatnonzero(h["new_episode"].to_numpy())) + [len(h)]
+        episodes = [(a, b) for a, b in zip(starts[:-1], starts[1:])]
+        finished = [(a, b) for a, b in episodes if bool(h["terminated"].iloc[b - 1] or h["truncated"].iloc[b - 1])]
+        a, b = finished[episode] if finished else episodes[-1]
+        ep = h.iloc[a:b]
+        srs = self._series[int(ep["dataset_idx"].iloc[0])]
+        assert all(c in srs.info for c in ("open", "high", "low", "close")), \
+            "Your DataFrame needs to contain columns : open, high, low, close to render !"        # :297
+        if srs.index is None:
+            raise ValueError("save_for_render needs a DatetimeIndex (History's 'date' column, environments.py:188)")
+        market = pd.DataFrame({**{n: srs.features[:, j] for j, n in enumerate(srs.feature_names)}, **srs.info},
+                              index=pd.DatetimeIndex(srs.index, name="date"))
+        idx = ep["idx"].to_numpy()
+        hist = ep.drop(columns=["terminated", "truncated", "new_episode", "dataset_idx", "data_close"])
+        for c, col in srs.info.items():                                          # History's data_<info column> (:131-134)
+            hist["data_" + c] = col[idx]
+        hist = hist.set_index("date").sort_index()
+        render_df = market.join(hist, how="inner")                               # :304
+        os.makedirs(dir, exist_ok=True)
+        path = f"{dir}/{self.name}_{datetime.datetime.now().strftime('%Y-%m-%d_%H-%M-%S')}.pkl"
+        render_df.to_pickle(path)
+        return path
 
     # ------------------------------------------------------------------ metrics / errors / state
     def get_metrics(self, total=True):

@@ -1,0 +1,81 @@
+"""GPU tests of the caller-facing adapters around the hot path: the
+stable-baselines3 VecEnv view and `save_for_render`, both checked against goldens recorded from the reference."""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sb3_vecenv_view_matches_the_reference_golden():
+    """SB3's VecEnv contract on top of the CUDA env: numpy obs / float32 rewards / dones, and for every env whose
+    episode ended `terminal_observation` = what the reference's step() returned, `TimeLimit.truncated` = its flag."""
+    import gym_trading_env_b200 as gte
+    g = H.load_golden("c3_windows_leveraged")
+    env = H.make_device_env(g, final_obs=True)
+    venv = gte.SB3VecEnv(env, info_keys=("portfolio_valuation", "idx"))
+    n = g["params"]["n_envs"]
+    assert venv.num_envs == n and venv.action_space.n == len(g["positions"])
+    assert venv.observation_space.shape == g["obs0"].shape[1:]
+    obs = venv.reset()
+    assert isinstance(obs, np.ndarray) and obs.dtype == np.float32
+    H.assert_bits(obs, g["obs0"], "reset obs")
+    ended_seen = 0
+    for k in range(g["actions"].shape[0]):
+        venv.step_async(g["actions"][k])
+        obs, rew, dones, infos = venv.step_wait()
+        H.assert_bits(obs, g["obs"][k], f"step {k} obs")
+        assert rew.dtype == np.float32
+        np.testing.assert_allclose(rew, g["reward"][k].astype(np.float32), rtol=1e-6, atol=1e-12)
+        want_done = (g["terminated"][k] | g["truncated"][k]).astype(bool)
+        assert np.array_equal(dones, want_done)
+        assert isinstance(infos, list) and len(infos) == n
+        for i in range(n):
+            assert infos[i]["idx"] == g["post_idx"][k, i]
+            if want_done[i]:
+                ended_seen += 1
+                H.assert_bits(infos[i]["terminal_observation"], g["step_obs"][k, i], f"step {k} env {i} terminal obs")
+                assert infos[i]["TimeLimit.truncated"] == bool(g["truncated"][k, i] and not g["terminated"][k, i])
+            else:
+                assert "terminal_observation" not in infos[i]
+    assert ended_seen > 0
+    assert venv.env_is_wrapped(object) == [False] * n and venv.get_attr("num_envs", [0, 1]) == [n, n]
+    venv.close()
+
+
+def test_save_for_render_writes_the_frame_the_reference_renderer_loads(tmp_path):
+    """The pickle holds one episode: market columns joined with the History columns on the date index
+    (environments.py:296-307); valuations / positions equal the golden rows of that episode."""
+    import gym_trading_env_b200 as gte
+    g = H.load_golden("c1_single_nowindow")
+    T = int(g["lengths"][0])
+    index = pd.date_range("2000-01-01", periods=T, freq="h").values
+    close = np.ascontiguousarray(g["price"][0, :T])
+    info = {"open": close * 1.001, "high": close * 1.002, "low": close * 0.998, "close": close}
+    srs = gte.SeriesArrays(np.ascontiguousarray(g["features"][0, :T]), close,
+                           [f"feature_{j}" for j in range(g["features"].shape[2])], info, index)
+    kw = H.env_kwargs(g)
+    env = gte.TradingVectorEnv(srs, num_envs=1, reset_plan=g["plan"], verbose=0, debug_outputs=True, name="golden", **kw)
+    env.track([0], max_steps=4000)
+    env.reset()
+    K = g["actions"].shape[0]
+    import torch
+    for k in range(K):
+        env.step(torch.as_tensor(g["actions"][k], device=env.device))
+    path = env.save_for_render(dir=str(tmp_path), which=0, episode=0)
+    df = pd.read_pickle(path)
+    first_end = int(np.flatnonzero(g["terminated"][:, 0] | g["truncated"][:, 0])[0])
+    assert len(df) == first_end + 2                                    # the reset row + one row per step
+    for c in ("open", "high", "low", "close", "feature_0", "portfolio_valuation", "position", "real_position", "reward",
+              "idx", "step", "position_index", "data_close", "data_high", "portfolio_distribution_fiat"):
+        assert c in df.columns, c
+    assert df.index.name == "date" and df.index.is_monotonic_increasing
+    np.testing.assert_array_equal(df["idx"].to_numpy()[1:], g["idx"][:first_end + 1, 0])
+    np.testing.assert_allclose(df["portfolio_valuation"].to_numpy()[1:], g["valuation"][:first_end + 1, 0], rtol=H.RTOL, atol=H.ATOL)
+    np.testing.assert_array_equal(df["position"].to_numpy()[1:], g["position"][:first_end + 1, 0])
+    np.testing.assert_array_equal(df["data_close"].to_numpy(), df["close"].to_numpy())
+    assert path.startswith(str(tmp_path)) and "/golden_" in path
