@@ -306,26 +306,13 @@ def main():
     actions = torch.randint(0, len(wl["positions"]), (n_sets, N), generator=gen, device=dev, dtype=torch.int64)
     env.reset()
 
-    side = torch.cuda.Stream(device=dev)
-    red_buf = torch.zeros(8, dtype=torch.float64, device=dev)
-    red_total = torch.zeros(8, dtype=torch.float64, device=dev)
-    side_done = [None]
+    if world > 1:
+        # C5: NCCL all-reduce(sum) of the 8 fp64 episode metrics EVERY iteration, issued by the env between its two
+        # kernels on a side stream (overlaps the gather; the next iteration only waits for the 64-byte snapshot)
+        env.enable_metric_allreduce()
 
     def lockstep(k):
-        if side_done[0] is not None:
-            torch.cuda.current_stream().wait_event(side_done[0])     # metrics_step is about to be overwritten
         env.step(actions[k % n_sets])
-        if world > 1:                                                # per-iteration NCCL allreduce, off the critical path
-            ev = torch.cuda.Event()
-            ev.record()
-            with torch.cuda.stream(side):
-                side.wait_event(ev)
-                red_buf.copy_(env._metrics_step)
-                dist.all_reduce(red_buf)
-                red_total.add_(red_buf)
-                done = torch.cuda.Event()
-                done.record()
-            side_done[0] = done
 
     def barrier():
         torch.cuda.synchronize()
@@ -339,19 +326,18 @@ def main():
     for k in range(max(args.warmup, 3)):
         lockstep(k)
     barrier()
-    # per-kernel CUDA events INSIDE the timed region: on every 8th iteration env.step() issues its two kernels as
-    # two calls (the very kernels gte_step_obs launches) with events on the launching stream around each
+    # per-kernel CUDA events INSIDE the timed region: on every 4th (8th) iteration env.step() issues its two kernels
+    # as two calls (the very kernels gte_step_obs launches) with events on the launching stream around each; the
+    # event records cost ~3 us per iteration they bracket, hence not every iteration
     env._kernel_events = [] if wl["windows"] is not None else None
-    # iterations of tens of microseconds are perturbed by the extra call + event records: sample every 8th there
-    env._kernel_events_every = 1 if (wl["envs"] >= 2 ** 20 or args.steps < 64) else 8
+    env._kernel_events_every = 1 if args.steps < 64 else (4 if wl["envs"] >= 2 ** 20 else 8)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_host0 = time.time()
     e0.record()
     for k in range(args.steps):
         lockstep(k)
-    if world > 1:
-        torch.cuda.current_stream().wait_stream(side)
+    env.wait_metric_allreduce()              # the timed region ends when the last all-reduce has landed
     e1.record()
     barrier()
     clocks = sampler.stop(t_host0, time.time()) if rank == 0 else None
@@ -361,6 +347,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     env.check_errors()
+    if world > 1:
+        # the per-iteration all-reduces must add up to the all-reduced local totals (counts exactly, fp sums to rounding)
+        torch.cuda.synchronize()
+        tot = env._metrics_total.clone()
+        dist.all_reduce(tot)
+        got = env.global_metrics_total
+        if not (torch.equal(got[:3], tot[:3]) and torch.equal(got[5], tot[5]) and torch.allclose(got, tot, rtol=1e-9, atol=1e-9)):
+            raise RuntimeError(f"per-iteration metric all-reduce disagrees with the local totals: {got.tolist()} vs {tot.tolist()}")
     value = world * N * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (window gather; the step kernel when windows=None) ----
@@ -398,7 +392,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_env": dom_bytes, "kernel_ms": obs_ms_avg,
-                "timing": "CUDA events on the launching stream around the launches of every %s iteration of the timed region" % ("single" if env._kernel_events_every == 1 else "8th"),
+                "timing": "CUDA events on the launching stream around the launches of every %s iteration of the timed region" % {1: "single", 4: "4th", 8: "8th"}[env._kernel_events_every],
                 "step_kernel_ms": step_ms_avg,
                 "step_kernel": {"algorithmic_bytes_per_env": a_step, "achieved": a_step * N / (step_ms_avg * 1e-3) / 1e9,
                                 "frac": a_step * N / (step_ms_avg * 1e-3) / 1e9 / peak},

@@ -271,6 +271,7 @@ class TradingVectorEnv:
         self._copy_in = self._copy_out = None
         self._track_ids = None
         self._limit_price = None
+        self._red_stream = None              # enable_metric_allreduce(): side stream of the per-iteration all-reduce
         self._kernel_events = None           # bench.py: list collecting (start, after step, after gather) CUDA events
         self._kernel_events_every = 1        # ... on every k-th iteration
         self._obs_variant = _cabi.OBS_VARIANTS[obs_variant]
@@ -565,6 +566,8 @@ class TradingVectorEnv:
             return ret
 
     def _step_launch(self, act, main):
+        if self._red_stream is not None and self._red_snapshot is not None:
+            main.wait_event(self._red_snapshot)             # metrics_step is about to be overwritten
         if self.keep_final_obs and self.autoreset:
             # step without the in-kernel reset, gather the terminal observations, keep those of the ended envs,
             # then reset exactly those envs and gather again (what a SAME_STEP vector env returns)
@@ -583,6 +586,7 @@ class TradingVectorEnv:
             # reward / flags leave for the host right after the step kernel, beside the gather
             hb = self._host_buffers()
             self._launch_step(C.c_void_p(act.data_ptr()))
+            self._issue_metric_allreduce(main)
             self._copy_out.wait_stream(main)
             with torch.cuda.stream(self._copy_out):
                 for k, t in (("reward", self._reward), ("terminated", self._terminated),
@@ -600,6 +604,12 @@ class TradingVectorEnv:
                 self._capture_graph()
             self._tick += 1
             self._graph.replay()
+        elif self._red_stream is not None and self.windows is not None and not (
+                self._kernel_events is not None and self._tick % self._kernel_events_every == 0):
+            # the all-reduce is issued between the two kernels so that it overlaps the gather
+            self._launch_step(C.c_void_p(act.data_ptr()))
+            self._issue_metric_allreduce(main)
+            self._launch_obs()
         elif self._kernel_events is not None and self.windows is not None and self._tick % self._kernel_events_every == 0:
             # (bench.py, every k-th iteration) the same two kernels as gte_step_obs, issued as two calls so that
             # CUDA events can bracket each of them without perturbing the other iterations
@@ -607,11 +617,13 @@ class TradingVectorEnv:
             ev[0].record()
             self._launch_step(C.c_void_p(act.data_ptr()))
             ev[1].record()
+            self._issue_metric_allreduce(main)
             self._launch_obs()
             ev[2].record()
             self._kernel_events.append(ev)
         else:
             self._launch_step_obs(C.c_void_p(act.data_ptr()))
+            self._issue_metric_allreduce(main)
         if self.output == "numpy":
             h = self._host_buffers()
             for k, t in (("obs", self._obs), ("reward", self._reward), ("terminated", self._terminated),
@@ -842,6 +854,40 @@ class TradingVectorEnv:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=async_op)
         return None
+
+    def enable_metric_allreduce(self):
+        """Sum the metric vector of EVERY lockstep iteration over all ranks (the path's only
+        collective, 8 doubles over NCCL / NVLink) into ``global_metrics_step`` / ``global_metrics_total``.  The
+        exchange rides a side stream: right after the step kernel the 64 bytes are snapshotted by the copy engine,
+        the all-reduce then runs beside the window gather (or beside the next step kernel once an SM has room),
+        and the next iteration only waits for the snapshot — never for the collective."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("enable_metric_allreduce() needs an initialised torch.distributed process group")
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self._red_stream = torch.cuda.Stream(device=self.device)
+        self.global_metrics_step, self.global_metrics_total = torch.zeros(8, **f64), torch.zeros(8, **f64)
+        self._red_snapshot = None
+
+    def _issue_metric_allreduce(self, main):
+        if self._red_stream is None:
+            return
+        import torch.distributed as dist
+        ev = torch.cuda.Event()
+        ev.record(main)                                  # the step kernel (which wrote metrics_step) is the last thing on main
+        with torch.cuda.stream(self._red_stream):
+            self._red_stream.wait_event(ev)
+            self.global_metrics_step.copy_(self._metrics_step, non_blocking=True)     # 64 B device-to-device copy
+            snap = torch.cuda.Event()
+            snap.record()
+            dist.all_reduce(self.global_metrics_step)
+            self.global_metrics_total.add_(self.global_metrics_step)
+        self._red_snapshot = snap
+
+    def wait_metric_allreduce(self):
+        """Make the current stream wait for the all-reduces issued so far (before reading ``global_metrics_*``)."""
+        if self._red_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._red_stream)
 
     def check_errors(self):
         """Synchronising check of the in-kernel error flags (device-resident actions are not validated on the host)."""

@@ -79,3 +79,38 @@ def test_save_for_render_writes_the_frame_the_reference_renderer_loads(tmp_path)
     np.testing.assert_array_equal(df["position"].to_numpy()[1:], g["position"][:first_end + 1, 0])
     np.testing.assert_array_equal(df["data_close"].to_numpy(), df["close"].to_numpy())
     assert path.startswith(str(tmp_path)) and "/golden_" in path
+
+
+def test_per_iteration_metric_allreduce_accumulates_the_step_metrics():
+    """enable_metric_allreduce(): the side-stream exchange (snapshot -> NCCL all-reduce -> accumulate) sees every
+    iteration's metric vector exactly once, also in the hybrid output mode (single-rank NCCL group here; the
+    multi-rank sums are checked by bench.py on every torchrun launch)."""
+    import torch
+    import torch.distributed as dist
+    import gym_trading_env_b200 as gte
+    if dist.is_initialized():
+        pytest.skip("a process group already exists in this process")
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29641", rank=0, world_size=1,
+                            device_id=torch.device("cuda", 0))
+    try:
+        g = H.load_golden("c3_windows_leveraged")
+        for output in ("torch", "hybrid"):
+            env = H.make_device_env(g, output=output)
+            env.enable_metric_allreduce()
+            env.reset()
+            per_step = []
+            for k in range(g["actions"].shape[0]):
+                a = g["actions"][k] if output == "hybrid" else torch.as_tensor(g["actions"][k], device=env.device)
+                env.step(a)
+                per_step.append(env._metrics_step.clone())
+            env.wait_metric_allreduce()
+            torch.cuda.synchronize()
+            assert torch.equal(env.global_metrics_step, per_step[-1])
+            want = torch.zeros(8, dtype=torch.float64, device=env.device)
+            for v in per_step:
+                want += v
+            assert torch.equal(env.global_metrics_total, want)
+            assert torch.equal(env.global_metrics_total, env._metrics_total)
+            assert float(env.global_metrics_total[0]) == float((g["terminated"] | g["truncated"]).sum())
+    finally:
+        dist.destroy_process_group()
