@@ -403,6 +403,26 @@ def main():
                                    "achieved": whole * (a_step + a_obs + a_static) / (a_step + a_obs),
                                    "frac": whole * (a_step + a_obs + a_static) / (a_step + a_obs) / peak}}}
 
+    # ---- launch / latency floor at small N (BASELINE config 2): the same iterations enqueued by ONE host call
+    # (env.rollout -> gte_rollout: a C loop of kernel launches, no Python between iterations) ----
+    latency = None
+    if wl["envs"] < 2 ** 20 and world == 1 and not args.cuda_graph:
+        K = 2000
+        acts_k = actions[torch.arange(K, device=dev) % n_sets]
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        us_open = float("inf")
+        for _ in range(4):                   # the GPU idled while the clocks were read: let the SM clock ramp up again
+            r0.record()
+            env.rollout(acts_k, keep_obs=False)
+            r1.record()
+            torch.cuda.synchronize()
+            us_open = min(us_open, 1e3 * r0.elapsed_time(r1) / K)
+        latency = {"step_call_us": 1e3 * ms / args.steps,
+                   "rollout_us_per_iteration": us_open, "rollout_env_steps_per_s": N / (us_open * 1e-6),
+                   "note": "step_call = env.step() per iteration from Python (one ctypes call, step + gather kernels); rollout = "
+                           "%d iterations enqueued by one gte_rollout call (open-loop actions; only the last observation is "
+                           "gathered, so with windows this is the step kernel's rate), best of 4" % K}
+
     # ---- e2e: public API with HOST numpy actions in and HOST numpy reward/terminated/truncated out.
     # "hybrid" (headline): observations stay device-resident for an on-device policy;
     # "numpy": the full observation windows also cross PCIe (2.5 KB per env-step: PCIe-bound). ----
@@ -467,6 +487,8 @@ def main():
             "clocks": clocks, "e2e": e2e, "e2e_full_obs_to_host": e2e_full,
             "gpu_launches": (1 if wl["windows"] is None else 2 * env.chunks) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
         }
+        if latency is not None:
+            out["latency"] = latency
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -82,7 +82,7 @@ class GteInfo(C.Structure):
 
 
 EXPORTS = ["gte_version", "gte_last_error", "gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs",
-           "gte_info", "gte_obs_variant_for", "gte_default_chunks", "gte_struct_size"]
+           "gte_rollout", "gte_info", "gte_obs_variant_for", "gte_default_chunks", "gte_struct_size"]
 
 
 def nvcc_command(out_path: str = LIB_PATH):
@@ -133,11 +133,13 @@ def load():
     lib.gte_gather_obs.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, C.c_int, C.c_void_p]
     lib.gte_step_obs.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, P(GteStepOut), C.c_void_p,
                                  C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.gte_rollout.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, C.c_int, P(GteStepOut), C.c_void_p,
+                                C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.gte_info.argtypes = [P(GteParams), P(GteData), P(GteState), P(GteInfo), C.c_void_p]
     lib.gte_obs_variant_for.argtypes = [P(GteParams), P(GteData)]
     lib.gte_default_chunks.argtypes = [C.c_int]
     lib.gte_default_chunks.restype = C.c_int
-    for name in ("gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs", "gte_info", "gte_obs_variant_for"):
+    for name in ("gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs", "gte_rollout", "gte_info", "gte_obs_variant_for"):
         getattr(lib, name).restype = C.c_int
     lib.gte_struct_size.argtypes = [C.c_int]
     lib.gte_struct_size.restype = C.c_int

@@ -100,6 +100,16 @@ int gte_step_obs(const GteParams* params, const GteData* data, const GteState* s
                                                            variant, n_chunks, static_cast<cudaStream_t>(stream)));
 }
 
+int gte_rollout(const GteParams* params, const GteData* data, const GteState* state, const int64_t* actions,
+                int n_steps, const GteStepOut* out, float* obs, int keep_obs, int autoreset, int variant, void* stream) {
+    if (int rc = check_common("gte_rollout", params, data, state)) return rc;
+    if (int rc = check_step_out("gte_rollout", actions, out)) return rc;
+    GTE_REQUIRE("gte_rollout", obs != nullptr && n_steps >= 1);
+    if (int rc = check_variant("gte_rollout", params, data, variant)) return rc;
+    return check_cuda("gte_rollout", gte::launch_rollout(*params, *data, *state, actions, n_steps, *out, obs, keep_obs,
+                                                         autoreset, variant, static_cast<cudaStream_t>(stream)));
+}
+
 int gte_gather_obs(const GteParams* params, const GteData* data, const GteState* state, float* obs,
                    int variant, void* stream) {
     if (int rc = check_common("gte_gather_obs", params, data, state)) return rc;

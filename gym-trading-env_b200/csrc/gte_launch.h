@@ -28,4 +28,8 @@ cudaError_t launch_step_obs(const GteParams& P, const GteData& D, const GteState
                             const GteStepOut& O, float* obs, int autoreset, int variant, int n_chunks,
                             cudaStream_t stream);
 
+cudaError_t launch_rollout(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
+                           int n_steps, const GteStepOut& O, float* obs, int keep_obs, int autoreset, int variant,
+                           cudaStream_t stream);
+
 }  // namespace gte

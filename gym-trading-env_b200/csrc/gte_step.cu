@@ -241,6 +241,36 @@ cudaError_t launch_step_obs(const GteParams& P, const GteData& D, const GteState
     return cudaStreamWaitEvent(stream, aux->join, 0);
 }
 
+// ---- n_steps iterations from one host call (open-loop action stream) ------------------------------
+cudaError_t launch_rollout(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
+                           int n_steps, const GteStepOut& O, float* obs, int keep_obs, int autoreset, int variant,
+                           cudaStream_t stream) {
+    const int64_t N = P.n_envs;
+    const int64_t obs_elems = N * (int64_t)(P.windows > 0 ? P.windows : 1) * (P.n_static + P.n_dyn);
+    cudaError_t e;
+    for (int k = 0; k < n_steps; ++k) {
+        GteStepOut o = O;                                   // iteration k writes copy k of every per-env array
+        o.reward += k * N; o.terminated += k * N; o.truncated += k * N;
+        if (o.valuation) o.valuation += k * N;
+        if (o.real_position) o.real_position += k * N;
+        if (o.info_idx) o.info_idx += k * N;
+        if (o.info_step) o.info_step += k * N;
+        if (o.pre_reset_portfolio) o.pre_reset_portfolio += k * 4 * N;
+        const bool want_obs = keep_obs || k == n_steps - 1;
+        float* obs_k = obs + (keep_obs ? k * obs_elems : 0);
+        const int64_t* a = actions + k * N;
+        if (P.windows == 0) {                               // the step kernel writes the one-row observation itself
+            e = launch_step_range(P, D, S, a, o, autoreset, 0, P.n_envs, kChunkFirst | kChunkLast, stream,
+                                  want_obs ? obs_k : nullptr);
+        } else {
+            e = launch_step(P, D, S, a, o, autoreset, stream);
+            if (e == cudaSuccess && want_obs) e = launch_obs_range(P, D, S, obs_k, variant, 0, P.n_envs, stream);
+        }
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t launch_info(const GteParams& P, const GteData& D, const GteState& S, const GteInfo& I,
                         cudaStream_t stream) {
     const int grid = (P.n_envs + kStepThreads - 1) / kStepThreads;

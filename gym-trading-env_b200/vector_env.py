@@ -706,6 +706,29 @@ class TradingVectorEnv:
                "valuation": torch.empty(K, N, dtype=torch.float64, device=dev)}
         if keep_obs:
             out["obs"] = torch.empty((K,) + tuple(self._obs.shape), dtype=torch.float32, device=dev)
+        if self._track_ids is None and not self.keep_final_obs and self._red_stream is None and self.autoreset:
+            # one C call enqueues all K iterations (gte_rollout); the observation windows are only gathered for the
+            # iterations whose observation is kept
+            term8 = torch.empty(K, N, dtype=torch.uint8, device=dev)
+            trunc8 = torch.empty(K, N, dtype=torch.uint8, device=dev)
+            o = _cabi.GteStepOut()
+            C.memmove(C.byref(o), C.byref(self._O), C.sizeof(o))
+            o.reward, o.terminated, o.truncated = out["reward"].data_ptr(), term8.data_ptr(), trunc8.data_ptr()
+            o.valuation = out["valuation"].data_ptr()
+            o.real_position = o.info_idx = o.info_step = o.pre_reset_portfolio = None
+            obs_buf = out["obs"] if keep_obs else self._obs
+            self._tick += K
+            _cabi.check(self._lib.gte_rollout(C.byref(self._P), C.byref(self._D), C.byref(self._S),
+                                              C.c_void_p(actions.data_ptr()), K, C.byref(o),
+                                              C.c_void_p(obs_buf.data_ptr()), int(keep_obs), 1,
+                                              self._obs_variant or 0, self._stream()), "gte_rollout")
+            out["terminated"], out["truncated"] = term8.view(torch.bool), trunc8.view(torch.bool)
+            # the persistent one-iteration outputs keep meaning "the last iteration"
+            self._reward.copy_(out["reward"][-1]); self._valuation.copy_(out["valuation"][-1])
+            self._terminated.copy_(term8[-1]); self._truncated.copy_(trunc8[-1])
+            if keep_obs:
+                self._obs.copy_(out["obs"][-1])
+            return out
         saved, self.output = self.output, "torch"
         try:
             for k in range(K):

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GTE_VERSION 104            /* 0.1.4 */
+#define GTE_VERSION 105            /* 0.1.5 */
 #define GTE_MAX_POSITIONS 64
 #define GTE_MAX_DATASETS 64        /* least-used rotation keeps a 64-bit "used this round" mask per env */
 #define GTE_N_METRICS 8
@@ -217,6 +217,18 @@ int gte_gather_obs(const GteParams* params, const GteData* data, const GteState*
 int gte_step_obs(const GteParams* params, const GteData* data, const GteState* state,
                  const int64_t* actions, const GteStepOut* out, float* obs, int autoreset,
                  int variant, int n_chunks, void* stream);
+
+/* n_steps lockstep iterations from a device-resident action stream, enqueued by ONE host call (the open-loop driver:
+ * replay of recorded actions, random-policy baselines, back-tests; at small N an iteration then costs a kernel launch
+ * instead of a trip through the host language).  actions: i64 [n_steps, N].  Every non-NULL per-env array of `out`
+ * (reward, terminated, truncated, valuation, real_position, info_idx, info_step, pre_reset_portfolio) holds n_steps
+ * consecutive copies of its one-iteration shape, iteration k writing copy k; metrics_step ends up holding the last
+ * iteration's metrics, metrics_total accumulates all of them.  keep_obs != 0: obs is f32 [n_steps, N, (W,) F] and
+ * every iteration's observation is gathered; keep_obs == 0: obs is f32 [N, (W,) F] and only the LAST iteration's
+ * observation is gathered (the dynamic-feature ring is kept up to date by the step kernel either way). */
+int gte_rollout(const GteParams* params, const GteData* data, const GteState* state,
+                const int64_t* actions, int n_steps, const GteStepOut* out, float* obs, int keep_obs,
+                int autoreset, int variant, void* stream);
 
 /* History's last row as tensors (environments.py:253-264, portfolio.py:49-57), from current state. */
 int gte_info(const GteParams* params, const GteData* data, const GteState* state,

@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/gte_b200.h but not exported"
     assert set(_cabi.EXPORTS) == set(_declared_functions())
     lib.gte_version.restype = ctypes.c_int
-    assert lib.gte_version() == 104
+    assert lib.gte_version() == 105
 
 
 def test_ctypes_struct_layout_matches_the_compiled_structs():

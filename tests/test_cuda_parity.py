@@ -311,21 +311,34 @@ def test_final_obs_mode_keeps_the_terminal_observation():
     assert seen >= 30
 
 
-def test_rollout_equals_stepping_one_by_one():
+@pytest.mark.parametrize("windows", [8, None])
+def test_rollout_equals_stepping_one_by_one(windows):
+    """rollout() = ONE gte_rollout call enqueueing K iterations: same results as K step() calls, with every
+    observation kept (keep_obs) and with only the last one gathered."""
     import torch
     import gym_trading_env_b200 as gte
     arr = gte.frame_to_arrays(gte.make_gbm_ohlcv(1500, seed=4))
-    kw = dict(positions=[-1, 0, 1], windows=8, trading_fees=1e-4, max_episode_duration=30, num_envs=500, seed=2, verbose=0)
-    a, b = gte.TradingVectorEnv(arr, **kw), gte.TradingVectorEnv(arr, **kw)
-    a.reset(); b.reset()
+    kw = dict(positions=[-1, 0, 1], windows=windows, trading_fees=1e-4, max_episode_duration=30, num_envs=500, seed=2, verbose=0)
+    a, b, c = gte.TradingVectorEnv(arr, **kw), gte.TradingVectorEnv(arr, **kw), gte.TradingVectorEnv(arr, **kw)
+    a.reset(); b.reset(); c.reset()
     g = torch.Generator(device=a.device); g.manual_seed(0)
     acts = torch.randint(0, 3, (40, 500), generator=g, device=a.device)
     out = a.rollout(acts, keep_obs=True)
+    last = c.rollout(acts[:25])                              # observation of the last iteration only ...
+    last2 = c.rollout(acts[25:])                             # ... and the ring stays current across calls
     for k in range(40):
         obs, rew, term, trunc, _ = b.step(acts[k])
         assert torch.equal(out["obs"][k].view(torch.int32), obs.view(torch.int32))
         assert torch.equal(out["reward"][k], rew) and torch.equal(out["terminated"][k], term) and torch.equal(out["truncated"][k], trunc)
-    assert torch.equal(a._metrics_total, b._metrics_total)
+        assert torch.equal(out["valuation"][k], b._valuation)
+    assert torch.equal(torch.cat([last["reward"], last2["reward"]]), out["reward"])
+    assert torch.equal(torch.cat([last["terminated"], last2["terminated"]]), out["terminated"])
+    for e in (a, c):
+        assert torch.equal(e._obs.view(torch.int32), b._obs.view(torch.int32))
+        assert torch.equal(e._metrics_total, b._metrics_total)
+        for name in ("_asset", "_fiat", "_pos_idx", "_step", "_ep_start", "_reward", "_terminated", "_valuation"):
+            assert torch.equal(getattr(e, name), getattr(b, name)), name
+    assert "obs" not in last and out["obs"].shape[0] == 40
 
 
 def test_limit_order_api_validation():
