@@ -1,6 +1,6 @@
 # tuning helper: one line per configuration given as "ENV=VAL ..." strings; WORKLOAD selects the bench workload
 WORKLOAD=${WORKLOAD:-c5}
-for cfg in "X=0" "GTE_TMA_L2PROMO=1" "GTE_TMA_L2PROMO=2" "GTE_TMA_L2PROMO=3" "GTE_TMA_STAGES=3 GTE_TMA_RTILES=3 GTE_TMA_GROUP=4" "GTE_TMA_STAGES=4 GTE_TMA_RTILES=2 GTE_TMA_GROUP=4" "GTE_TMA_STAGES=2 GTE_TMA_RTILES=2 GTE_TMA_GROUP=4" "GTE_TMA_STAGES=3 GTE_TMA_RTILES=2 GTE_TMA_GROUP=2" "GTE_TMA_STAGES=6 GTE_TMA_RTILES=2 GTE_TMA_GROUP=2" "GTE_TMA_STAGES=6 GTE_TMA_RTILES=3 GTE_TMA_GROUP=2" "GTE_TMA_STAGES=3 GTE_TMA_RTILES=2 GTE_TMA_GROUP=8" "GTE_TMA_STAGES=2 GTE_TMA_RTILES=2 GTE_TMA_GROUP=8"; do
+for cfg in "X=0" "GTE_TMA_STAGES=4 GTE_TMA_RTILES=2 GTE_TMA_GROUP=4" "GTE_TMA_STAGES=3 GTE_TMA_RTILES=3 GTE_TMA_GROUP=4" "GTE_TMA_STAGES=3 GTE_TMA_RTILES=2 GTE_TMA_GROUP=2" "GTE_TMA_STAGES=6 GTE_TMA_RTILES=2 GTE_TMA_GROUP=2" "GTE_TMA_STAGES=3 GTE_TMA_RTILES=2 GTE_TMA_GROUP=8"; do
   env $cfg python bench.py --workload $WORKLOAD --no-e2e --no-cpu --steps ${STEPS:-100} --warmup 5 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
