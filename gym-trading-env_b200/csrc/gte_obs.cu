@@ -148,12 +148,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // saturating write stream) and only need the tile index, the windows come from L2 and need the envs'
 // metadata: ring tiles are requested a whole tile ahead, the big window buffers are only held for an L2
 // round trip + patch + store drain.
-template <int WS, int RT, int G>
+template <int WS, int RT, int G, int UNIT = kTileEnvs>
 __global__ void __launch_bounds__(kCoopThreads)
 obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float* __restrict__ obs,
                     const ObsShape sh, const int env_begin, const int env_end) {
     static_assert(RT >= 2, "a ring tile is requested while the previous one is being consumed");
-    constexpr int GROUPS = kTileEnvs / G;                        // groups per tile
+    static_assert(UNIT % G == 0 && kTileEnvs % UNIT == 0, "a work unit is a whole number of groups inside one ring block");
+    // work unit ("tile") = UNIT consecutive envs inside one 32-env ring block: 32 normally, 16 or 8 when the batch
+    // is so small that whole blocks would leave CTAs idle or unevenly loaded (the block is then fetched once per unit)
+    constexpr int unit_envs = UNIT;
+    constexpr int GROUPS = UNIT / G;                             // groups per tile
     constexpr int NCONS = kCoopConsumerWarps * 32;
     constexpr int SPP = NCONS / G;                               // ring slots patched per pass
     constexpr int RING_AT = WS < GROUPS - 1 ? WS : GROUPS - 1;   // group at which the tile RT-1 ahead is requested:
@@ -180,11 +184,11 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
     }
     __syncthreads();
 
-    // tile k of this CTA = 32 consecutive envs, tiles strided over the grid; group q = (tile q/GROUPS, slot q%GROUPS)
-    auto tile_env0 = [&](int k) -> int64_t { return env_begin + (((int64_t)blockIdx.x + (int64_t)k * gridDim.x) << 5); };
-    auto group_env0 = [&](int q) -> int64_t { return tile_env0(q / GROUPS) + (q % GROUPS) * G; };
-    auto group_valid = [&](int q) -> int {                       // envs of group q inside [env_begin, env_end)
-        const int64_t left = (int64_t)env_end - group_env0(q);
+    // tile k of this CTA = unit_envs consecutive envs, tiles strided over the grid; group gi of it = G envs
+    auto tile_env0 = [&](int k) -> int64_t { return env_begin + ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * unit_envs; };
+    auto group_env0 = [&](int k, int gi) -> int64_t { return tile_env0(k) + gi * G; };
+    auto group_valid = [&](int k, int gi) -> int {               // envs of the group inside [env_begin, env_end)
+        const int64_t left = (int64_t)env_end - group_env0(k, gi);
         return left >= G ? G : (left > 0 ? (int)left : 0);
     };
 
@@ -195,7 +199,7 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
             TilePre p;
             p.src = 0ull; p.first_live = 0;
             const int64_t env = tile_env0(k) + lane;
-            if (env < env_end) {
+            if (lane < unit_envs && env < env_end) {
                 const int ep = __ldg(S.ep_start + env), st = __ldg(S.step + env), ds = __ldg(S.dataset_idx + env);
                 p.first_live = sh.W - 1 - st;                    // window row of ep_start (<= 0: the whole window is live)
                 p.src = (unsigned long long)window_src(D, sh, ds, ep + st + 1 - sh.W);
@@ -216,7 +220,7 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
         int q = 0;
         for (int k = 0; tile_env0(k) < env_end; ++k) {
             for (int gi = 0; gi < GROUPS; ++gi, ++q) {
-                const int n_valid = group_valid(q);
+                const int n_valid = group_valid(k, gi);
                 if (n_valid == 0) break;
                 if (lane == 0 && gi == RING_AT) issue_ring(k + RT - 1);
                 __syncwarp();
@@ -244,11 +248,11 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
             int q = 0;
             for (int k = 0; tile_env0(k) < env_end; ++k) {
                 for (int gi = 0; gi < GROUPS; ++gi, ++q) {
-                    const int n_valid = group_valid(q);
+                    const int n_valid = group_valid(k, gi);
                     if (n_valid == 0) break;
                     const int ws = q % WS;
                     mbar_wait(&ready_w[ws], (uint32_t)(q / WS) & 1u);        // every consumer warp has patched the group
-                    bulk_s2g(reinterpret_cast<char*>(obs) + group_env0(q) * (int64_t)win_bytes,
+                    bulk_s2g(reinterpret_cast<char*>(obs) + group_env0(k, gi) * (int64_t)win_bytes,
                              wbase + (size_t)ws * wstage_bytes, (uint32_t)n_valid * win_bytes);
                     bulk_commit();
                     if (q > 0) {
@@ -270,7 +274,7 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
         for (int k = 0; tile_env0(k) < env_end; ++k) {
             const int rs = k % RT;
             for (int gi = 0; gi < GROUPS; ++gi, ++q) {
-                const int n_valid = group_valid(q);
+                const int n_valid = group_valid(k, gi);
                 if (n_valid == 0) break;
                 const int ws = q % WS;
                 unsigned char* sbuf = wbase + (size_t)ws * wstage_bytes;
@@ -278,8 +282,8 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
                 if (ring) {
                     mbar_wait(&full_r[rs], (uint32_t)(k / RT) & 1u);         // the tile's ring block landed
                     if (g < n_valid) {
-                        const int e = gi * G + g;                            // env within the tile
-                        const int live0 = first_live[k & 1][e];
+                        const int live0 = first_live[k & 1][gi * G + g];
+                        const int e = (int)(tile_env0(k) & 31) + gi * G + g;      // env lane within the 32-env ring block
                         float* fbuf = reinterpret_cast<float*>(sbuf + (size_t)g * win_bytes);
                         const unsigned char* rtile = rbase + (size_t)rs * rstride;
                         for (int s = t; s < sh.W; s += SPP) {
@@ -313,8 +317,24 @@ static size_t tma_smem_bytes(const ObsShape& sh, const TmaConfig& c) {
     return (size_t)c.group * c.wstages * sh.win_bytes + ring;
 }
 
-static ObsKernelFn tma_kernel(const TmaConfig& c) {
-    // (window stages, ring-tile stages, envs per group) combinations compiled in
+static ObsKernelFn tma_kernel(const TmaConfig& c, int unit = kTileEnvs) {
+    // (window stages, ring-tile stages, envs per group) combinations compiled in; smaller work units for the default shapes
+    if (unit == 16) {
+        switch (c.wstages * 10000 + c.rtiles * 100 + c.group) {
+            case 30201: return obs_tma_coop_kernel<3, 2, 1, 16>;
+            case 30202: return obs_tma_coop_kernel<3, 2, 2, 16>;
+            case 30204: return obs_tma_coop_kernel<3, 2, 4, 16>;
+            default: return nullptr;
+        }
+    }
+    if (unit == 8) {
+        switch (c.wstages * 10000 + c.rtiles * 100 + c.group) {
+            case 30201: return obs_tma_coop_kernel<3, 2, 1, 8>;
+            case 30202: return obs_tma_coop_kernel<3, 2, 2, 8>;
+            case 30204: return obs_tma_coop_kernel<3, 2, 4, 8>;
+            default: return nullptr;
+        }
+    }
     switch (c.wstages * 10000 + c.rtiles * 100 + c.group) {
         case 30201: return obs_tma_coop_kernel<3, 2, 1>;
         case 30202: return obs_tma_coop_kernel<3, 2, 2>;
@@ -401,27 +421,39 @@ cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteStat
         if (!obs_tma_supported(P, D)) return cudaErrorInvalidValue;
         const TmaConfig cfg = tma_config(sh);
         const size_t smem = tma_smem_bytes(sh, cfg);
-        ObsKernelFn kern = tma_kernel(cfg);
-        if (kern == nullptr) return cudaErrorInvalidValue;
+        if (tma_kernel(cfg) == nullptr) return cudaErrorInvalidValue;
         const int threads = kCoopThreads;
-        static ObsKernelFn configured_kern = nullptr;      // opt-in to > 48 KB dynamic smem once per kernel
-        static size_t configured_smem = 0;
-        if (kern != configured_kern || smem > configured_smem) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured_kern = kern;
-            configured_smem = smem;
-        }
         int per_sm = (int)((227 * 1024) / (smem + 2048));
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 2048 / threads) per_sm = 2048 / threads;
         if (per_sm > 32) per_sm = 32;
-        // work unit = one 32-env tile; persistent grid of <= SMs x per_sm CTAs, sized so that every CTA gets
-        // the same number of tiles (no straggler wave at mid-size N)
-        const int64_t need = ((int64_t)n_envs + 31) / 32;
+        // work unit = one 32-env tile, or half / a quarter of one when that spreads a small batch more evenly (the time
+        // of the launch follows the units of the busiest CTA x the unit size); persistent grid of <= SMs x per_sm CTAs,
+        // sized so that every CTA gets the same number of units (no straggler wave at mid-size N)
         const int64_t cap = (int64_t)sms * per_sm;
+        int unit = 32;
+        int64_t best = -1;
+        for (int u = 32; u >= 8 && u >= cfg.group; u /= 2) {
+            if (tma_kernel(cfg, u) == nullptr) continue;
+            const int64_t units = ((int64_t)n_envs + u - 1) / u;
+            const int64_t per_cta = (units + cap - 1) / cap;
+            if (u == 8 && per_cta > 1) break;                  // quarter tiles only while every CTA gets at most one
+            if (best < 0 || per_cta * u < best) { best = per_cta * u; unit = u; }
+        }
+        const int64_t need = ((int64_t)n_envs + unit - 1) / unit;
         const int64_t waves = (need + cap - 1) / cap;
         const int grid = (int)((need + waves - 1) / waves);
+        ObsKernelFn kern = tma_kernel(cfg, unit);
+        static ObsKernelFn configured_kern[8] = {};        // opt-in to > 48 KB dynamic smem once per kernel
+        static size_t configured_smem[8] = {};
+        int slot = 0;
+        while (slot < 7 && configured_kern[slot] != nullptr && configured_kern[slot] != kern) ++slot;
+        if (configured_kern[slot] != kern || smem > configured_smem[slot]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured_kern[slot] = kern;
+            configured_smem[slot] = smem;
+        }
         kern<<<grid, threads, smem, stream>>>(P, D, S, obs, sh, env_begin, env_end);
         return cudaGetLastError();
     }
