@@ -175,9 +175,9 @@ cudaError_t launch_reset(const GteParams& P, const GteData& D, const GteState& S
     return cudaGetLastError();
 }
 
-// ---- one lockstep iteration = step + gather, env chunks pipelined over two streams ---------------
-// The step kernel is latency-bound (dependent loads + fp64 divide/log chains), the gather is
-// HBM-bound; running the step of chunk c+1 beside the gather of chunk c hides the former.
+// ---- one lockstep iteration = step + gather; optionally env chunks pipelined over two streams -----
+// (opt-in: the step kernel is latency-bound and the gather HBM-bound, but running the step of chunk c+1
+// beside the gather of chunk c did not beat two plain launches on B200)
 struct AuxStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork[16] = {};

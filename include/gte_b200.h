@@ -210,10 +210,11 @@ int gte_gather_obs(const GteParams* params, const GteData* data, const GteState*
                    float* obs, int variant, void* stream);
 
 /* One whole lockstep iteration — what a vector env's step() returns: gte_step + gte_gather_obs.
- * The envs are cut into n_chunks ranges (0 = choose; 1 = two plain launches) and the step kernel of
- * range c+1 runs beside the gather of range c on a library-owned side stream (forked from and
- * joined back into `stream` with events, so the call is still stream-ordered and graph-capturable):
- * the latency-bound transition math hides under the HBM-bound gather. */
+ * n_chunks: 0 or 1 = two plain launches (the default: measured fastest on B200, profiles/r01_tuning.md).  n_chunks > 1
+ * is an opt-in experiment: the envs are cut into that many ranges and the step kernel of range c+1 runs beside the
+ * gather of range c on a library-owned side stream (forked from and joined back into `stream` with events, so the
+ * call is still stream-ordered and graph-capturable).  With windows == 0 the call is ONE launch: the step kernel
+ * writes the one-row observation itself. */
 int gte_step_obs(const GteParams* params, const GteData* data, const GteState* state,
                  const int64_t* actions, const GteStepOut* out, float* obs, int autoreset,
                  int variant, int n_chunks, void* stream);
