@@ -166,3 +166,62 @@ def test_long_soak_against_the_oracle_with_every_episode_end_kind():
     m = c(dev._metrics_total)
     assert m[1] > 1000 and m[2] > 50 and m[0] <= m[1] + m[2]    # valuation stops AND end-of-data truncations occurred
     dev.check_errors()
+
+
+@pytest.mark.parametrize("variant", ["tma", "vec", "generic"])
+def test_masked_reset_in_the_middle_of_a_run_matches_the_oracle(variant):
+    """reset(options={"mask": ...}) restarts only the chosen envs: their windows restart (zero rows before the new
+    episode start), everybody else's dynamic-feature history is untouched — with the time-indexed ring a reset env's
+    first row lands in the slot of the CURRENT iteration."""
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    s = _series(900, 21)
+    n, positions = 203, [-2, -1, 0, 1, 2]
+    kw = dict(positions=positions, windows=12, trading_fees=1e-4, borrow_interest_rate=3e-6,
+              portfolio_initial_value=1000, max_episode_duration=50)
+    dev = gte.TradingVectorEnv(s, num_envs=n, seed=9, verbose=0, obs_variant=variant, debug_outputs=True, **kw)
+    o = orc.OracleVecEnv(s.features[None], s.price[None], np.array([s.length]), num_envs=n, seed=9, **kw)
+    obs, _ = dev.reset()
+    H.assert_bits(obs.cpu().numpy(), o.reset(), "reset obs")
+    rng = np.random.default_rng(1)
+    for k in range(90):
+        if k in (7, 8, 30, 61):                                     # also two resets in consecutive iterations
+            mask = rng.random(n) < 0.3
+            obs, _ = dev.reset(options={"mask": mask})
+            H.assert_bits(obs.cpu().numpy(), o.reset(mask=mask), f"masked reset before step {k}")
+        a = rng.integers(-1, len(positions), size=n)
+        dev.step(torch.as_tensor(a, device=dev.device))
+        o.step(a)
+        H.assert_bits(dev._obs.cpu().numpy(), o.obs, f"step {k} obs")
+        H.assert_bits(dev._valuation.cpu().numpy(), o.valuation, f"step {k} valuation")
+        H.assert_bits(dev._ep_start.cpu().numpy(), o.ep_start, f"step {k} ep_start")
+    dev.check_errors()
+
+
+def test_checkpoint_round_trip_resumes_bit_identically():
+    """state_dict() / load_state_dict(): portfolio state, dynamic-feature ring + its clock, rotation state and the
+    Philox tick — a restored env produces the same observations, rewards and random restarts as the original."""
+    import gym_trading_env_b200 as gte
+    series = [_series(T, 30 + k) for k, T in enumerate([400, 520, 460])]
+    kw = dict(positions=[-1, 0, 1, 2], windows=16, trading_fees=1e-4, borrow_interest_rate=3e-6,
+              max_episode_duration=25, num_envs=300, seed=4, verbose=0, episodes_between_dataset_switch=2)
+    a = gte.MultiDatasetTradingVectorEnv(datasets=series, **kw)
+    b = gte.MultiDatasetTradingVectorEnv(datasets=series, **kw)
+    a.reset(); b.reset()
+    g = torch.Generator(device=a.device); g.manual_seed(3)
+    acts = torch.randint(0, 4, (80, 300), generator=g, device=a.device)
+    for k in range(37):
+        a.step(acts[k])
+    snap = a.state_dict()
+    obs_at_snap = a._obs.clone()
+    b.load_state_dict(snap)
+    b._launch_obs()
+    assert torch.equal(b._obs.view(torch.int32), obs_at_snap.view(torch.int32))
+    for k in range(37, 80):
+        oa, ra, ta, tra, _ = a.step(acts[k])
+        ob, rb, tb, trb, _ = b.step(acts[k])
+        assert torch.equal(oa.view(torch.int32), ob.view(torch.int32)), k
+        assert torch.equal(ra, rb) and torch.equal(ta, tb) and torch.equal(tra, trb), k
+        assert torch.equal(a._dataset_idx, b._dataset_idx) and torch.equal(a._ep_start, b._ep_start), k
+    assert torch.equal(a._metrics_total, b._metrics_total)
+    assert float(a._metrics_total[0]) > 300                          # several random restarts were replayed identically
