@@ -31,6 +31,8 @@ class SB3VecEnv(_Base):
 
     def __init__(self, env, info_keys=()):
         self.env = env
+        env.output = "numpy"                             # obs / reward / flags through pinned host buffers, one sync per step
+        env._host = None
         self.num_envs = env.num_envs
         self.observation_space = env.single_observation_space
         self.action_space = env.single_action_space

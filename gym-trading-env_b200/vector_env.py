@@ -601,8 +601,7 @@ class TradingVectorEnv:
             self._launch_reset(C.c_void_p(ended.data_ptr()), first=False)
             self._tick -= 1                                 # one public call = one info version
             self._launch_obs()
-            return self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), self.infos
-        if self.output == "hybrid":
+        elif self.output == "hybrid":
             # reward / flags leave for the host right after the step kernel, beside the gather
             hb = self._host_buffers()
             self._launch_step(C.c_void_p(act.data_ptr()))
@@ -617,7 +616,7 @@ class TradingVectorEnv:
             self._raise_on_flag(int(hb["error_flag"][0]))
             return (self._obs, hb["reward"].numpy(), hb["terminated"].numpy().view(np.bool_),
                     hb["truncated"].numpy().view(np.bool_), self.infos)
-        if self.cuda_graph:
+        elif self.cuda_graph:
             if act.data_ptr() != self._actions_dev.data_ptr():
                 self._actions_dev.copy_(act, non_blocking=True)
             if self._graph is None:
