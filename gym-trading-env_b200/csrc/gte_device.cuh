@@ -16,6 +16,10 @@ namespace gte {
 constexpr int kStepThreads = GTE_STEP_THREADS;
 constexpr int kMaxPartialRows = 4096;     // metric_partials rows the step kernel may use (grid cap)
 
+// Programmatic dependent launch: wait until the preceding kernel of the stream has completed and its writes are visible
+// (returns at once for a kernel that was not launched with the attribute).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct Portfolio {        // signed state of utils/portfolio.py:2-6
     double asset, fiat, ia, ifi;
 };

@@ -8,6 +8,21 @@
 
 namespace gte {
 
+// Launch with programmatic dependent launch allowed: the kernel may be scheduled while its predecessor in the
+// stream drains, and orders itself behind it with pdl_wait() before touching anything the predecessor wrote.
+// GTE_PDL=0 falls back to plain stream order.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 int num_sms();
 int step_grid(int n_envs);
 

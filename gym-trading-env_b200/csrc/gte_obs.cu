@@ -183,6 +183,7 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    pdl_wait();                              // state / ring / clock below were written by the step kernel before us
 
     // tile k of this CTA = unit_envs consecutive envs, tiles strided over the grid; group gi of it = G envs
     auto tile_env0 = [&](int k) -> int64_t { return env_begin + ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * unit_envs; };
@@ -454,8 +455,7 @@ cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteStat
             configured_kern[slot] = kern;
             configured_smem[slot] = smem;
         }
-        kern<<<grid, threads, smem, stream>>>(P, D, S, obs, sh, env_begin, env_end);
-        return cudaGetLastError();
+        return launch_pdl(kern, dim3(grid), dim3(threads), smem, stream, P, D, S, obs, sh, env_begin, env_end);
     }
     return cudaErrorInvalidValue;
 }

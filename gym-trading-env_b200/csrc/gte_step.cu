@@ -24,6 +24,7 @@ step_kernel(const GteParams P, const GteData D, const GteState S, const int64_t*
     __shared__ double s_pos[GTE_MAX_POSITIONS];
     if (threadIdx.x < GTE_MAX_POSITIONS) s_pos[threadIdx.x] = P.positions[threadIdx.x];
     __syncthreads();
+    pdl_wait();                              // everything below reads what the previous kernel of the stream wrote
     MetricAcc acc;
     const uint64_t tick = *S.tick;
     // the slot this iteration's row goes to: the first env range of an iteration still sees the old clock
@@ -120,6 +121,11 @@ info_kernel(const GteParams P, const GteData D, const GteState S, const GteInfo 
 
 // ---- host launchers -------------------------------------------------------------------------------
 
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("GTE_PDL"); return e == nullptr || atoi(e) != 0; }();
+    return on;
+}
+
 static int g_num_sms = 0;
 int num_sms() {
     if (g_num_sms == 0) {
@@ -156,10 +162,10 @@ cudaError_t launch_step_range(const GteParams& P, const GteData& D, const GteSta
     }();
     (void)carveout_set;
     if (min_ctas >= 4)
-        step_kernel<4><<<grid, kStepThreads, 0, stream>>>(P, D, S, actions, O, autoreset, tpc, env_begin, env_end, chunk_flags, obs_rows);
-    else
-        step_kernel<3><<<grid, kStepThreads, 0, stream>>>(P, D, S, actions, O, autoreset, tpc, env_begin, env_end, chunk_flags, obs_rows);
-    return cudaGetLastError();
+        return launch_pdl(step_kernel<4>, dim3(grid), dim3(kStepThreads), 0, stream, P, D, S, actions, O, autoreset, tpc,
+                          env_begin, env_end, chunk_flags, obs_rows);
+    return launch_pdl(step_kernel<3>, dim3(grid), dim3(kStepThreads), 0, stream, P, D, S, actions, O, autoreset, tpc,
+                      env_begin, env_end, chunk_flags, obs_rows);
 }
 
 cudaError_t launch_step(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
