@@ -25,6 +25,9 @@ from . import _cabi
 from .data import SeriesArrays, build_window_tables, frame_to_arrays
 
 
+_NARROW_ACTION_DTYPES = (np.dtype(np.int8), np.dtype(np.uint8), np.dtype(np.int16), np.dtype(np.int32))
+
+
 # ---- names the reference exports and callers pass back in (identity-compared, never called) -------
 def basic_reward_function(history=None):
     """Sentinel for the reference's ``basic_reward_function`` (environments.py:17-18):
@@ -555,13 +558,21 @@ class TradingVectorEnv:
                     raise ValueError(f"actions must have shape ({self.num_envs},), got {a.shape}")
                 hb = self._host_buffers()
                 src = None
-                if a.dtype == np.int64 and a.flags.c_contiguous and a.flags.writeable:
+                narrow = a.dtype in _NARROW_ACTION_DTYPES            # int8/int16/int32 (uint8): widened ON THE DEVICE
+                if (a.dtype == np.int64 or narrow) and a.flags.c_contiguous and a.flags.writeable:
                     t = torch.from_numpy(a)
                     if t.is_pinned():
                         src = t                                      # caller already staged them in pinned memory
                 if src is None:
-                    hb["actions"].numpy()[...] = a                   # pageable -> pinned staging copy
-                    src = hb["actions"]
+                    if narrow:
+                        key = "actions_" + a.dtype.name
+                        if key not in hb:
+                            hb[key] = torch.empty(self.num_envs, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
+                        hb[key].numpy()[...] = a
+                        src = hb[key]
+                    else:
+                        hb["actions"].numpy()[...] = a               # pageable (any integer dtype) -> pinned int64 staging copy
+                        src = hb["actions"]
                 # H2D on its own stream: it may run beside the previous iteration's gather.  Out-of-range
                 # actions are flagged by the kernel (positions[position_index] would raise, :234) and the
                 # flag rides back with the results in the host-output modes.
@@ -570,7 +581,14 @@ class TradingVectorEnv:
                 # (hybrid: step() returned only after the last step kernel's results had reached the host, so the
                 #  buffer is free and the copy may run beside the previous iteration's gather)
                 with torch.cuda.stream(self._copy_in):
-                    self._actions_dev.copy_(src, non_blocking=True)
+                    if src.dtype == torch.int64:
+                        self._actions_dev.copy_(src, non_blocking=True)
+                    else:                                            # 1/2/4 bytes per action over PCIe, sign-extended here
+                        key = "dev_" + str(src.dtype)
+                        if key not in hb:
+                            hb[key] = torch.empty(self.num_envs, dtype=src.dtype, device=self.device)
+                        hb[key].copy_(src, non_blocking=True)
+                        self._actions_dev.copy_(hb[key])
                 main.wait_stream(self._copy_in)
                 act = self._actions_dev
             else:
@@ -935,9 +953,10 @@ class TradingVectorEnv:
         """Synchronising check of the in-kernel error flags (device-resident actions are not validated on the host)."""
         self._raise_on_flag(int(self._error_flag.item()))
 
-    def pinned_actions(self):
-        """A pinned int64 [N] numpy array: fill it and pass it to `step()` to skip the staging copy."""
-        return torch.empty(self.num_envs, dtype=torch.int64, pin_memory=True).numpy()
+    def pinned_actions(self, dtype=np.int64):
+        """A pinned [N] numpy array (int64, or int8/uint8/int16/int32 to move fewer bytes over PCIe — the device
+        widens them): fill it and pass it to `step()` to skip the staging copy."""
+        return torch.empty(self.num_envs, dtype=torch.from_numpy(np.empty(0, dtype)).dtype, pin_memory=True).numpy()
 
     @staticmethod
     def _raise_on_flag(flag):

@@ -114,3 +114,37 @@ def test_per_iteration_metric_allreduce_accumulates_the_step_metrics():
             assert float(env.global_metrics_total[0]) == float((g["terminated"] | g["truncated"]).sum())
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("output", ["numpy", "hybrid"])
+def test_narrow_integer_host_actions_are_widened_on_the_device(output):
+    """int8 / int16 / int32 numpy actions (pageable or from pinned_actions(dtype)) cross PCIe as they are and give the
+    results of the int64 stream, hold (-1) included."""
+    import gym_trading_env_b200 as gte
+    g = H.load_golden("c3_windows_leveraged")
+    K = 60
+    for dt in (np.int8, np.int16, np.int32):
+        ref = H.make_device_env(g, output=output)
+        env = H.make_device_env(g, output=output)
+        ref.reset(); env.reset()
+        pin = env.pinned_actions(dt)
+        assert pin.dtype == dt
+        for k in range(K):
+            a = g["actions"][k].copy()
+            a[k % a.size] = -1                                       # a hold
+            want = ref.step(a)
+            if k % 2:
+                pin[...] = a
+                got = env.step(pin)                                  # pinned, no staging copy
+            else:
+                got = env.step(a.astype(dt))                         # pageable
+            for w, x in zip(want[:4], got[:4]):
+                w = w.cpu().numpy() if hasattr(w, "cpu") else w
+                x = x.cpu().numpy() if hasattr(x, "cpu") else x
+                assert np.array_equal(w, x), (dt, k)
+    u8 = H.make_device_env(g, output=output)
+    u8.reset()
+    u8.step(g["actions"][0].astype(np.uint8))
+    with pytest.raises(IndexError):                                  # 255 is not a position: flagged like any bad index
+        u8.step(np.full(g["params"]["n_envs"], 255, np.uint8))
+        u8.check_errors()
