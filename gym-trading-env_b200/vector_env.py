@@ -187,7 +187,9 @@ class TradingVectorEnv:
     ``debug_outputs`` (also write the terminal step's idx/step/real_position/portfolio, +48 B/env);
     ``final_obs`` (gymnasium's SAME_STEP ``final_obs``: ``env.final_obs`` keeps, for every env whose episode
     ended in this step, the observation ``step()`` itself returned before the in-place reset
-    (environments.py:272); costs a second gather, off by default).
+    (environments.py:272); costs a second gather, off by default); ``host_reward_dtype`` (float64; float32 halves
+    the reward bytes the "numpy" / "hybrid" modes copy to the host — rounded on the device from the fp64 reward,
+    which stays available as ``env._reward``).
 
     ``reward_function`` must be :func:`basic_reward_function` or a :class:`DeviceReward` from the fused
     catalogue (log / simple return with scale and clip), and ``dynamic_feature_functions`` the two
@@ -205,7 +207,8 @@ class TradingVectorEnv:
                  max_episode_duration="max", verbose=1, name="Stock", render_mode="logs", *,
                  num_envs=1, device=None, seed=0, env_id_offset=0, done_valuation_ratio=0.7,
                  reset_plan=None, obs_variant="auto", output="torch", autoreset=True,
-                 debug_outputs=False, cuda_graph=False, n_chunks=0, final_obs=False, _multi_dataset=False, _episodes_between_dataset_switch=1):
+                 debug_outputs=False, cuda_graph=False, n_chunks=0, final_obs=False, host_reward_dtype=np.float64,
+                 _multi_dataset=False, _episodes_between_dataset_switch=1):
         self._lib = _cabi.load()                      # fails loudly when the CUDA library is missing
         if not torch.cuda.is_available():
             raise RuntimeError("gym_trading_env_b200 needs a CUDA device (no CPU fallback)")
@@ -264,6 +267,9 @@ class TradingVectorEnv:
         self.env_id_offset = int(env_id_offset)
         self.done_valuation_ratio = float(done_valuation_ratio)
         self.output = output
+        self.host_reward_dtype = np.dtype(host_reward_dtype)
+        if self.host_reward_dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise ValueError("host_reward_dtype must be float64 or float32")
         self.autoreset = bool(autoreset)
         self.debug_outputs = bool(debug_outputs)
         self.cuda_graph = bool(cuda_graph)
@@ -504,6 +510,9 @@ class TradingVectorEnv:
             self._host = {"actions": pin(self._actions_dev), "reward": pin(self._reward),
                           "terminated": pin(self._terminated), "truncated": pin(self._truncated),
                           "error_flag": pin(self._error_flag)}
+            if self.host_reward_dtype == np.dtype(np.float32):
+                self._reward32 = torch.empty(self.num_envs, dtype=torch.float32, device=self.device)
+                self._host["reward"] = pin(self._reward32)
             if self.output == "numpy":
                 self._host["obs"] = pin(self._obs)
             self._copy_in = torch.cuda.Stream(device=self.device)
@@ -626,7 +635,7 @@ class TradingVectorEnv:
             self._issue_metric_allreduce(main)
             self._copy_out.wait_stream(main)
             with torch.cuda.stream(self._copy_out):
-                for k, t in (("reward", self._reward), ("terminated", self._terminated),
+                for k, t in (("reward", self._host_reward_src()), ("terminated", self._terminated),
                              ("truncated", self._truncated), ("error_flag", self._error_flag)):
                     hb[k].copy_(t, non_blocking=True)
             self._launch_obs()
@@ -663,7 +672,7 @@ class TradingVectorEnv:
             self._issue_metric_allreduce(main)
         if self.output == "numpy":
             h = self._host_buffers()
-            for k, t in (("obs", self._obs), ("reward", self._reward), ("terminated", self._terminated),
+            for k, t in (("obs", self._obs), ("reward", self._host_reward_src()), ("terminated", self._terminated),
                          ("truncated", self._truncated), ("error_flag", self._error_flag)):
                 h[k].copy_(t, non_blocking=True)
             main.synchronize()
@@ -671,6 +680,14 @@ class TradingVectorEnv:
             return (h["obs"].numpy(), h["reward"].numpy(), h["terminated"].numpy().view(np.bool_),
                     h["truncated"].numpy().view(np.bool_), self.infos)
         return self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), self.infos
+
+    def _host_reward_src(self):
+        """The device tensor the host reward is copied from (on the current stream): the fp64 reward itself, or its
+        float32 rounding when ``host_reward_dtype`` asks for fewer bytes on the wire."""
+        if self.host_reward_dtype == np.dtype(np.float64):
+            return self._reward
+        self._reward32.copy_(self._reward)
+        return self._reward32
 
     def _emit_obs(self):
         if self.output == "numpy":
