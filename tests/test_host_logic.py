@@ -70,3 +70,39 @@ def test_constructor_fails_loudly_without_a_gpu():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         gte.TradingVectorEnv(gte.make_gbm_ohlcv(300, seed=0), num_envs=4)
+
+
+def test_sb3_view_exposes_the_vecenv_surface_without_touching_the_gpu():
+    """The stable-baselines3 adapter is plain host code over an env object: check its contract on a stand-in env
+    (the GPU test replays a reference golden through it)."""
+    import torch
+    import gym_trading_env_b200 as gte
+
+    class FakeEnv:
+        num_envs, device, render_mode, output, _host, final_obs = 3, torch.device("cpu"), "logs", "torch", None, None
+        single_observation_space, single_action_space = "obs-space", "act-space"
+
+        def reset(self):
+            return np.zeros((3, 2), np.float32), {}
+
+        def step(self, a):
+            assert a.dtype == np.int64 and a.shape == (3,)
+            self.final_obs = torch.full((3, 2), 7.0)
+            return (np.ones((3, 2), np.float32), np.array([0.5, 0.25, 0.0]), np.array([False, True, False]),
+                    np.array([False, False, True]), {"idx": np.array([4, 5, 6])})
+
+        def close(self):
+            self.closed = True
+
+    env = FakeEnv()
+    v = gte.SB3VecEnv(env, info_keys=("idx",))
+    assert env.output == "numpy" and v.num_envs == 3 and v.observation_space == "obs-space"
+    assert v.reset().shape == (3, 2)
+    obs, rew, dones, infos = v.step([0, 1, 0])
+    assert rew.dtype == np.float32 and dones.tolist() == [False, True, True]
+    assert [i["idx"] for i in infos] == [4, 5, 6]
+    assert "terminal_observation" not in infos[0] and infos[1]["TimeLimit.truncated"] is False
+    assert infos[2]["TimeLimit.truncated"] is True and infos[2]["terminal_observation"].tolist() == [7.0, 7.0]
+    assert v.env_is_wrapped(object) == [False] * 3 and v.get_attr("num_envs", 1) == [3]
+    v.close()
+    assert env.closed
