@@ -234,7 +234,7 @@ def run_reference_arm(args, wl, rank):
     dt = time.perf_counter() - t0
     value = n_sample * inner * args.steps / dt
     sample = f"{n_sample} envs x {inner} lockstep iterations per step, {cores} host threads, scalar C port of the reference"
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -243,7 +243,28 @@ def run_reference_arm(args, wl, rank):
                          "python_reference": python_reference_rate(wl, args.workload)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
+
+
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE result line: everything else that writes to fd 1 — NCCL's version banner, library
+    chatter, worker output — is sent to stderr from here on."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
 
 
 def main():
@@ -277,6 +298,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    _claim_stdout()
 
     if args.impl == "reference":
         run_reference_arm(args, wl, rank)
@@ -513,7 +535,7 @@ def main():
         }
         if latency is not None:
             out["latency"] = latency
-        print(json.dumps(out), flush=True)
+        _emit(out)
     if world > 1:
         dist.destroy_process_group()
 
