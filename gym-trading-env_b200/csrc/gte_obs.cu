@@ -445,15 +445,20 @@ cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteStat
         const int64_t waves = (need + cap - 1) / cap;
         const int grid = (int)((need + waves - 1) / waves);
         ObsKernelFn kern = tma_kernel(cfg, unit);
-        static ObsKernelFn configured_kern[8] = {};        // opt-in to > 48 KB dynamic smem once per kernel
-        static size_t configured_smem[8] = {};
+        // opt-in to > 48 KB dynamic smem once per kernel AND device (the attribute is per device)
+        static ObsKernelFn configured_kern[16][8] = {};
+        static size_t configured_smem[16][8] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        ObsKernelFn* ck = configured_kern[dev & 15];
+        size_t* cs = configured_smem[dev & 15];
         int slot = 0;
-        while (slot < 7 && configured_kern[slot] != nullptr && configured_kern[slot] != kern) ++slot;
-        if (configured_kern[slot] != kern || smem > configured_smem[slot]) {
+        while (slot < 7 && ck[slot] != nullptr && ck[slot] != kern) ++slot;
+        if (ck[slot] != kern || smem > cs[slot]) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            configured_kern[slot] = kern;
-            configured_smem[slot] = smem;
+            ck[slot] = kern;
+            cs[slot] = smem;
         }
         return launch_pdl(kern, dim3(grid), dim3(threads), smem, stream, P, D, S, obs, sh, env_begin, env_end);
     }

@@ -155,12 +155,14 @@ cudaError_t launch_step_range(const GteParams& P, const GteData& D, const GteSta
     const int n = env_end - env_begin;
     const int grid = step_grid(n), tpc = step_tiles_per_cta(n);
     // same shared-memory carve-out as the gather kernel, so CTAs of both can be resident on one SM
-    static const bool carveout_set = [] {
+    static bool carveout_set[16] = {};                 // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!carveout_set[dev & 15]) {
         cudaFuncSetAttribute(step_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(step_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        return true;
-    }();
-    (void)carveout_set;
+        carveout_set[dev & 15] = true;
+    }
     // 4 CTAs/SM (64 registers, a few spills) pays once the grid runs in several waves; a grid that is resident at once
     // is latency-bound and runs the spill-free 3-CTA build a little faster (C3: 47.3 -> 46.6 us per iteration)
     if (min_ctas >= 4 && grid > num_sms() * 3)
