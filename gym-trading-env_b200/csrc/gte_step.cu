@@ -1,7 +1,7 @@
 // gte_step.cu — fused per-env transition kernel, reset kernel and info kernel (sm_100a).
 //
-// One thread per env, structure-of-arrays state in HBM (coalesced 8/4-byte accesses), one 256-env
-// tile per CTA (a few consecutive tiles when N is huge, so the per-CTA metric partials stay bounded).
+// One thread per env, structure-of-arrays state in HBM (coalesced 8/4-byte accesses), 256-env tiles; a grid of at
+// most one resident wave of CTAs, each walking through consecutive tiles.
 // Replaces TradingEnv.step (environments.py:233-272) for N envs in lockstep; see
 // include/gte_b200.h for the boundary and DESIGN.md for the data layout / roofline.
 #include <cstdlib>
@@ -11,9 +11,8 @@
 
 namespace gte {
 
-// Each CTA owns `tiles_per_cta` CONSECUTIVE 256-env tiles (1 unless N > 256 x kMaxPartialRows), so the
-// grid is as wide as the problem (latency hiding comes from CTA-level parallelism, not a loop) while
-// the metric partials stay bounded.
+// Each CTA owns `tiles_per_cta` CONSECUTIVE 256-env tiles: 1 while the grid fits on the GPU at once, more beyond that
+// (see step_tiles_per_cta).
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(kStepThreads, MIN_CTAS)
 step_kernel(const GteParams P, const GteData D, const GteState S, const int64_t* __restrict__ actions,
@@ -137,9 +136,15 @@ int num_sms() {
     return g_num_sms;
 }
 
+// Consecutive 256-env tiles per CTA: the grid is capped at the CTAs that are resident at once (SMs x 4), so a large
+// batch runs as ONE wave of CTAs that each walk through their tiles — the per-CTA set-up and the metric fold are paid
+// once per CTA instead of once per tile or two (C5 shard: 0.112 -> 0.089 ms; GTE_STEP_MAX_CTAS overrides the cap).
 static int step_tiles_per_cta(int n_envs) {
+    static const int max_ctas = [] { const char* e = getenv("GTE_STEP_MAX_CTAS"); return e ? atoi(e) : 0; }();
+    int64_t cap = max_ctas > 0 ? max_ctas : (int64_t)num_sms() * 4;
+    if (cap > kMaxPartialRows) cap = kMaxPartialRows;
     const int64_t tiles = ((int64_t)n_envs + kStepThreads - 1) / kStepThreads;
-    return (int)((tiles + kMaxPartialRows - 1) / kMaxPartialRows);
+    return (int)((tiles + cap - 1) / cap);
 }
 
 int step_grid(int n_envs) {
