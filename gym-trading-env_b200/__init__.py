@@ -26,6 +26,9 @@ def __getattr__(name):          # torch / the CUDA library are only imported whe
     if name == "SB3VecEnv":
         from .sb3_adapter import SB3VecEnv
         return SB3VecEnv
+    if name == "bind_host_to_gpu":
+        from .hostbind import bind_host_to_gpu
+        return bind_host_to_gpu
     if name == "build":
         from ._cabi import build
         return build

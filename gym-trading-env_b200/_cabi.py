@@ -6,7 +6,9 @@ library is missing or fails to load, :func:`load` raises and every env construct
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
 import os
+import re
 import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
@@ -16,6 +18,7 @@ INCLUDE_DIR = os.path.join(os.path.dirname(_PKG), "include")
 SOURCES = ["gte_step.cu", "gte_obs.cu", "gte_cabi.cu"]
 HEADERS = ["gte_device.cuh", "gte_step_env.cuh", "gte_tma.cuh", "gte_launch.h", os.path.join(INCLUDE_DIR, "gte_b200.h")]
 
+GTE_VERSION = 200                 # include/gte_b200.h GTE_VERSION this binding was written against
 GTE_MAX_POSITIONS = 64
 GTE_MAX_DATASETS = 64
 GTE_N_METRICS = 8
@@ -35,7 +38,8 @@ class GteParams(C.Structure):
         ("n_datasets", C.c_int32), ("initial_position_idx", C.c_int32),
         ("episodes_between_switch", C.c_int32), ("plan_episodes", C.c_int32),
         ("multi_dataset", C.c_int32), ("reward_kind", C.c_int32),
-        ("n_limit_positions", C.c_int32), ("reserved0", C.c_int32),
+        ("n_limit_positions", C.c_int32), ("action_bytes", C.c_int32),
+        ("strict_actions", C.c_int32), ("reserved0", C.c_int32),
         ("t_stride", C.c_int64), ("env_id_offset", C.c_int64), ("seed", C.c_uint64),
         ("fee", C.c_double), ("rate", C.c_double), ("v0", C.c_double), ("done_ratio", C.c_double),
         ("reward_scale", C.c_double), ("reward_lo", C.c_double), ("reward_hi", C.c_double),
@@ -69,8 +73,27 @@ class GteStepOut(C.Structure):
         ("valuation", C.c_void_p), ("real_position", C.c_void_p), ("info_idx", C.c_void_p),
         ("info_step", C.c_void_p), ("pre_reset_portfolio", C.c_void_p),
         ("metric_partials", C.c_void_p), ("metrics_step", C.c_void_p),
-        ("metrics_total", C.c_void_p), ("block_counter", C.c_void_p),
+        ("metrics_total", C.c_void_p), ("block_counter", C.c_void_p), ("error_out", C.c_void_p),
+        ("seq_out", C.c_void_p), ("seq_value", C.c_uint32), ("reserved1", C.c_uint32),
     ]
+
+
+class GteHostIO(C.Structure):
+    _fields_ = [
+        ("actions", C.c_void_p), ("results", C.c_void_p), ("dev_actions", C.c_void_p), ("dev_results", C.c_void_p),
+        ("step_done_event", C.c_void_p), ("mode", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+IO_AUTO, IO_COPY, IO_MAPPED = 0, 1, 2
+IO_MODES = {"auto": IO_AUTO, "copy": IO_COPY, "mapped": IO_MAPPED}
+E_ACTION_RANGE, E_PAST_END, E_PLAN_RANGE, E_PLAN_EXHAUSTED, E_NEGATIVE_ACTION = 1, 2, 4, 8, 16
+
+
+def host_result_layout(n: int):
+    """(term offset, trunc offset, error offset, total bytes) of gte_step_host's result block (GTE_HOST_RESULT_*)."""
+    err = (n * 10 + 7) // 8 * 8
+    return n * 8, n * 9, err, err + 8
 
 
 class GteInfo(C.Structure):
@@ -81,25 +104,43 @@ class GteInfo(C.Structure):
     ]
 
 
-EXPORTS = ["gte_version", "gte_last_error", "gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs",
-           "gte_rollout", "gte_info", "gte_obs_variant_for", "gte_default_chunks", "gte_struct_size"]
+EXPORTS = ["gte_version", "gte_last_error", "gte_build_id", "gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs",
+           "gte_step_host", "gte_rollout", "gte_info", "gte_obs_variant_for", "gte_default_chunks", "gte_struct_size"]
+
+
+def source_hash() -> str:
+    """Hash of every CUDA source / header the library is compiled from: the build line bakes it into the binary
+    (``gte_build_id()``), so a stale ``libgte_b200.so`` — mtimes mean nothing after a checkout or a copy to the GPU
+    box — is recognised by content, not by date."""
+    h = hashlib.sha256()
+    for f in SOURCES + HEADERS:
+        path = f if os.path.isabs(f) else os.path.join(_CSRC, f)
+        h.update(os.path.basename(path).encode() + b"\0")
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 def nvcc_command(out_path: str = LIB_PATH):
     """The exact build line (sm_100a only; -fmad=false keeps fp64 math FMA-free, -lineinfo for ncu)."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-            "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-o", out_path] + \
+            "-fmad=false", f'-DGTE_BUILD_ID="{source_hash()}"', "-Xcompiler", "-fPIC", "-shared", "-o", out_path] + \
            [os.path.join(_CSRC, s) for s in SOURCES]
 
 
+def built_id(path: str = LIB_PATH):
+    """The source hash baked into an existing library file (read from the file, not through dlopen), or None."""
+    try:
+        with open(path, "rb") as fh:
+            m = re.search(rb"GTE_BUILD_ID=([0-9a-f]{16})", fh.read())
+        return m.group(1).decode() if m else None
+    except OSError:
+        return None
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(_CSRC, s) for s in SOURCES] + \
-           [h if os.path.isabs(h) else os.path.join(_CSRC, h) for h in HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    return built_id() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -127,23 +168,32 @@ def load():
     lib = C.CDLL(LIB_PATH)
     lib.gte_version.restype = C.c_int
     lib.gte_last_error.restype = C.c_char_p
+    lib.gte_build_id.restype = C.c_char_p
+    if lib.gte_version() != GTE_VERSION:
+        raise RuntimeError(f"{LIB_PATH} is ABI version {lib.gte_version()}, this binding expects {GTE_VERSION} — rebuild it")
+    if os.path.exists(os.path.join(_CSRC, SOURCES[0])) and lib.gte_build_id().decode() != source_hash():
+        raise RuntimeError(f"{LIB_PATH} was built from other sources (build id {lib.gte_build_id().decode()}, "
+                           f"sources {source_hash()}) — rebuild it: python -c 'import __graft_entry__ as g; g.build()'")
     P = C.POINTER
     lib.gte_reset.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, C.c_int, C.c_void_p]
     lib.gte_step.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, P(GteStepOut), C.c_int, C.c_void_p]
     lib.gte_gather_obs.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, C.c_int, C.c_void_p]
     lib.gte_step_obs.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, P(GteStepOut), C.c_void_p,
                                  C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.gte_step_host.argtypes = [P(GteParams), P(GteData), P(GteState), P(GteHostIO), P(GteStepOut), C.c_void_p,
+                                  C.c_int, C.c_int, P(C.c_int), C.c_void_p]
     lib.gte_rollout.argtypes = [P(GteParams), P(GteData), P(GteState), C.c_void_p, C.c_int, P(GteStepOut), C.c_void_p,
                                 C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.gte_info.argtypes = [P(GteParams), P(GteData), P(GteState), P(GteInfo), C.c_void_p]
     lib.gte_obs_variant_for.argtypes = [P(GteParams), P(GteData)]
     lib.gte_default_chunks.argtypes = [C.c_int]
     lib.gte_default_chunks.restype = C.c_int
-    for name in ("gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs", "gte_rollout", "gte_info", "gte_obs_variant_for"):
+    for name in ("gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs", "gte_step_host", "gte_rollout", "gte_info",
+                 "gte_obs_variant_for"):
         getattr(lib, name).restype = C.c_int
     lib.gte_struct_size.argtypes = [C.c_int]
     lib.gte_struct_size.restype = C.c_int
-    for which, st in enumerate((GteParams, GteData, GteState, GteStepOut, GteInfo)):
+    for which, st in enumerate((GteParams, GteData, GteState, GteStepOut, GteInfo, GteHostIO)):
         if lib.gte_struct_size(which) != C.sizeof(st):
             raise RuntimeError(f"ABI mismatch: {st.__name__} is {C.sizeof(st)} bytes here, "
                                f"{lib.gte_struct_size(which)} in {LIB_PATH} — rebuild the library")

@@ -48,6 +48,9 @@ int check_common(const char* fn, const GteParams* p, const GteData* d, const Gte
     GTE_REQUIRE(fn, p->plan_episodes == 0 || s->reset_plan != nullptr);
     GTE_REQUIRE(fn, p->n_limit_positions >= 0 && p->n_limit_positions <= p->n_positions);
     GTE_REQUIRE(fn, p->n_limit_positions == 0 || (s->limit_price && s->limit_seq && d->high && d->low));
+    GTE_REQUIRE(fn, p->action_bytes == 0 || p->action_bytes == 1 || p->action_bytes == 2 || p->action_bytes == 4 || p->action_bytes == 8);
+    for (int c = 0; c < 4; ++c)          // copy c starts 4c bytes before a 16-byte boundary (cp.async.bulk / ld.v4 fault otherwise)
+        GTE_REQUIRE(fn, d->window_table[c] == nullptr || ((reinterpret_cast<uintptr_t>(d->window_table[c]) + 4u * c) & 15u) == 0);
     return GTE_OK;
 }
 
@@ -56,6 +59,12 @@ int check_common(const char* fn, const GteParams* p, const GteData* d, const Gte
 extern "C" {
 
 int gte_version(void) { return GTE_VERSION; }
+
+#ifndef GTE_BUILD_ID
+#define GTE_BUILD_ID "unknown"
+#endif
+static const char kBuildTag[] = "GTE_BUILD_ID=" GTE_BUILD_ID;     // the tag is also searched for in the file by the binding
+const char* gte_build_id(void) { return kBuildTag + 13; }
 
 const char* gte_last_error(void) { return g_err; }
 
@@ -66,14 +75,25 @@ int gte_reset(const GteParams* params, const GteData* data, const GteState* stat
                                                      static_cast<cudaStream_t>(stream)));
 }
 
-static int check_step_out(const char* fn, const int64_t* actions, const GteStepOut* out) {
+static int check_step_out(const char* fn, const void* actions, const GteStepOut* out, bool own_results = false) {
     GTE_REQUIRE(fn, actions != nullptr && out != nullptr);
-    GTE_REQUIRE(fn, out->reward && out->terminated && out->truncated);
+    GTE_REQUIRE(fn, own_results || (out->reward && out->terminated && out->truncated));
     GTE_REQUIRE(fn, out->metric_partials && out->metrics_step && out->block_counter);
     return GTE_OK;
 }
 
-int gte_step(const GteParams* params, const GteData* data, const GteState* state, const int64_t* actions,
+// the gather variant a call will run, and the alignment its 128-bit / bulk stores need from obs
+static int check_obs_ptr(const char* fn, const GteParams* params, const GteData* data, const float* obs, int variant) {
+    GTE_REQUIRE(fn, obs != nullptr);
+    int v = variant;
+    if (v == GTE_OBS_AUTO)
+        v = gte::obs_tma_supported(*params, *data) ? GTE_OBS_TMA : (gte::obs_vec_supported(*params, *data) ? GTE_OBS_VEC : GTE_OBS_GENERIC);
+    if (params->windows > 0 && (v == GTE_OBS_VEC || v == GTE_OBS_TMA) && (reinterpret_cast<uintptr_t>(obs) & 15u) != 0)
+        return fail_arg(fn, "obs must be 16-byte aligned for the vector / TMA gather");
+    return GTE_OK;
+}
+
+int gte_step(const GteParams* params, const GteData* data, const GteState* state, const void* actions,
              const GteStepOut* out, int autoreset, void* stream) {
     if (int rc = check_common("gte_step", params, data, state)) return rc;
     if (int rc = check_step_out("gte_step", actions, out)) return rc;
@@ -90,22 +110,40 @@ static int check_variant(const char* fn, const GteParams* params, const GteData*
     return GTE_OK;
 }
 
-int gte_step_obs(const GteParams* params, const GteData* data, const GteState* state, const int64_t* actions,
+int gte_step_obs(const GteParams* params, const GteData* data, const GteState* state, const void* actions,
                  const GteStepOut* out, float* obs, int autoreset, int variant, int n_chunks, void* stream) {
     if (int rc = check_common("gte_step_obs", params, data, state)) return rc;
     if (int rc = check_step_out("gte_step_obs", actions, out)) return rc;
     GTE_REQUIRE("gte_step_obs", obs != nullptr && n_chunks >= 0 && n_chunks <= 16);
     if (int rc = check_variant("gte_step_obs", params, data, variant)) return rc;
+    if (int rc = check_obs_ptr("gte_step_obs", params, data, obs, variant)) return rc;
     return check_cuda("gte_step_obs", gte::launch_step_obs(*params, *data, *state, actions, *out, obs, autoreset,
                                                            variant, n_chunks, static_cast<cudaStream_t>(stream)));
 }
 
-int gte_rollout(const GteParams* params, const GteData* data, const GteState* state, const int64_t* actions,
+int gte_step_host(const GteParams* params, const GteData* data, const GteState* state, const GteHostIO* io,
+                  const GteStepOut* out, float* obs, int autoreset, int variant, int* mode_used, void* stream) {
+    if (int rc = check_common("gte_step_host", params, data, state)) return rc;
+    GTE_REQUIRE("gte_step_host", io != nullptr && io->actions != nullptr && io->results != nullptr);
+    if (int rc = check_step_out("gte_step_host", io->actions, out, true)) return rc;
+    GTE_REQUIRE("gte_step_host", io->mode >= GTE_IO_AUTO && io->mode <= GTE_IO_MAPPED);
+    GTE_REQUIRE("gte_step_host", (reinterpret_cast<uintptr_t>(io->results) & 7u) == 0);
+    if (gte::host_io_mode(*params, io->mode) == GTE_IO_COPY)
+        GTE_REQUIRE("gte_step_host", io->dev_actions != nullptr && io->dev_results != nullptr &&
+                                     (reinterpret_cast<uintptr_t>(io->dev_results) & 7u) == 0);
+    if (int rc = check_variant("gte_step_host", params, data, variant)) return rc;
+    if (int rc = check_obs_ptr("gte_step_host", params, data, obs, variant)) return rc;
+    return check_cuda("gte_step_host", gte::launch_step_host(*params, *data, *state, *io, *out, obs, autoreset, variant,
+                                                             mode_used, static_cast<cudaStream_t>(stream)));
+}
+
+int gte_rollout(const GteParams* params, const GteData* data, const GteState* state, const void* actions,
                 int n_steps, const GteStepOut* out, float* obs, int keep_obs, int autoreset, int variant, void* stream) {
     if (int rc = check_common("gte_rollout", params, data, state)) return rc;
     if (int rc = check_step_out("gte_rollout", actions, out)) return rc;
     GTE_REQUIRE("gte_rollout", obs != nullptr && n_steps >= 1);
     if (int rc = check_variant("gte_rollout", params, data, variant)) return rc;
+    if (int rc = check_obs_ptr("gte_rollout", params, data, obs, variant)) return rc;
     return check_cuda("gte_rollout", gte::launch_rollout(*params, *data, *state, actions, n_steps, *out, obs, keep_obs,
                                                          autoreset, variant, static_cast<cudaStream_t>(stream)));
 }
@@ -115,6 +153,7 @@ int gte_gather_obs(const GteParams* params, const GteData* data, const GteState*
     if (int rc = check_common("gte_gather_obs", params, data, state)) return rc;
     GTE_REQUIRE("gte_gather_obs", obs != nullptr);
     if (int rc = check_variant("gte_gather_obs", params, data, variant)) return rc;
+    if (int rc = check_obs_ptr("gte_gather_obs", params, data, obs, variant)) return rc;
     return check_cuda("gte_gather_obs", gte::launch_obs_range(*params, *data, *state, obs, variant, 0,
                                                               params->n_envs, static_cast<cudaStream_t>(stream)));
 }
@@ -134,6 +173,7 @@ int gte_struct_size(int which) {
         case 2: return (int)sizeof(GteState);
         case 3: return (int)sizeof(GteStepOut);
         case 4: return (int)sizeof(GteInfo);
+        case 5: return (int)sizeof(GteHostIO);
         default: return GTE_ERR_ARG;
     }
 }

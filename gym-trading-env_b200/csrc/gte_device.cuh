@@ -14,7 +14,7 @@
 namespace gte {
 
 constexpr int kStepThreads = GTE_STEP_THREADS;
-constexpr int kMaxPartialRows = 4096;     // metric_partials rows the step kernel may use (grid cap)
+constexpr int kMaxPartialRows = GTE_MAX_PARTIAL_ROWS;     // metric_partials rows the step kernel may use (grid cap)
 
 // Programmatic dependent launch: wait until the preceding kernel of the stream has completed and its writes are visible
 // (returns at once for a kernel that was not launched with the attribute).
@@ -175,9 +175,18 @@ __device__ __forceinline__ void reset_env(const GteParams& P, const GteData& D, 
     int plan_start = 0, plan_pos = 0, plan_ds = 0;
     if (have_plan) {
         const int cur = S.plan_cursor[i];
+        if (cur >= P.plan_episodes) atomicOr(S.error_flag, GTE_E_PLAN_EXHAUSTED);     // replays from the start
         const int32_t* pl = S.reset_plan + ((int64_t)i * P.plan_episodes + (cur % P.plan_episodes)) * 3;
         plan_start = pl[0]; plan_pos = pl[1]; plan_ds = pl[2];
         S.plan_cursor[i] = cur + 1;
+        // a plan row must name a dataset, a position and a start row the reference could have drawn
+        // (environments.py:167-177): clamp and flag instead of reading out of bounds
+        bool bad = plan_pos < 0 || plan_pos >= P.n_positions || plan_ds < 0 || plan_ds >= P.n_datasets;
+        plan_pos = min(max(plan_pos, 0), P.n_positions - 1);
+        plan_ds = P.multi_dataset ? min(max(plan_ds, 0), P.n_datasets - 1) : e.ds;
+        const int Tp = D.lengths[plan_ds], lo = P.windows > 0 ? P.windows - 1 : 0;
+        if (plan_start < lo || plan_start > Tp - 2) { bad = true; plan_start = min(max(plan_start, lo), Tp - 2); }
+        if (bad) atomicOr(S.error_flag, GTE_E_PLAN_RANGE);
     }
     if (P.multi_dataset) {                                                   // :394-398
         const int n = S.ds_episodes[i] + 1;

@@ -26,8 +26,14 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 int num_sms();
 int step_grid(int n_envs);
 
-cudaError_t launch_step(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
+cudaError_t launch_step(const GteParams& P, const GteData& D, const GteState& S, const void* actions,
                         const GteStepOut& O, int autoreset, cudaStream_t stream);
+cudaError_t launch_step_range(const GteParams& P, const GteData& D, const GteState& S, const void* actions,
+                              const GteStepOut& O, int autoreset, int env_begin, int env_end, int chunk_flags,
+                              cudaStream_t stream, float* obs_rows);
+cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteState& S, const GteHostIO& io,
+                             const GteStepOut& O, float* obs, int autoreset, int variant, int* mode_used,
+                             cudaStream_t stream);
 cudaError_t launch_reset(const GteParams& P, const GteData& D, const GteState& S, const uint8_t* mask,
                          int first, cudaStream_t stream);
 cudaError_t launch_info(const GteParams& P, const GteData& D, const GteState& S, const GteInfo& I,
@@ -39,11 +45,12 @@ bool obs_tma_supported(const GteParams& P, const GteData& D);
 cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteState& S, float* obs, int variant,
                              int env_begin, int env_end, cudaStream_t stream);
 int default_chunks(int n_envs);
-cudaError_t launch_step_obs(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
+int host_io_mode(const GteParams& P, int mode);
+cudaError_t launch_step_obs(const GteParams& P, const GteData& D, const GteState& S, const void* actions,
                             const GteStepOut& O, float* obs, int autoreset, int variant, int n_chunks,
                             cudaStream_t stream);
 
-cudaError_t launch_rollout(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
+cudaError_t launch_rollout(const GteParams& P, const GteData& D, const GteState& S, const void* actions,
                            int n_steps, const GteStepOut& O, float* obs, int keep_obs, int autoreset, int variant,
                            cudaStream_t stream);
 

@@ -102,11 +102,11 @@ obs_vec_kernel(const GteParams P, const GteData D, const GteState S, float* __re
                         const float* rrp = reinterpret_cast<const float*>(ring + GTE_RING_RP_OFFSET(slot, e32));
                         if (PAIR) {
                             const bool live = r >= ep_start;
-                            pv[k] = live ? (float)P.positions[__ldg(rpos)] : 0.0f;
-                            pv[k + 1] = live ? __ldg(rrp) : 0.0f;
+                            pv[k] = live ? (float)P.positions[__ldcg(rpos)] : 0.0f;
+                            pv[k + 1] = live ? __ldcg(rrp) : 0.0f;
                         } else {
                             pv[k] = (r < ep_start) ? 0.0f
-                                  : (c == sh.ns ? (float)P.positions[__ldg(rpos)] : __ldg(rrp));
+                                  : (c == sh.ns ? (float)P.positions[__ldcg(rpos)] : __ldcg(rrp));
                         }
                     }
                 }
@@ -201,7 +201,9 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
             p.src = 0ull; p.first_live = 0;
             const int64_t env = tile_env0(k) + lane;
             if (lane < unit_envs && env < env_end) {
-                const int ep = __ldg(S.ep_start + env), st = __ldg(S.step + env), ds = __ldg(S.dataset_idx + env);
+                // per-env state is WRITTEN by the step kernel this grid may overlap with (programmatic dependent launch): never
+                // through the non-coherent path (ld.global.nc is only defined for data that is read-only for the whole kernel)
+                const int ep = __ldcg(S.ep_start + env), st = __ldcg(S.step + env), ds = __ldcg(S.dataset_idx + env);
                 p.first_live = sh.W - 1 - st;                    // window row of ep_start (<= 0: the whole window is live)
                 p.src = (unsigned long long)window_src(D, sh, ds, ep + st + 1 - sh.W);
             }

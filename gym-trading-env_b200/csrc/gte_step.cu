@@ -4,7 +4,9 @@
 // most one resident wave of CTAs, each walking through consecutive tiles.
 // Replaces TradingEnv.step (environments.py:233-272) for N envs in lockstep; see
 // include/gte_b200.h for the boundary and DESIGN.md for the data layout / roofline.
+#include <cmath>
 #include <cstdlib>
+#include <immintrin.h>
 
 #include "gte_step_env.cuh"
 #include "gte_launch.h"
@@ -15,7 +17,7 @@ namespace gte {
 // (see step_tiles_per_cta).
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(kStepThreads, MIN_CTAS)
-step_kernel(const GteParams P, const GteData D, const GteState S, const int64_t* __restrict__ actions,
+step_kernel(const GteParams P, const GteData D, const GteState S, const void* __restrict__ actions, const StepConsts K,
             const GteStepOut O, int autoreset, int tiles_per_cta, int env_begin, int env_end, int chunk_flags,
             float* __restrict__ obs_rows) {
     // the positions table in shared memory: a per-lane index into the kernel-parameter constant bank would be
@@ -32,7 +34,7 @@ step_kernel(const GteParams P, const GteData D, const GteState S, const int64_t*
     for (int t = 0; t < tiles_per_cta; ++t) {
         const int64_t i = base0 + (int64_t)t * kStepThreads + threadIdx.x;
         if (i < env_end) {
-            const StepThreadOut r = step_env(P, D, S, actions, O, tick, ring_slot, autoreset, (int)i, acc, s_pos);
+            const StepThreadOut r = step_env(P, D, S, actions, K, O, tick, ring_slot, autoreset, (int)i, acc, s_pos);
             if (obs_rows != nullptr) {
                 // windows=None (environments.py:156-157): the observation is the single row idx, written by the
                 // env's own thread -> one launch per lockstep iteration at small N
@@ -120,6 +122,33 @@ info_kernel(const GteParams P, const GteData D, const GteState S, const GteInfo 
 
 // ---- host launchers -------------------------------------------------------------------------------
 
+// Largest double x with fl(x / v0) <= ratio.  Correctly rounded division is monotonic in x, so `valuation <= x` decides
+// the reference's `valuation / initial <= ratio` (environments.py:246) bit for bit without dividing on the device.
+// NaN when the search does not settle within a few ulps (denormal ratios): the kernel then divides.
+static double done_threshold(double v0, double ratio) {
+    if (!(v0 > 0.0) || !std::isfinite(v0) || !std::isfinite(ratio)) return NAN;
+    volatile double x = ratio * v0;
+    for (int k = 0; k < 64 && (double)(x / v0) <= ratio; ++k) x = std::nextafter((double)x, INFINITY);
+    for (int k = 0; k < 128; ++k) {
+        volatile double q = x / v0;
+        if (q <= ratio) {
+            volatile double up = std::nextafter((double)x, INFINITY);
+            volatile double qu = up / v0;
+            return (qu > ratio) ? (double)x : NAN;
+        }
+        x = std::nextafter((double)x, -INFINITY);
+    }
+    return NAN;
+}
+
+StepConsts make_step_consts(const GteParams& P) {
+    static const bool no_thr = [] { const char* e = getenv("GTE_NO_DONE_THRESHOLD"); return e != nullptr && atoi(e) != 0; }();
+    StepConsts K;
+    K.done_thr = no_thr ? NAN : done_threshold(P.v0, P.done_ratio);
+    K.action_bytes = P.action_bytes == 0 ? 8 : P.action_bytes;
+    return K;
+}
+
 bool pdl_enabled() {
     static const bool on = [] { const char* e = getenv("GTE_PDL"); return e == nullptr || atoi(e) != 0; }();
     return on;
@@ -153,9 +182,10 @@ int step_grid(int n_envs) {
     return (int)((tiles + tpc - 1) / tpc);
 }
 
-cudaError_t launch_step_range(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
+cudaError_t launch_step_range(const GteParams& P, const GteData& D, const GteState& S, const void* actions,
                               const GteStepOut& O, int autoreset, int env_begin, int env_end, int chunk_flags,
-                              cudaStream_t stream, float* obs_rows = nullptr) {
+                              cudaStream_t stream, float* obs_rows) {
+    const StepConsts K = make_step_consts(P);
     static const int min_ctas = [] { const char* e = getenv("GTE_STEP_MIN_CTAS"); return e ? atoi(e) : 4; }();
     const int n = env_end - env_begin;
     const int grid = step_grid(n), tpc = step_tiles_per_cta(n);
@@ -171,15 +201,15 @@ cudaError_t launch_step_range(const GteParams& P, const GteData& D, const GteSta
     // 4 CTAs/SM (64 registers, a few spills) pays once the grid runs in several waves; a grid that is resident at once
     // is latency-bound and runs the spill-free 3-CTA build a little faster (C3: 47.3 -> 46.6 us per iteration)
     if (min_ctas >= 4 && grid > num_sms() * 3)
-        return launch_pdl(step_kernel<4>, dim3(grid), dim3(kStepThreads), 0, stream, P, D, S, actions, O, autoreset, tpc,
+        return launch_pdl(step_kernel<4>, dim3(grid), dim3(kStepThreads), 0, stream, P, D, S, actions, K, O, autoreset, tpc,
                           env_begin, env_end, chunk_flags, obs_rows);
-    return launch_pdl(step_kernel<3>, dim3(grid), dim3(kStepThreads), 0, stream, P, D, S, actions, O, autoreset, tpc,
+    return launch_pdl(step_kernel<3>, dim3(grid), dim3(kStepThreads), 0, stream, P, D, S, actions, K, O, autoreset, tpc,
                       env_begin, env_end, chunk_flags, obs_rows);
 }
 
-cudaError_t launch_step(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
+cudaError_t launch_step(const GteParams& P, const GteData& D, const GteState& S, const void* actions,
                         const GteStepOut& O, int autoreset, cudaStream_t stream) {
-    return launch_step_range(P, D, S, actions, O, autoreset, 0, P.n_envs, kChunkFirst | kChunkLast, stream);
+    return launch_step_range(P, D, S, actions, O, autoreset, 0, P.n_envs, kChunkFirst | kChunkLast, stream, nullptr);
 }
 
 cudaError_t launch_reset(const GteParams& P, const GteData& D, const GteState& S, const uint8_t* mask,
@@ -227,7 +257,7 @@ int default_chunks(int n_envs) {
     return 1;
 }
 
-cudaError_t launch_step_obs(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
+cudaError_t launch_step_obs(const GteParams& P, const GteData& D, const GteState& S, const void* actions,
                             const GteStepOut& O, float* obs, int autoreset, int variant, int n_chunks,
                             cudaStream_t stream) {
     if (n_chunks <= 0) n_chunks = default_chunks(P.n_envs);
@@ -247,7 +277,7 @@ cudaError_t launch_step_obs(const GteParams& P, const GteData& D, const GteState
         const int b = (int)(c * per);
         const int en = (int)((c + 1) * per < P.n_envs ? (c + 1) * per : P.n_envs);
         const int flags = (c == 0 ? kChunkFirst : 0) | (c == n_chunks - 1 ? kChunkLast : 0);
-        if ((e = launch_step_range(P, D, S, actions, O, autoreset, b, en, flags, stream)) != cudaSuccess) return e;
+        if ((e = launch_step_range(P, D, S, actions, O, autoreset, b, en, flags, stream, nullptr)) != cudaSuccess) return e;
         if ((e = cudaEventRecord(aux->fork[c], stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(aux->stream, aux->fork[c], 0)) != cudaSuccess) return e;
         if ((e = launch_obs_range(P, D, S, obs, variant, b, en, aux->stream)) != cudaSuccess) return e;
@@ -257,7 +287,7 @@ cudaError_t launch_step_obs(const GteParams& P, const GteData& D, const GteState
 }
 
 // ---- n_steps iterations from one host call (open-loop action stream) ------------------------------
-cudaError_t launch_rollout(const GteParams& P, const GteData& D, const GteState& S, const int64_t* actions,
+cudaError_t launch_rollout(const GteParams& P, const GteData& D, const GteState& S, const void* actions,
                            int n_steps, const GteStepOut& O, float* obs, int keep_obs, int autoreset, int variant,
                            cudaStream_t stream) {
     const int64_t N = P.n_envs;
@@ -273,7 +303,7 @@ cudaError_t launch_rollout(const GteParams& P, const GteData& D, const GteState&
         if (o.pre_reset_portfolio) o.pre_reset_portfolio += k * 4 * N;
         const bool want_obs = keep_obs || k == n_steps - 1;
         float* obs_k = obs + (keep_obs ? k * obs_elems : 0);
-        const int64_t* a = actions + k * N;
+        const void* a = static_cast<const char*>(actions) + (int64_t)k * N * (P.action_bytes == 0 ? 8 : P.action_bytes);
         if (P.windows == 0) {                               // the step kernel writes the one-row observation itself
             e = launch_step_range(P, D, S, a, o, autoreset, 0, P.n_envs, kChunkFirst | kChunkLast, stream,
                                   want_obs ? obs_k : nullptr);
@@ -282,6 +312,96 @@ cudaError_t launch_rollout(const GteParams& P, const GteData& D, const GteState&
             if (e == cudaSuccess && want_obs) e = launch_obs_range(P, D, S, obs_k, variant, 0, P.n_envs, stream);
         }
         if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// ---- one lockstep iteration for a HOST policy: actions from pinned host memory, results into one pinned block ----
+struct HostIOStreams {
+    cudaStream_t in = nullptr, out = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_step = nullptr;
+    uint32_t seq = 0;                // MAPPED mode: number of the last call (what its kernel writes into the block)
+};
+static HostIOStreams g_hio[16];
+
+static cudaError_t hio_for_current_device(HostIOStreams** out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    HostIOStreams& h = g_hio[dev & 15];
+    if (h.in == nullptr) {
+        if ((e = cudaStreamCreateWithFlags(&h.in, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&h.out, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&h.ev_in, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&h.ev_step, cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    *out = &h;
+    return cudaSuccess;
+}
+
+int host_io_mode(const GteParams& P, int mode) {
+    static const long long mapped_max = [] { const char* e = getenv("GTE_IO_MAPPED_MAX_BYTES"); return e ? atoll(e) : (1ll << 20); }();
+    if (mode == GTE_IO_COPY || mode == GTE_IO_MAPPED) return mode;
+    const int ab = P.action_bytes == 0 ? 8 : P.action_bytes;
+    return (int64_t)P.n_envs * (ab + 10) <= mapped_max ? GTE_IO_MAPPED : GTE_IO_COPY;
+}
+
+cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteState& S, const GteHostIO& io,
+                             const GteStepOut& O, float* obs, int autoreset, int variant, int* mode_used,
+                             cudaStream_t stream) {
+    const int64_t N = P.n_envs;
+    const int ab = P.action_bytes == 0 ? 8 : P.action_bytes;
+    const int mode = host_io_mode(P, io.mode);
+    if (mode_used != nullptr) *mode_used = mode;
+    HostIOStreams* h = nullptr;
+    cudaError_t e;
+    if ((e = hio_for_current_device(&h)) != cudaSuccess) return e;
+    // the results of this iteration: one block, on the device (COPY) or straight in the mapped host memory (MAPPED)
+    char* blk = static_cast<char*>(mode == GTE_IO_MAPPED ? io.results : io.dev_results);
+    GteStepOut o = O;
+    o.reward = reinterpret_cast<double*>(blk);
+    o.terminated = reinterpret_cast<uint8_t*>(blk + GTE_HOST_RESULT_TERM_OFFSET(N));
+    o.truncated = reinterpret_cast<uint8_t*>(blk + GTE_HOST_RESULT_TRUNC_OFFSET(N));
+    o.error_out = reinterpret_cast<int32_t*>(blk + GTE_HOST_RESULT_ERROR_OFFSET(N));
+    volatile uint32_t* seq_word = reinterpret_cast<volatile uint32_t*>(static_cast<char*>(io.results) + GTE_HOST_RESULT_SEQ_OFFSET(N));
+    uint32_t seq = 0;
+    if (mode == GTE_IO_MAPPED) {
+        seq = ++h->seq ? h->seq : ++h->seq;                  // never 0
+        *seq_word = 0;
+        o.seq_out = const_cast<uint32_t*>(seq_word);
+        o.seq_value = seq;
+    } else {
+        o.seq_out = nullptr;
+    }
+    const void* actions = io.actions;
+    if (mode == GTE_IO_COPY) {
+        // the previous call returned only after ITS step kernel's results had reached the host, so dev_actions is
+        // free: the copy does not wait for `stream` and runs beside the previous iteration's gather
+        if ((e = cudaMemcpyAsync(io.dev_actions, io.actions, (size_t)(N * ab), cudaMemcpyHostToDevice, h->in)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(h->ev_in, h->in)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(stream, h->ev_in, 0)) != cudaSuccess) return e;
+        actions = io.dev_actions;
+    }
+    float* obs_rows = P.windows == 0 ? obs : nullptr;        // windows=None: the step kernel writes the one-row observation
+    if ((e = launch_step_range(P, D, S, actions, o, autoreset, 0, P.n_envs, kChunkFirst | kChunkLast, stream, obs_rows)) != cudaSuccess) return e;
+    if (io.step_done_event != nullptr &&
+        (e = cudaEventRecord(static_cast<cudaEvent_t>(io.step_done_event), stream)) != cudaSuccess) return e;
+    if (mode == GTE_IO_COPY) {
+        if ((e = cudaEventRecord(h->ev_step, stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(h->out, h->ev_step, 0)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(io.results, io.dev_results, (size_t)GTE_HOST_RESULT_BYTES(N), cudaMemcpyDeviceToHost, h->out)) != cudaSuccess) return e;
+        if (P.windows > 0 && (e = launch_obs_range(P, D, S, obs, variant, 0, P.n_envs, stream)) != cudaSuccess) return e;
+        return cudaStreamSynchronize(h->out);               // reward / flags / error flag are on the host; the gather runs on
+    }
+    // MAPPED: the kernel itself wrote the host block and, last, the call's sequence number: poll that word instead
+    // of going through the driver (the lowest-latency completion signal there is)
+    if (P.windows > 0 && (e = launch_obs_range(P, D, S, obs, variant, 0, P.n_envs, stream)) != cudaSuccess) return e;
+    for (uint32_t spins = 1; *seq_word != seq; ++spins) {
+        _mm_pause();
+        if ((spins & 0x3fffu) == 0) {                        // a faulted kernel never writes the word: ask the driver now and then
+            e = cudaStreamQuery(stream);
+            if (e != cudaErrorNotReady) return (e == cudaSuccess && *seq_word != seq) ? cudaErrorUnknown : e;
+        }
     }
     return cudaSuccess;
 }

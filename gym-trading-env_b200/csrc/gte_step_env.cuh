@@ -19,8 +19,26 @@ struct MetricAcc {           // per-thread accumulators (deterministic: fixed ti
 };
 
 // The transition of ONE env (the reference's step(), line by line).
+// action i of an array of 1-, 2-, 4- or 8-byte signed ints (GteParams.action_bytes; warp-uniform switch).  The array may
+// be mapped HOST memory (gte_step_host, MAPPED mode): plain loads, each element read exactly once.
+__device__ __forceinline__ int64_t load_action(const void* __restrict__ actions, int bytes, int64_t i) {
+    switch (bytes) {
+        case 1: return (int64_t) reinterpret_cast<const int8_t*>(actions)[i];
+        case 2: return (int64_t) reinterpret_cast<const int16_t*>(actions)[i];
+        case 4: return (int64_t) reinterpret_cast<const int32_t*>(actions)[i];
+        default: return reinterpret_cast<const int64_t*>(actions)[i];
+    }
+}
+
+// Per-launch constants derived on the host (gte_step.cu: make_step_consts).
+struct StepConsts {
+    double done_thr;      // largest double x with fl(x / v0) <= done_ratio (IEEE division is monotonic in x), or NaN:
+                          // `valuation <= done_thr` is then bit-for-bit `valuation / v0 <= done_ratio` (:246) without the divide
+    int action_bytes;     // 1, 2, 4 or 8
+};
+
 __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteData& D, const GteState& S,
-                                                  const int64_t* __restrict__ actions,
+                                                  const void* __restrict__ actions, const StepConsts& K,
                                                   const GteStepOut& O, uint64_t tick, int ring_slot, int autoreset,
                                                   int i, MetricAcc& acc, const double* __restrict__ pos_tab) {
     EnvRegs e;
@@ -32,16 +50,17 @@ __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteD
     e.step = S.step[i];
     e.ep_start = S.ep_start[i];
     e.ds = (P.n_datasets > 1) ? S.dataset_idx[i] : 0;
-    int64_t a = actions[i];
+    int64_t a = load_action(actions, K.action_bytes, i);
 
     const double* __restrict__ price = D.price + (int64_t)e.ds * P.t_stride;
     const int T = D.lengths[e.ds];
     int idx = e.ep_start + e.step;
     if (idx + 1 >= T) {              // stepping past the end of the data without a reset (caller bug)
-        atomicOr(S.error_flag, 2);
+        atomicOr(S.error_flag, GTE_E_PAST_END);
         idx = T - 2;
     }
-    if (a >= (int64_t)P.n_positions) { atomicOr(S.error_flag, 1); a = -1; }
+    if (a >= (int64_t)P.n_positions) { atomicOr(S.error_flag, GTE_E_ACTION_RANGE); a = -1; }
+    if (P.strict_actions && a < -1) atomicOr(S.error_flag, GTE_E_NEGATIVE_ACTION);
 
     const double p0 = __ldg(price + idx);                                    // price BEFORE advancing (:204-207)
     const double p1 = __ldg(price + idx + 1);
@@ -74,7 +93,8 @@ __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteD
     }
     update_interest(e.pf, P.rate);                                           // :240
     const double val = valorisation(e.pf, p1);                               // :241
-    const bool done = ddiv(val, P.v0) <= P.done_ratio;                       // :246
+    const bool done = (K.done_thr == K.done_thr) ? (val <= K.done_thr)       // :246 without the divide (StepConsts)
+                                                 : (ddiv(val, P.v0) <= P.done_ratio);
     bool trunc = idx >= T - 1;                                               // :248
     if (P.max_episode_duration >= 0 && e.step >= P.max_episode_duration - 1) trunc = true;   // :250
     const double rp = real_position(e.pf, p1, val);                          // :259
@@ -169,6 +189,8 @@ static __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O,
         s_part[warp][GTE_M_RESERVED] = 0.0;
     }
     __syncthreads();
+    // results written straight into mapped host memory: visible system-wide before this CTA takes its ticket
+    if (O.seq_out != nullptr) __threadfence_system();
     if (threadIdx.x < GTE_N_METRICS) {
         double t = 0.0;
 #pragma unroll
@@ -196,6 +218,12 @@ static __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O,
         if (O.metrics_total) O.metrics_total[threadIdx.x] = dadd(O.metrics_total[threadIdx.x], tot);
     }
     if (threadIdx.x == 0) {
+        // every CTA OR-ed its error bits before it took its ticket: the flag is complete here (may be mapped host memory)
+        if (O.error_out != nullptr) *O.error_out = __ldcg(S.error_flag);
+        if (O.seq_out != nullptr) {                      // every CTA fenced its results system-wide before its ticket
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t*>(O.seq_out) = O.seq_value;
+        }
         *O.block_counter = 0u;                           // self-resetting for the next launch
         // every CTA of this launch has read the tick / ring clock by now.  The Philox event counter advances with
         // the LAST env range of an iteration; the ring clock with the FIRST one, so that the later ranges and

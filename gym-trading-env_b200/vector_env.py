@@ -25,7 +25,8 @@ from . import _cabi
 from .data import SeriesArrays, build_window_tables, frame_to_arrays
 
 
-_NARROW_ACTION_DTYPES = (np.dtype(np.int8), np.dtype(np.uint8), np.dtype(np.int16), np.dtype(np.int32))
+# host action arrays cross PCIe in their own width and are widened by the step kernel's load (GteParams.action_bytes)
+_WIRE_ACTION_DTYPES = (np.dtype(np.int8), np.dtype(np.int16), np.dtype(np.int32), np.dtype(np.int64))
 
 
 # ---- names the reference exports and callers pass back in (identity-compared, never called) -------
@@ -144,8 +145,8 @@ class LazyInfos(Mapping):
 
     def __getitem__(self, key):
         e = self._env
-        if key == "reward":
-            return e._reward
+        if key == "reward":               # host-output modes: the step's rewards are in the pinned result block
+            return e._host["reward"] if (e.output != "torch" and e._host is not None) else e._reward
         if key == "episode_metrics":
             return e.get_metrics()
         if key not in self.KEYS:
@@ -177,9 +178,11 @@ class TradingVectorEnv:
     ``[N, E, 3]`` of (start row, position index, dataset index) consumed by successive resets
     instead of the RNG (record-and-replay for parity tests); ``obs_variant`` in
     {"auto","generic","vec","tma"}; ``output`` "torch" (CUDA tensors, default), "numpy" (everything
-    in pinned host buffers, host<->device copies inside `step`) or "hybrid" (reward / terminated /
-    truncated on the host, observations stay device-resident for an on-device policy; the copies
-    run on side streams beside the gather kernel); ``autoreset`` (True = in-place); ``cuda_graph``
+    in pinned host buffers, host<->device copies inside `step`) or "hybrid" (host actions in, reward /
+    terminated / truncated on the host, observations stay device-resident for the policy's forward pass:
+    one blocking ``gte_step_host`` C call per step — ONE copy per direction beside the gather kernel, or,
+    for small batches, no copy at all: the step kernel reads / writes the pinned host memory itself;
+    ``host_io`` = "auto" | "copy" | "mapped" picks the mechanism); ``autoreset`` (True = in-place); ``cuda_graph``
     (capture one lockstep iteration and replay it: removes the launch overhead at small N; actions
     are then read from the env's own buffer); ``n_chunks`` (0 = library default = 1; k > 1 cuts the envs
     into k ranges and runs the step kernel of range c+1 beside the gather of range c on a side stream —
@@ -187,9 +190,13 @@ class TradingVectorEnv:
     ``debug_outputs`` (also write the terminal step's idx/step/real_position/portfolio, +48 B/env);
     ``final_obs`` (gymnasium's SAME_STEP ``final_obs``: ``env.final_obs`` keeps, for every env whose episode
     ended in this step, the observation ``step()`` itself returned before the in-place reset
-    (environments.py:272); costs a second gather, off by default); ``host_reward_dtype`` (float64; float32 halves
-    the reward bytes the "numpy" / "hybrid" modes copy to the host — rounded on the device from the fp64 reward,
-    which stays available as ``env._reward``).
+    (environments.py:272); costs a second gather, off by default); ``strict_actions`` (False: every negative
+    action means "hold", the reference's ``position_index=None``; True: only -1 does, any other negative index raises
+    IndexError — the reference's ``positions[-k]`` would silently index from the end of the list).
+
+    Host actions (``output`` "numpy" / "hybrid") may be int8 / int16 / int32 / int64: they cross PCIe in that width
+    (``Discrete(P)`` fits int8 for every supported P, which is what :meth:`pinned_actions` hands out by default) and
+    are widened by the step kernel's own load — lossless, 8x fewer host-to-device bytes than gymnasium's int64.
 
     ``reward_function`` must be :func:`basic_reward_function` or a :class:`DeviceReward` from the fused
     catalogue (log / simple return with scale and clip), and ``dynamic_feature_functions`` the two
@@ -207,8 +214,8 @@ class TradingVectorEnv:
                  max_episode_duration="max", verbose=1, name="Stock", render_mode="logs", *,
                  num_envs=1, device=None, seed=0, env_id_offset=0, done_valuation_ratio=0.7,
                  reset_plan=None, obs_variant="auto", output="torch", autoreset=True,
-                 debug_outputs=False, cuda_graph=False, n_chunks=0, final_obs=False, host_reward_dtype=np.float64,
-                 _multi_dataset=False, _episodes_between_dataset_switch=1):
+                 debug_outputs=False, cuda_graph=False, n_chunks=0, final_obs=False, strict_actions=False,
+                 host_io="auto", _multi_dataset=False, _episodes_between_dataset_switch=1):
         self._lib = _cabi.load()                      # fails loudly when the CUDA library is missing
         if not torch.cuda.is_available():
             raise RuntimeError("gym_trading_env_b200 needs a CUDA device (no CPU fallback)")
@@ -267,9 +274,10 @@ class TradingVectorEnv:
         self.env_id_offset = int(env_id_offset)
         self.done_valuation_ratio = float(done_valuation_ratio)
         self.output = output
-        self.host_reward_dtype = np.dtype(host_reward_dtype)
-        if self.host_reward_dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
-            raise ValueError("host_reward_dtype must be float64 or float32")
+        if host_io not in _cabi.IO_MODES:
+            raise ValueError(f"host_io must be one of {list(_cabi.IO_MODES)}")
+        self.host_io = host_io
+        self.strict_actions = bool(strict_actions)
         self.autoreset = bool(autoreset)
         self.debug_outputs = bool(debug_outputs)
         self.cuda_graph = bool(cuda_graph)
@@ -277,7 +285,8 @@ class TradingVectorEnv:
         self.keep_final_obs = bool(final_obs)
         self.final_obs = None
         self._graph = None
-        self._copy_in = self._copy_out = None
+        self._copy_in = None
+        self._pin_ident = {}                 # id(array) -> (array, pointer, itemsize) of pinned action arrays seen by step()
         self._track_ids = None
         self._limit_price = None
         self._red_stream = None              # enable_metric_allreduce(): side stream of the per-iteration all-reduce
@@ -384,15 +393,22 @@ class TradingVectorEnv:
             self._reset_plan = plan.to(dev).contiguous()
         obs_shape = (N, F) if self.windows is None else (N, W, F)
         self._obs = torch.zeros(obs_shape, dtype=torch.float32, device=dev)
-        self._reward, self._valuation, self._real_position = f64(N), f64(N), f64(N)
-        self._terminated = torch.zeros(N, dtype=torch.uint8, device=dev)
-        self._truncated = torch.zeros(N, dtype=torch.uint8, device=dev)
+        # reward | terminated | truncated | error flag live in ONE block (GTE_HOST_RESULT_* layout): what a host policy
+        # needs back from an iteration leaves the device with a single copy
+        toff, uoff, eoff, nbytes = _cabi.host_result_layout(N)
+        self._result_block = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        self._reward = self._result_block[:8 * N].view(torch.float64)
+        self._terminated = self._result_block[toff:toff + N]
+        self._truncated = self._result_block[uoff:uoff + N]
+        self._error_out = self._result_block[eoff:eoff + 4].view(torch.int32)
+        self._valuation, self._real_position = f64(N), f64(N)
         self._info_idx, self._info_step = i32(N), i32(N)
         self._pre_reset_portfolio = f64(4, N)
         self._metric_partials = f64(_cabi.GTE_MAX_PARTIAL_ROWS, _cabi.GTE_N_METRICS)
         self._metrics_step, self._metrics_total = f64(_cabi.GTE_N_METRICS), f64(_cabi.GTE_N_METRICS)
         self._block_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self._actions_dev = torch.zeros(N, dtype=torch.int64, device=dev)
+        self._actions_raw = self._actions_dev.view(torch.uint8)          # the same bytes, for narrow host actions
         # lazily computed info columns
         self._info_t = {"idx": i32(N), "step": i32(N), "position_index": i32(N), "dataset_idx": i32(N),
                         "position": f64(N), "real_position": f64(N), "portfolio_valuation": f64(N),
@@ -417,6 +433,7 @@ class TradingVectorEnv:
         p.v0, p.done_ratio = self.portfolio_initial_value, self.done_valuation_ratio
         p.reward_kind = DeviceReward.KINDS[self._reward_spec.kind]
         p.reward_scale, p.reward_lo, p.reward_hi = self._reward_spec.scale, self._reward_spec.lo, self._reward_spec.hi
+        p.strict_actions = int(self.strict_actions)
         for i, x in enumerate(self.positions):
             p.positions[i] = float(x)
         d = _cabi.GteData()
@@ -444,6 +461,7 @@ class TradingVectorEnv:
             o.pre_reset_portfolio = self._pre_reset_portfolio.data_ptr()
         o.metric_partials, o.metrics_step = self._metric_partials.data_ptr(), self._metrics_step.data_ptr()
         o.metrics_total, o.block_counter = self._metrics_total.data_ptr(), self._block_counter.data_ptr()
+        o.error_out = self._error_out.data_ptr()
         i = _cabi.GteInfo()
         t = self._info_t
         i.idx, i.step, i.position_index, i.dataset_idx = (t["idx"].data_ptr(), t["step"].data_ptr(),
@@ -505,19 +523,52 @@ class TradingVectorEnv:
         self._graph = g
 
     def _host_buffers(self):
+        """Pinned host side of the "numpy" / "hybrid" modes: ONE result block (reward | terminated | truncated | error
+        flag, the layout of the device block) and one action staging buffer per wire dtype."""
         if self._host is None:
-            pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)   # noqa: E731
-            self._host = {"actions": pin(self._actions_dev), "reward": pin(self._reward),
-                          "terminated": pin(self._terminated), "truncated": pin(self._truncated),
-                          "error_flag": pin(self._error_flag)}
-            if self.host_reward_dtype == np.dtype(np.float32):
-                self._reward32 = torch.empty(self.num_envs, dtype=torch.float32, device=self.device)
-                self._host["reward"] = pin(self._reward32)
+            N = self.num_envs
+            toff, uoff, eoff, nbytes = _cabi.host_result_layout(N)
+            blk = torch.zeros(nbytes, dtype=torch.uint8, pin_memory=True)
+            r = blk.numpy()
+            self._host = {"results": blk, "reward": r[:8 * N].view(np.float64),
+                          "terminated": r[toff:toff + N].view(np.bool_), "truncated": r[uoff:uoff + N].view(np.bool_),
+                          "error": r[eoff:eoff + 4].view(np.int32), "actions": {}, "pinned": {}}
             if self.output == "numpy":
-                self._host["obs"] = pin(self._obs)
+                self._host["obs_t"] = torch.empty(self._obs.shape, dtype=self._obs.dtype, pin_memory=True)
+                self._host["obs"] = self._host["obs_t"].numpy()
             self._copy_in = torch.cuda.Stream(device=self.device)
-            self._copy_out = torch.cuda.Stream(device=self.device)
+            io = _cabi.GteHostIO()
+            io.results, io.dev_results = blk.data_ptr(), self._result_block.data_ptr()
+            io.dev_actions, io.mode = self._actions_raw.data_ptr(), _cabi.IO_MODES[self.host_io]
+            self._io, self._io_mode_used = io, C.c_int(0)
+            self._io_ref, self._io_mode_ref = C.byref(io), C.byref(self._io_mode_used)
+            # recorded by gte_step_host right behind the step kernel: lets the metric all-reduce run beside the gather
+            self._step_done = torch.cuda.Event()
+            self._step_done.record(torch.cuda.current_stream(self.device))
         return self._host
+
+    def _stage_host_actions(self, actions):
+        """numpy / list actions -> (array in PINNED memory, its dtype one of int8/16/32/64).  Arrays handed out by
+        :meth:`pinned_actions` (or any other pinned array) are used in place; everything else goes through one
+        staging copy into a pinned buffer of the same width (other integer dtypes: widened to int64)."""
+        hb = self._host_buffers()
+        a = np.asarray(actions)
+        if a.shape != (self.num_envs,):
+            raise ValueError(f"actions must have shape ({self.num_envs},), got {a.shape}")
+        if a.dtype in _WIRE_ACTION_DTYPES and a.flags.c_contiguous:
+            known = hb["pinned"].get(a.ctypes.data)
+            if known is None and a.flags.writeable and len(hb["pinned"]) < 64:
+                known = hb["pinned"][a.ctypes.data] = bool(torch.from_numpy(a).is_pinned())
+            if known:
+                return a
+        dt = a.dtype if a.dtype in _WIRE_ACTION_DTYPES else np.dtype(np.int64)
+        buf = hb["actions"].get(dt)
+        if buf is None:
+            t = torch.empty(self.num_envs, dtype=torch.from_numpy(np.empty(0, dt)).dtype, pin_memory=True)
+            buf = hb["actions"][dt] = t.numpy()
+            hb["actions"][("t", dt)] = t                      # keeps the pinned allocation alive
+        buf[...] = a
+        return buf
 
     # ------------------------------------------------------------------ gymnasium vector API
     def reset(self, seed=None, options=None):
@@ -527,6 +578,7 @@ class TradingVectorEnv:
             if seed is not None:
                 self.seed = int(seed)
                 self._P.seed = self.seed & (2**64 - 1)
+                self._graph = None        # captured kernel nodes hold GteParams (and with it the old seed) by value
             if self._needs_first:                                  # MultiDatasetTradingEnv.__init__ draw (:378)
                 self._launch_reset(None, first=True)
                 self._needs_first = False
@@ -558,59 +610,84 @@ class TradingVectorEnv:
             if rc:
                 _cabi.check(rc, "gte_step_obs")
             return self._obs, self._reward, self._term_b, self._trunc_b, self.infos
+        host_in = not (isinstance(actions, torch.Tensor) and actions.is_cuda)
+        if (host_in and self.output == "hybrid" and self._track_ids is None and not self.keep_final_obs
+                and not self.cuda_graph and self._kernel_events is None and self.autoreset):
+            return self._step_host(actions)
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
-            host_in = not (isinstance(actions, torch.Tensor) and actions.is_cuda)
             if host_in:
-                a = np.asarray(actions)
-                if a.shape != (self.num_envs,):
-                    raise ValueError(f"actions must have shape ({self.num_envs},), got {a.shape}")
-                hb = self._host_buffers()
-                src = None
-                narrow = a.dtype in _NARROW_ACTION_DTYPES            # int8/int16/int32 (uint8): widened ON THE DEVICE
-                if (a.dtype == np.int64 or narrow) and a.flags.c_contiguous and a.flags.writeable:
-                    t = torch.from_numpy(a)
-                    if t.is_pinned():
-                        src = t                                      # caller already staged them in pinned memory
-                if src is None:
-                    if narrow:
-                        key = "actions_" + a.dtype.name
-                        if key not in hb:
-                            hb[key] = torch.empty(self.num_envs, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
-                        hb[key].numpy()[...] = a
-                        src = hb[key]
-                    else:
-                        hb["actions"].numpy()[...] = a               # pageable (any integer dtype) -> pinned int64 staging copy
-                        src = hb["actions"]
-                # H2D on its own stream: it may run beside the previous iteration's gather.  Out-of-range
-                # actions are flagged by the kernel (positions[position_index] would raise, :234) and the
-                # flag rides back with the results in the host-output modes.
-                if self.output != "hybrid":
-                    self._copy_in.wait_stream(main)          # the last step kernel may still be reading the buffer
-                # (hybrid: step() returned only after the last step kernel's results had reached the host, so the
-                #  buffer is free and the copy may run beside the previous iteration's gather)
+                src = self._stage_host_actions(actions)
+                # H2D on its own stream, in the array's own width (the step kernel widens while loading).  Out-of-range
+                # actions are flagged by the kernel (positions[position_index] would raise, :234) and the flag rides
+                # back with the results in the host-output modes.
+                self._copy_in.wait_stream(main)              # the last step kernel may still be reading the buffer
+                nb = src.dtype.itemsize
                 with torch.cuda.stream(self._copy_in):
-                    if src.dtype == torch.int64:
-                        self._actions_dev.copy_(src, non_blocking=True)
-                    else:                                            # 1/2/4 bytes per action over PCIe, sign-extended here
-                        key = "dev_" + str(src.dtype)
-                        if key not in hb:
-                            hb[key] = torch.empty(self.num_envs, dtype=src.dtype, device=self.device)
-                        hb[key].copy_(src, non_blocking=True)
-                        self._actions_dev.copy_(hb[key])
+                    self._actions_raw[:nb * self.num_envs].copy_(torch.from_numpy(src.view(np.uint8)), non_blocking=True)
                 main.wait_stream(self._copy_in)
-                act = self._actions_dev
+                act, act_bytes = self._actions_dev, nb
             else:
-                act = actions
+                act, act_bytes = actions, 8
                 if act.dtype != torch.int64 or not act.is_contiguous() or act.shape != (self.num_envs,) \
                         or act.device != self.device:
                     act = act.to(device=self.device, dtype=torch.int64).contiguous().view(self.num_envs)
+            if self._track_ids is not None or (self.cuda_graph and act_bytes != 8):
+                if act_bytes != 8:               # the History log / the captured graph read the actions as int64
+                    nt = {1: torch.int8, 2: torch.int16, 4: torch.int32}[act_bytes]
+                    wide = self._actions_raw[:act_bytes * self.num_envs].view(nt).to(torch.int64)
+                    self._actions_dev.copy_(wide)
+                    act, act_bytes = self._actions_dev, 8
             if self._track_ids is not None:
                 self._track_pre = (self._pos_idx[self._track_ids].clone(), self._dataset_idx[self._track_ids].clone())
-            ret = self._step_launch(act, main)
+            self._P.action_bytes = act_bytes
+            try:
+                ret = self._step_launch(act, main)
+            finally:
+                self._P.action_bytes = 0
             if self._track_ids is not None:
                 self._track_append(after_reset=False, actions=act)
             return ret
+
+    def _step_host(self, actions):
+        """output="hybrid": ONE blocking C call (gte_step_host) — host actions in, step kernel, reward / terminated /
+        truncated / error flag back in one pinned block, gather enqueued; returns as soon as the block has landed."""
+        ent = self._pin_ident.get(id(actions))
+        if ent is not None and ent[0] is actions:            # a pinned array seen before (kept alive by the cache)
+            ptr, nb = ent[1], ent[2]
+        else:
+            a = self._stage_host_actions(actions)
+            ptr, nb = a.ctypes.data, a.dtype.itemsize
+            if a is actions and len(self._pin_ident) < 64:
+                self._pin_ident[id(actions)] = (actions, ptr, nb)
+        hb, io, red = self._host, self._io, self._red_stream
+        if hb is None:
+            hb = self._host_buffers()
+            io = self._io
+        if red is not None and self._red_snapshot is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._red_snapshot)   # metrics_step is about to be overwritten
+        io.actions = ptr
+        io.step_done_event = self._step_done.cuda_event if red is not None else None
+        self._P.action_bytes = nb
+        self._tick += 1
+        f = self._fast_args
+        try:
+            if torch.cuda.current_device() == self._dev_index:
+                rc = self._lib.gte_step_host(f[0], f[1], f[2], self._io_ref, f[3], f[4], 1, self._obs_variant,
+                                             self._io_mode_ref, torch.cuda.current_stream(self.device).cuda_stream)
+            else:
+                with torch.cuda.device(self.device):
+                    rc = self._lib.gte_step_host(f[0], f[1], f[2], self._io_ref, f[3], f[4], 1, self._obs_variant,
+                                                 self._io_mode_ref, torch.cuda.current_stream(self.device).cuda_stream)
+        finally:
+            self._P.action_bytes = 0
+        if rc:
+            _cabi.check(rc, "gte_step_host")
+        if red is not None:
+            self._issue_metric_allreduce(None, after=self._step_done)
+        if hb["error"][0]:
+            self._raise_on_flag(int(hb["error"][0]))
+        return self._obs, hb["reward"], hb["terminated"], hb["truncated"], self.infos
 
     def _step_launch(self, act, main):
         if self._red_stream is not None and self._red_snapshot is not None:
@@ -628,21 +705,6 @@ class TradingVectorEnv:
             self._launch_reset(C.c_void_p(ended.data_ptr()), first=False)
             self._tick -= 1                                 # one public call = one info version
             self._launch_obs()
-        elif self.output == "hybrid":
-            # reward / flags leave for the host right after the step kernel, beside the gather
-            hb = self._host_buffers()
-            self._launch_step(C.c_void_p(act.data_ptr()))
-            self._issue_metric_allreduce(main)
-            self._copy_out.wait_stream(main)
-            with torch.cuda.stream(self._copy_out):
-                for k, t in (("reward", self._host_reward_src()), ("terminated", self._terminated),
-                             ("truncated", self._truncated), ("error_flag", self._error_flag)):
-                    hb[k].copy_(t, non_blocking=True)
-            self._launch_obs()
-            self._copy_out.synchronize()
-            self._raise_on_flag(int(hb["error_flag"][0]))
-            return (self._obs, hb["reward"].numpy(), hb["terminated"].numpy().view(np.bool_),
-                    hb["truncated"].numpy().view(np.bool_), self.infos)
         elif self.cuda_graph:
             if act.data_ptr() != self._actions_dev.data_ptr():
                 self._actions_dev.copy_(act, non_blocking=True)
@@ -650,11 +712,14 @@ class TradingVectorEnv:
                 self._capture_graph()
             self._tick += 1
             self._graph.replay()
-        elif self._red_stream is not None and self.windows is not None and not (
+        elif self.windows is not None and (self._red_stream is not None or self.output == "hybrid") and not (
                 self._kernel_events is not None and self._tick % self._kernel_events_every == 0):
-            # the all-reduce is issued between the two kernels so that it overlaps the gather
+            # the all-reduce (and, in the hybrid mode, the result copy) is issued between the two kernels so that it
+            # overlaps the gather
             self._launch_step(C.c_void_p(act.data_ptr()))
             self._issue_metric_allreduce(main)
+            if self.output == "hybrid":
+                return self._results_to_host(main, before_gather=True)
             self._launch_obs()
         elif self._kernel_events is not None and self.windows is not None and self._tick % self._kernel_events_every == 0:
             # (bench.py, every k-th iteration) the same two kernels as gte_step_obs, issued as two calls so that
@@ -670,35 +735,41 @@ class TradingVectorEnv:
         else:
             self._launch_step_obs(C.c_void_p(act.data_ptr()))
             self._issue_metric_allreduce(main)
-        if self.output == "numpy":
-            h = self._host_buffers()
-            for k, t in (("obs", self._obs), ("reward", self._host_reward_src()), ("terminated", self._terminated),
-                         ("truncated", self._truncated), ("error_flag", self._error_flag)):
-                h[k].copy_(t, non_blocking=True)
-            main.synchronize()
-            self._raise_on_flag(int(h["error_flag"][0]))
-            return (h["obs"].numpy(), h["reward"].numpy(), h["terminated"].numpy().view(np.bool_),
-                    h["truncated"].numpy().view(np.bool_), self.infos)
+        if self.output in ("numpy", "hybrid"):
+            return self._results_to_host(main, before_gather=False)
         return self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), self.infos
 
-    def _host_reward_src(self):
-        """The device tensor the host reward is copied from (on the current stream): the fp64 reward itself, or its
-        float32 rounding when ``host_reward_dtype`` asks for fewer bytes on the wire."""
-        if self.host_reward_dtype == np.dtype(np.float64):
-            return self._reward
-        self._reward32.copy_(self._reward)
-        return self._reward32
+    def _results_to_host(self, main, before_gather):
+        """The general host-output path (device actions, tracking, final_obs, CUDA graphs ...): ONE device-to-host copy
+        of the result block (+ the observation batch in the "numpy" mode), then the error flag is checked."""
+        hb = self._host_buffers()
+        if before_gather:                                   # hybrid: the block leaves beside the gather kernel
+            self._copy_in.wait_stream(main)
+            with torch.cuda.stream(self._copy_in):
+                hb["results"].copy_(self._result_block, non_blocking=True)
+            self._launch_obs()
+            self._copy_in.synchronize()
+        else:
+            hb["results"].copy_(self._result_block, non_blocking=True)
+            if self.output == "numpy":
+                hb["obs_t"].copy_(self._obs, non_blocking=True)
+            main.synchronize()
+        if hb["error"][0]:
+            self._raise_on_flag(int(hb["error"][0]))
+        obs = hb["obs"] if self.output == "numpy" else self._obs
+        return obs, hb["reward"], hb["terminated"], hb["truncated"], self.infos
 
     def _emit_obs(self):
         if self.output == "numpy":
             h = self._host_buffers()
-            h["obs"].copy_(self._obs, non_blocking=True)
+            h["obs_t"].copy_(self._obs, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
-            return h["obs"].numpy()
+            return h["obs"]
         return self._obs
 
     def close(self):
         self._host = None
+        self._pin_ident = {}
         self._graph = None
 
     def add_limit_order(self, position, limit, persistent=False, env_ids=None):
@@ -946,12 +1017,14 @@ class TradingVectorEnv:
         self.global_metrics_step, self.global_metrics_total = torch.zeros(8, **f64), torch.zeros(8, **f64)
         self._red_snapshot = None
 
-    def _issue_metric_allreduce(self, main):
+    def _issue_metric_allreduce(self, main, after=None):
         if self._red_stream is None:
             return
         import torch.distributed as dist
-        ev = torch.cuda.Event()
-        ev.record(main)                                  # the step kernel (which wrote metrics_step) is the last thing on main
+        ev = after                                       # gte_step_host recorded it right behind the step kernel
+        if ev is None:
+            ev = torch.cuda.Event()
+            ev.record(main)                              # the step kernel (which wrote metrics_step) is the last thing on main
         with torch.cuda.stream(self._red_stream):
             self._red_stream.wait_event(ev)
             self.global_metrics_step.copy_(self._metrics_step, non_blocking=True)     # 64 B device-to-device copy
@@ -970,17 +1043,33 @@ class TradingVectorEnv:
         """Synchronising check of the in-kernel error flags (device-resident actions are not validated on the host)."""
         self._raise_on_flag(int(self._error_flag.item()))
 
-    def pinned_actions(self, dtype=np.int64):
-        """A pinned [N] numpy array (int64, or int8/uint8/int16/int32 to move fewer bytes over PCIe — the device
-        widens them): fill it and pass it to `step()` to skip the staging copy."""
-        return torch.empty(self.num_envs, dtype=torch.from_numpy(np.empty(0, dtype)).dtype, pin_memory=True).numpy()
+    def pinned_actions(self, dtype=None):
+        """A pinned [N] numpy array to fill and pass to `step()` (no staging copy).  ``dtype`` None = the narrowest
+        signed integer that holds ``Discrete(len(positions))`` — int8 for every supported position list: one byte per
+        env over PCIe instead of gymnasium's eight, widened losslessly by the step kernel; int16 / int32 / int64 on request."""
+        dt = np.dtype(np.int8 if dtype is None else dtype)
+        if dt not in _WIRE_ACTION_DTYPES:
+            raise ValueError("pinned_actions: dtype must be int8, int16, int32 or int64")
+        t = torch.empty(self.num_envs, dtype=torch.from_numpy(np.empty(0, dt)).dtype, pin_memory=True)
+        a = t.numpy()
+        hb = self._host_buffers()
+        hb["pinned"][a.ctypes.data] = True
+        hb["actions"][("handed", a.ctypes.data)] = t          # keeps the allocation alive as long as the env
+        return a
 
-    @staticmethod
-    def _raise_on_flag(flag):
-        if flag & 1:
+    def _raise_on_flag(self, flag):
+        """Raise for the sticky in-kernel error bits (include/gte_b200.h GteErrorBit) and clear them."""
+        self._error_flag.zero_()
+        if flag & _cabi.E_ACTION_RANGE:
             raise IndexError("an action >= len(positions) was passed to step() (treated as hold)")
-        if flag & 2:
+        if flag & _cabi.E_NEGATIVE_ACTION:
+            raise IndexError("a negative action other than -1 was passed to step() (strict_actions=True; treated as hold)")
+        if flag & _cabi.E_PAST_END:
             raise IndexError("an env was stepped past the end of its data without a reset")
+        if flag & _cabi.E_PLAN_RANGE:
+            raise ValueError("reset_plan holds a row outside the dataset / position list (clamped)")
+        if flag & _cabi.E_PLAN_EXHAUSTED:
+            raise RuntimeError("reset_plan exhausted: more episodes were started than the plan holds (it wrapped around)")
 
     def state_dict(self):
         """Env state as tensors (checkpoint/resume: SURVEY.md §5)."""

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GTE_VERSION 105            /* 0.1.5 */
+#define GTE_VERSION 200            /* 0.2.0 */
 #define GTE_MAX_POSITIONS 64
 #define GTE_MAX_DATASETS 64        /* least-used rotation keeps a 64-bit "used this round" mask per env */
 #define GTE_N_METRICS 8
@@ -41,7 +41,15 @@ extern "C" {
 #define GTE_RING_BYTES(N, W) ((((int64_t)(N) + 31) / 32) * GTE_RING_TILE_BYTES(W))
 #define GTE_RING_RP_OFFSET(s, e) ((s) * 128 + (((((e) >> 2) ^ ((s) & 7))) << 4) + (((e) & 3) << 2))
 #define GTE_RING_POS_OFFSET(W, s, e) ((W) * 128 + (s) * 32 + (e))
-#define GTE_STEP_THREADS 256       /* envs per CTA of the step kernel; metric_partials has ceil(N/256) rows */
+#define GTE_STEP_THREADS 256       /* envs per tile of the step kernel */
+#define GTE_MAX_PARTIAL_ROWS 4096  /* rows of GteStepOut.metric_partials (one per CTA; every grid is capped at this) */
+/* host result block of gte_step_host: reward f64[N] | terminated u8[N] | truncated u8[N] | pad to 8 | error_flag i32 |
+ * sequence u32 (MAPPED mode: the number of the call whose results the block holds) */
+#define GTE_HOST_RESULT_TERM_OFFSET(N) ((int64_t)(N) * 8)
+#define GTE_HOST_RESULT_TRUNC_OFFSET(N) ((int64_t)(N) * 9)
+#define GTE_HOST_RESULT_ERROR_OFFSET(N) ((((int64_t)(N) * 10) + 7) / 8 * 8)
+#define GTE_HOST_RESULT_SEQ_OFFSET(N) (GTE_HOST_RESULT_ERROR_OFFSET(N) + 4)
+#define GTE_HOST_RESULT_BYTES(N) (GTE_HOST_RESULT_ERROR_OFFSET(N) + 8)
 
 #define GTE_OK 0
 #define GTE_ERR_ARG (-1)
@@ -68,6 +76,10 @@ enum GteRewardKind {
     GTE_REWARD_SIMPLE_RETURN = 1   /* f = (v_t - v_{t-1}) / v_{t-1}                                         */
 };
 
+enum GteErrorBit {
+    GTE_E_ACTION_RANGE = 1, GTE_E_PAST_END = 2, GTE_E_PLAN_RANGE = 4, GTE_E_PLAN_EXHAUSTED = 8, GTE_E_NEGATIVE_ACTION = 16
+};
+
 /* observation-gather kernel variants (gte_gather_obs `variant`) */
 enum GteObsVariant {
     GTE_OBS_AUTO = 0,              /* fastest variant the shape allows                              */
@@ -92,6 +104,11 @@ typedef struct GteParams {
     int32_t multi_dataset;           /* 1 = MultiDatasetTradingEnv.reset semantics (:393-400)          */
     int32_t reward_kind;             /* enum GteRewardKind: which fused reward functor (:50-51 `reward_function`) */
     int32_t n_limit_positions;       /* how many positions carry limit orders (0 = feature off, :217-231)          */
+    int32_t action_bytes;            /* element width of the `actions` array: 1, 2, 4 or 8 (signed ints); 0 = 8.
+                                        Discrete(P) fits int8 for every P <= GTE_MAX_POSITIONS: the narrow widths cut the
+                                        host->device bytes of a host policy 8x and are widened in the step kernel's load */
+    int32_t strict_actions;          /* 1: any negative action other than -1 sets error bit 4 (still treated as hold).
+                                        The reference's positions[-k] would index from the END of the list (:234)        */
     int32_t reserved0;
     int64_t t_stride;                /* rows allocated per dataset in `price` / `features`             */
     int64_t env_id_offset;           /* global index of env 0 (multi-GPU sharding; keys the RNG)       */
@@ -150,8 +167,10 @@ typedef struct GteState {
                                         (TradingEnv.add_limit_order :227-231), NaN = none; cleared at reset (:168) */
     const int32_t* limit_seq;        /* i32 [n_limit_positions]: position indices in the order the orders are tried
                                         (the reference iterates its dict in insertion order, :220)              */
-    int32_t* error_flag;             /* i32 [1]  bit 0: action out of range seen (treated as hold);
-                                                 bit 1: an env was stepped past the end of its data    */
+    int32_t* error_flag;             /* i32 [1]  sticky bits, OR-ed by the kernels (enum GteErrorBit):
+                                                 1 action >= n_positions (treated as hold); 2 an env was stepped past the
+                                                 end of its data; 4 a reset_plan row out of range (clamped); 8 reset_plan
+                                                 exhausted (wrapped around); 16 negative action other than -1 (strict_actions) */
     uint64_t* tick;                  /* u64 [1]  event counter keying the Philox draws; every gte_reset /
                                         gte_step / gte_step_obs call advances it by one ON THE DEVICE, so
                                         a captured CUDA graph of a step replays with fresh draws       */
@@ -169,11 +188,38 @@ typedef struct GteStepOut {
     int32_t* info_idx;               /* i32 [N]  info["idx"]                                      or NULL */
     int32_t* info_step;              /* i32 [N]  info["step"]                                     or NULL */
     double* pre_reset_portfolio;     /* f64 [4, N] asset, fiat, interest_asset, interest_fiat before the auto-reset, or NULL */
-    double* metric_partials;         /* f64 [ceil(N/GTE_STEP_THREADS), GTE_N_METRICS] scratch          */
+    double* metric_partials;         /* f64 [GTE_MAX_PARTIAL_ROWS, GTE_N_METRICS] scratch (one row per CTA)   */
     double* metrics_step;            /* f64 [GTE_N_METRICS] this iteration's metrics                    */
     double* metrics_total;           /* f64 [GTE_N_METRICS] running totals (+= metrics_step)    or NULL */
     uint32_t* block_counter;         /* u32 [1]  zero-initialised scratch (self-resetting)              */
+    int32_t* error_out;              /* i32 [1]  the last CTA of the launch stores *state->error_flag here, or NULL.
+                                        May be mapped host memory: the flag then reaches the host with the results     */
+    uint32_t* seq_out;               /* u32 [1]  or NULL: after every result of the launch is visible system-wide, the last
+                                        CTA stores seq_value here — a host thread polling mapped memory sees the
+                                        iteration complete without a driver call                                       */
+    uint32_t seq_value;
+    uint32_t reserved1;
 } GteStepOut;
+
+/* Host side of one lockstep iteration for a HOST policy (gte_step_host): actions come from pinned host memory,
+ * reward / terminated / truncated / error flag land in ONE pinned host block, observations stay in HBM. */
+enum GteHostIOMode {
+    GTE_IO_AUTO = 0,                 /* MAPPED while N * (action_bytes + 10) <= 1 MiB, else COPY            */
+    GTE_IO_COPY = 1,                 /* copy engines: ONE cudaMemcpyAsync per direction, beside the gather  */
+    GTE_IO_MAPPED = 2                /* zero-copy: the step kernel reads the actions from, and writes its
+                                        10 B/env of results straight into, the pinned (UVA-mapped) host memory:
+                                        no copy to enqueue, the small-N latency floor                      */
+};
+typedef struct GteHostIO {
+    const void* actions;             /* HOST, pinned: [N] signed ints of params->action_bytes bytes each              */
+    void* results;                   /* HOST, pinned: GTE_HOST_RESULT_BYTES(N) bytes, layout above                     */
+    void* dev_actions;               /* DEVICE staging, N * action_bytes bytes (COPY mode)                             */
+    void* dev_results;               /* DEVICE block of GTE_HOST_RESULT_BYTES(N) bytes, same layout (COPY mode)        */
+    void* step_done_event;           /* cudaEvent_t recorded on `stream` right behind the step kernel, or NULL: lets the
+                                        caller hang more work (the metric all-reduce) beside the gather                */
+    int32_t mode;                    /* enum GteHostIOMode                                                             */
+    int32_t reserved;
+} GteHostIO;
 
 /* Lazily computed info columns (History's last row, environments.py:253-264 / utils/history.py). */
 typedef struct GteInfo {
@@ -186,6 +232,9 @@ typedef struct GteInfo {
 
 int gte_version(void);
 const char* gte_last_error(void);
+/* Hash of the CUDA sources the library was compiled from (set by the build line, -DGTE_BUILD_ID=...); bindings
+ * compare it with the hash of the sources they ship to refuse a stale binary. */
+const char* gte_build_id(void);
 
 /* Replaces TradingEnv.reset (environments.py:163-199) [+ MultiDatasetTradingEnv.reset :393-400 and,
  * with first != 0, ONLY the dataset draw of MultiDatasetTradingEnv.__init__ :377-378] for every env
@@ -198,10 +247,11 @@ int gte_reset(const GteParams* params, const GteData* data, const GteState* stat
 /* Replaces TradingEnv.step (environments.py:233-272) for N envs: _take_action/_trade (:204-215) ->
  * Portfolio.trade_to_position (portfolio.py:18-43) -> index advance -> update_interest (:44-46) ->
  * valorisation (:7-13) -> done/truncated (:244-251) -> basic_reward_function (:17-18) -> episode
- * metrics (:279-283) -> in-place auto-reset when autoreset != 0.  actions: i64 [N] indices into
- * positions; a negative action = hold (the reference's position_index=None, :234). */
+ * metrics (:279-283) -> in-place auto-reset when autoreset != 0.  actions: [N] signed ints of
+ * params->action_bytes bytes (i64 by default), indices into positions; a negative action = hold (the reference's
+ * position_index=None, :234). */
 int gte_step(const GteParams* params, const GteData* data, const GteState* state,
-             const int64_t* actions, const GteStepOut* out, int autoreset, void* stream);
+             const void* actions, const GteStepOut* out, int autoreset, void* stream);
 
 /* Replaces TradingEnv._get_obs (environments.py:152-160): obs f32 [N, F] (windows=None) or
  * [N, W, F], F = n_static + n_dyn; static columns gathered from the device-resident tables,
@@ -216,26 +266,37 @@ int gte_gather_obs(const GteParams* params, const GteData* data, const GteState*
  * call is still stream-ordered and graph-capturable).  With windows == 0 the call is ONE launch: the step kernel
  * writes the one-row observation itself. */
 int gte_step_obs(const GteParams* params, const GteData* data, const GteState* state,
-                 const int64_t* actions, const GteStepOut* out, float* obs, int autoreset,
+                 const void* actions, const GteStepOut* out, float* obs, int autoreset,
                  int variant, int n_chunks, void* stream);
+
+/* One lockstep iteration for a policy that lives on the HOST — what a gymnasium VectorEnv.step(numpy actions) does
+ * (environments.py:233-272 for N envs) — as ONE blocking call: host actions in -> step kernel -> reward / flags / error
+ * flag out -> gather enqueued.  Returns once io->results holds this iteration's values; the observation gather may
+ * still be running on `stream` (the observations stay device-resident for the next policy forward pass).
+ * out->reward / terminated / truncated / error_out are ignored: the call points them into the result block itself.
+ * COPY mode: one H2D cudaMemcpyAsync (N * action_bytes) on a library-owned stream, the step kernel, ONE D2H
+ * cudaMemcpyAsync (GTE_HOST_RESULT_BYTES(N)) on a second library-owned stream beside the gather.  MAPPED mode: no copy
+ * at all (see GteHostIOMode).  *mode_used (may be NULL) receives the mode the call resolved to. */
+int gte_step_host(const GteParams* params, const GteData* data, const GteState* state, const GteHostIO* io,
+                  const GteStepOut* out, float* obs, int autoreset, int variant, int* mode_used, void* stream);
 
 /* n_steps lockstep iterations from a device-resident action stream, enqueued by ONE host call (the open-loop driver:
  * replay of recorded actions, random-policy baselines, back-tests; at small N an iteration then costs a kernel launch
- * instead of a trip through the host language).  actions: i64 [n_steps, N].  Every non-NULL per-env array of `out`
+ * instead of a trip through the host language).  actions: [n_steps, N] ints of params->action_bytes bytes.  Every non-NULL per-env array of `out`
  * (reward, terminated, truncated, valuation, real_position, info_idx, info_step, pre_reset_portfolio) holds n_steps
  * consecutive copies of its one-iteration shape, iteration k writing copy k; metrics_step ends up holding the last
  * iteration's metrics, metrics_total accumulates all of them.  keep_obs != 0: obs is f32 [n_steps, N, (W,) F] and
  * every iteration's observation is gathered; keep_obs == 0: obs is f32 [N, (W,) F] and only the LAST iteration's
  * observation is gathered (the dynamic-feature ring is kept up to date by the step kernel either way). */
 int gte_rollout(const GteParams* params, const GteData* data, const GteState* state,
-                const int64_t* actions, int n_steps, const GteStepOut* out, float* obs, int keep_obs,
+                const void* actions, int n_steps, const GteStepOut* out, float* obs, int keep_obs,
                 int autoreset, int variant, void* stream);
 
 /* History's last row as tensors (environments.py:253-264, portfolio.py:49-57), from current state. */
 int gte_info(const GteParams* params, const GteData* data, const GteState* state,
              const GteInfo* info, void* stream);
 
-/* sizeof() of the ABI structs as compiled: 0 GteParams, 1 GteData, 2 GteState, 3 GteStepOut, 4 GteInfo
+/* sizeof() of the ABI structs as compiled: 0 GteParams, 1 GteData, 2 GteState, 3 GteStepOut, 4 GteInfo, 5 GteHostIO
  * (bindings assert their own layout against it). */
 int gte_struct_size(int which);
 

@@ -31,13 +31,16 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/gte_b200.h but not exported"
     assert set(_cabi.EXPORTS) == set(_declared_functions())
     lib.gte_version.restype = ctypes.c_int
-    assert lib.gte_version() == 105
+    assert lib.gte_version() == _cabi.GTE_VERSION == 200
+    lib.gte_build_id.restype = ctypes.c_char_p
+    assert lib.gte_build_id().decode() == _cabi.source_hash() == _cabi.built_id()
 
 
 def test_ctypes_struct_layout_matches_the_compiled_structs():
     from gym_trading_env_b200 import _cabi
     lib = _cabi.load()      # load() itself raises on an ABI mismatch
-    for which, st in enumerate((_cabi.GteParams, _cabi.GteData, _cabi.GteState, _cabi.GteStepOut, _cabi.GteInfo)):
+    for which, st in enumerate((_cabi.GteParams, _cabi.GteData, _cabi.GteState, _cabi.GteStepOut, _cabi.GteInfo,
+                                _cabi.GteHostIO)):
         assert lib.gte_struct_size(which) == ctypes.sizeof(st), st.__name__
     assert lib.gte_struct_size(99) == -1
     assert lib.gte_default_chunks(1 << 21) >= 1

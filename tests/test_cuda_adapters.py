@@ -144,24 +144,10 @@ def test_narrow_integer_host_actions_are_widened_on_the_device(output):
                 assert np.array_equal(w, x), (dt, k)
     u8 = H.make_device_env(g, output=output)
     u8.reset()
-    u8.step(g["actions"][0].astype(np.uint8))
+    u8.step(g["actions"][0].astype(np.uint8))                        # other integer dtypes are widened to int64 on the host
     with pytest.raises(IndexError):                                  # 255 is not a position: flagged like any bad index
         u8.step(np.full(g["params"]["n_envs"], 255, np.uint8))
         u8.check_errors()
-
-
-@pytest.mark.parametrize("output", ["numpy", "hybrid"])
-def test_float32_host_rewards_are_the_rounded_fp64_rewards(output):
-    g = H.load_golden("c3_windows_leveraged")
-    ref = H.make_device_env(g, output=output)
-    env = H.make_device_env(g, output=output, host_reward_dtype=np.float32)
-    ref.reset(); env.reset()
-    for k in range(50):
-        want = ref.step(g["actions"][k])
-        got = env.step(g["actions"][k])
-        assert got[1].dtype == np.float32 and want[1].dtype == np.float64
-        assert np.array_equal(got[1], want[1].astype(np.float32))
-        assert np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3])
-        assert np.array_equal(env._reward.cpu().numpy(), want[1])            # the fp64 reward stays on the device
+    assert env.pinned_actions().dtype == np.int8                     # the default wire type holds Discrete(P)
     with pytest.raises(ValueError):
-        H.make_device_env(g, host_reward_dtype=np.float16)
+        env.pinned_actions(np.uint8)

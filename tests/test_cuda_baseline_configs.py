@@ -1,0 +1,261 @@
+"""GPU: oracle parity at BASELINE.json's FULL configuration sizes, and of the host-facing paths at scale.
+
+  C4  : MultiDatasetTradingEnv semantics on 32 datasets x 1 000 000 rows with 2^20 envs, windows=64 — a block of 128
+        envs inside the run against the CPU oracle (Philox resets, least-used dataset rotation, in-place auto-reset),
+        plus the gathered windows of a sample of ALL envs against the rows of their own dataset's table;
+  C4+ : the same check on 64 datasets x 1M rows, whose window tables (2.56 GB per copy) push the int64 table offsets
+        past 2^31;
+  C5  : a block of 128 envs INSIDE a 2^21-env shard against the oracle;
+  f4  : the `dataset_dir` glob -> read_pickle -> preprocess loader against the multi-dataset goldens recorded from the
+        reference's MultiDatasetTradingEnv (environments.py:365-400);
+  host: the "hybrid" path (gte_step_host: copy-engine and zero-copy mechanisms, int8 / int64 wire actions) and the
+        "numpy" path at 65 536 envs against the oracle.
+Bars: observations / indices / flags / fp64 portfolio state and valuation bit-exact, reward within 1e-12 (helpers.RTOL).
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+FEES = dict(trading_fees=0.01 / 100, borrow_interest_rate=0.0003 / 100, portfolio_initial_value=1000)
+
+
+def _acts(n, k, n_pos, device, seed=99):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    return torch.randint(0, n_pos, (k, n), generator=g, device=device, dtype=torch.int64)
+
+
+def _compare_block(env, o, lo, n_s, acts, K, what):
+    """Step `env` (all envs, device actions) and the oracle (envs lo..lo+n_s) K times; compare the block every step."""
+    obs, _ = env.reset()
+    H.assert_bits(obs[lo:lo + n_s].cpu().numpy(), o.reset(), f"{what} reset obs")
+    sl = slice(lo, lo + n_s)
+    c = lambda t: t[sl].cpu().numpy()   # noqa: E731
+    eps = 0
+    for k in range(K):
+        env.step(acts[k])
+        o.step(acts[k][sl].cpu().numpy())
+        w = f"{what} step {k}"
+        H.assert_bits(c(env._obs), o.obs, f"{w} obs")
+        H.assert_bits(c(env._terminated), o.terminated, f"{w} terminated")
+        H.assert_bits(c(env._truncated), o.truncated, f"{w} truncated")
+        H.assert_bits(c(env._info_idx), o.info_idx, f"{w} idx")
+        H.assert_bits(c(env._info_step), o.info_step, f"{w} step")
+        H.assert_bits(c(env._valuation), o.valuation, f"{w} valuation")
+        H.assert_bits(c(env._real_position), o.real_position, f"{w} real_position")
+        H.assert_close64(c(env._reward), o.reward, f"{w} reward")
+        for nm in ("asset", "fiat", "interest_asset", "interest_fiat"):
+            H.assert_bits(c(getattr(env, "_" + nm)), getattr(o, nm), f"{w} {nm}")
+        H.assert_bits(c(env._pos_idx), o.pos_idx, f"{w} pos_idx")
+        H.assert_bits(c(env._ep_start), o.ep_start, f"{w} ep_start")
+        H.assert_bits(c(env._step), o.step_, f"{w} step state")
+        H.assert_bits(c(env._dataset_idx), o.dataset_idx, f"{w} dataset")
+        eps += int(o.metrics[0])
+    env.check_errors()
+    return eps
+
+
+def _check_windows_against_tables(env, W, n_sample=32768):
+    """P1 across datasets: the static columns of a sample of ALL envs' windows are rows idx-W+1..idx of THEIR dataset."""
+    dev, N, ns = env.device, env.num_envs, env._n_static
+    sel = torch.arange(0, N, max(1, N // n_sample), device=dev)
+    idx = (env._ep_start + env._step).long()[sel]
+    ds = env._dataset_idx.long()[sel]
+    rows = idx[:, None] - (W - 1) + torch.arange(W, device=dev)[None, :]
+    want = env._features[ds[:, None], rows]                               # [n_s, W, ns]
+    got = env._obs[sel][:, :, :ns]
+    assert torch.equal(got.view(torch.int32), want.view(torch.int32)), "static window != rows of the env's dataset"
+    return ds
+
+
+def _multi_series(n_ds, rows):
+    import gym_trading_env_b200 as gte
+    out = []
+    for k in range(n_ds):
+        f, p = gte.make_gbm_arrays(rows, seed=k)
+        out.append(gte.SeriesArrays(f, p, [f"feature_{j}" for j in range(f.shape[1])], {}, None))
+    return out
+
+
+@pytest.mark.parametrize("n_ds,n_envs", [(32, 1 << 20), (64, 1 << 16)])
+def test_c4_full_size_tables_match_the_oracle(n_ds, n_envs):
+    """BASELINE config 4 at its full size (32 x 1M rows, 2^20 envs), and a 64 x 1M-row variant whose table offsets
+    exceed 2^31 bytes: oracle block + table-row property over all datasets, with resets and rotation."""
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    rows, W, lo, n_s, K = 1_000_000, 64, n_envs - 4096 - 160, 128, 44
+    series = _multi_series(n_ds, rows)
+    pos = [-1, 0, 0.5, 1]
+    kw = dict(positions=pos, windows=W, max_episode_duration=12, **FEES)
+    env = gte.MultiDatasetTradingVectorEnv(datasets=series, episodes_between_dataset_switch=1, num_envs=n_envs,
+                                           seed=5, verbose=0, debug_outputs=True, **kw)
+    assert env.obs_variant == "tma"
+    assert env._window_ds_stride * n_ds > (1 << 31) or n_ds == 32
+    feats = np.stack([s.features for s in series])
+    price = np.stack([s.price for s in series])
+    del series
+    o = orc.OracleVecEnv(feats, price, num_envs=n_s, seed=5, env_id_offset=lo, multi_dataset=True,
+                         episodes_between_dataset_switch=1, **kw)
+    acts = _acts(n_envs, K, len(pos), env.device)
+    eps = _compare_block(env, o, lo, n_s, acts, K, f"C4 {n_ds}x1M")
+    assert eps >= 3 * n_s                                               # every env restarted (and rotated) several times
+    ds = _check_windows_against_tables(env, W)
+    assert len(torch.unique(ds)) == n_ds                                # the sample really spans every dataset
+    used = torch.bincount(env._dataset_idx.long(), minlength=n_ds)
+    assert (used > 0).all() and used.max() < 2 * used.float().mean()    # least-used rotation keeps the spread even
+
+
+def test_c5_shard_block_matches_the_oracle():
+    """BASELINE config 5's per-GPU shard (2^21 envs, positions -3..3, windows=64, T=100 000): 128 envs inside the run
+    against the oracle stepping exactly those global env ids, with resets (D=25 so that episodes end inside the run)."""
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    n_envs, lo, n_s, K = 1 << 21, 1_234_560, 128, 60
+    series = gte.frame_to_arrays(gte.make_gbm_ohlcv(100_000, seed=0))
+    pos = [-3, -2, -1, 0, 1, 2, 3]
+    kw = dict(positions=pos, windows=64, max_episode_duration=25, **FEES)
+    env = gte.TradingVectorEnv(series, num_envs=n_envs, seed=11, verbose=0, debug_outputs=True, **kw)
+    o = orc.OracleVecEnv(series.features, series.price, num_envs=n_s, seed=11, env_id_offset=lo, **kw)
+    eps = _compare_block(env, o, lo, n_s, _acts(n_envs, K, len(pos), env.device), K, "C5 shard")
+    assert eps >= 2 * n_s
+
+
+@pytest.mark.parametrize("name", ["multi_dataset_k1", "multi_dataset_k3"])
+def test_dataset_dir_loader_matches_the_reference_goldens(name, tmp_path):
+    """MultiDatasetTradingEnv(dataset_dir, preprocess=...) (environments.py:365-400): glob -> sorted paths ->
+    read_pickle -> preprocess, on the very frames the goldens were recorded from (oracle/make_golden.py), written as
+    pickles WITHOUT their feature columns so that `preprocess` has to produce them, as in the reference's examples
+    (examples/example_multi_environnement.py)."""
+    import gym_trading_env_b200 as gte
+    g = H.load_golden(name)
+    p = g["params"]
+    lens = [300, 420, 360, 500]
+    assert list(g["lengths"]) == lens
+    for k, T in enumerate(lens):
+        df = gte.make_gbm_ohlcv(T, seed=20 + k)
+        raw = df.rename(columns={c: c.replace("feature_", "raw_") for c in df.columns})
+        assert not any("feature" in c for c in raw.columns)
+        raw.to_pickle(tmp_path / f"series_{k}.pkl")
+    (tmp_path / "notes.txt").write_text("not a dataset")
+
+    def preprocess(df):
+        return df.rename(columns={c: c.replace("raw_", "feature_") for c in df.columns})
+
+    kw = H.env_kwargs(g)
+    env = gte.MultiDatasetTradingVectorEnv(str(tmp_path / "*.pkl"), preprocess=preprocess,
+                                           episodes_between_dataset_switch=p["episodes_between_dataset_switch"],
+                                           num_envs=p["n_envs"], reset_plan=g["plan"], verbose=0, debug_outputs=True, **kw)
+    assert env.dataset_names == [f"series_{k}.pkl" for k in range(4)]
+    for k, T in enumerate(lens):                                         # staged arrays == what the reference staged
+        H.assert_bits(env._features[k, :T].cpu().numpy(), g["features"][k, :T], f"dataset {k} features")
+        H.assert_bits(env._price[k, :T].cpu().numpy(), g["price"][k, :T], f"dataset {k} price")
+    stats = H.replay_golden(H.DeviceAdapter(env), g, exact_money=True)
+    assert stats["episodes"] > 0
+    with pytest.raises(FileNotFoundError):
+        gte.MultiDatasetTradingVectorEnv(str(tmp_path / "*.parquet"), num_envs=2, **kw)
+
+
+@pytest.mark.parametrize("mode,dtype", [("copy", np.int8), ("copy", np.int64), ("mapped", np.int8), ("mapped", np.int64),
+                                        ("numpy", np.int16)])
+def test_host_paths_at_65536_envs_match_the_oracle(mode, dtype):
+    """C3 size through the host-facing paths: hybrid via gte_step_host with the copy engines and with mapped (zero-copy)
+    host memory, narrow and gymnasium-typed actions, and the full "numpy" mode — all against the oracle."""
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    from gym_trading_env_b200 import _cabi
+    N, K = 65_536, 36
+    series = gte.frame_to_arrays(gte.make_gbm_ohlcv(20_000, seed=2))
+    pos = [-1, 0, 0.5, 1]
+    kw = dict(positions=pos, windows=64, max_episode_duration=15, **FEES)
+    if mode == "numpy":
+        env = gte.TradingVectorEnv(series, num_envs=N, seed=3, verbose=0, output="numpy", **kw)
+    else:
+        env = gte.TradingVectorEnv(series, num_envs=N, seed=3, verbose=0, output="hybrid", host_io=mode, **kw)
+    o = orc.OracleVecEnv(series.features, series.price, num_envs=N, seed=3, threads=8, **kw)
+    obs, _ = env.reset()
+    H.assert_bits(obs if isinstance(obs, np.ndarray) else obs.cpu().numpy(), o.reset(), "reset obs")
+    rng = np.random.default_rng(7)
+    pin = env.pinned_actions(dtype)
+    assert pin.dtype == dtype
+    for k in range(K):
+        a = rng.integers(0, len(pos), size=N)
+        a[rng.random(N) < 0.05] = -1
+        if k % 3 == 2:
+            got = env.step(a.astype(dtype))                              # pageable array: staged
+        else:
+            pin[...] = a
+            got = env.step(pin)                                          # pinned: used in place
+        o.step(a)
+        obs_h = got[0] if isinstance(got[0], np.ndarray) else got[0].cpu().numpy()
+        assert isinstance(got[1], np.ndarray) and got[1].dtype == np.float64
+        assert got[2].dtype == np.bool_ and got[3].dtype == np.bool_
+        H.assert_bits(obs_h, o.obs, f"step {k} obs")
+        H.assert_close64(got[1], o.reward, f"step {k} reward")
+        H.assert_bits(got[2].view(np.uint8), o.terminated, f"step {k} terminated")
+        H.assert_bits(got[3].view(np.uint8), o.truncated, f"step {k} truncated")
+        H.assert_bits(env._valuation.cpu().numpy(), o.valuation, f"step {k} valuation")
+        H.assert_bits(env._asset.cpu().numpy(), o.asset, f"step {k} asset")
+        assert np.array_equal(np.asarray(env.infos["reward"]), got[1])
+    if mode != "numpy":
+        assert env._io_mode_used.value == _cabi.IO_MODES[mode]
+    assert float(env.get_metrics()["episodes"].item()) >= 2 * N
+    # a bad action surfaces as IndexError with the results of the very step that carried it
+    bad = np.zeros(N, dtype=dtype)
+    bad[N // 2] = len(pos)
+    with pytest.raises(IndexError):
+        env.step(bad)
+    env.step(np.zeros(N, dtype=dtype))                                   # the flag was cleared: the env keeps working
+
+
+def test_strict_actions_reject_negative_indices_other_than_hold():
+    """The reference's positions[-2] would index from the end of the list (environments.py:234); here every negative
+    action is a hold unless strict_actions=True, which raises for anything below -1."""
+    import gym_trading_env_b200 as gte
+    series = gte.frame_to_arrays(gte.make_gbm_ohlcv(2000, seed=1))
+    kw = dict(positions=[-1, 0, 1], windows=8, max_episode_duration=50, **FEES)
+    lax = gte.TradingVectorEnv(series, num_envs=64, seed=1, verbose=0, output="hybrid", **kw)
+    strict = gte.TradingVectorEnv(series, num_envs=64, seed=1, verbose=0, output="hybrid", strict_actions=True, **kw)
+    lax.reset(); strict.reset()
+    a = np.full(64, -1, np.int8)
+    r0, r1 = lax.step(a), strict.step(a)                                # -1 = hold in both
+    assert np.array_equal(r0[1], r1[1])
+    a[5] = -2
+    lax.step(a)                                                          # hold
+    with pytest.raises(IndexError):
+        strict.step(a)
+    dev = gte.TradingVectorEnv(series, num_envs=64, seed=1, verbose=0, strict_actions=True, **kw)
+    dev.reset()
+    dev.step(torch.full((64,), -3, dtype=torch.int64, device=dev.device))
+    with pytest.raises(IndexError):
+        dev.check_errors()
+
+
+def test_reset_plan_rows_are_range_checked_and_exhaustion_is_flagged():
+    """A plan row outside the dataset / position list is clamped and flagged instead of reading out of bounds, and a
+    plan that runs out of episodes is flagged instead of silently replaying (C-ABI hardening)."""
+    import gym_trading_env_b200 as gte
+    series = gte.frame_to_arrays(gte.make_gbm_ohlcv(600, seed=1))
+    kw = dict(positions=[0, 1], windows=4, max_episode_duration=10, **FEES)
+    plan = np.zeros((8, 2, 3), np.int32)
+    plan[:, :, 0] = 50
+    env = gte.TradingVectorEnv(series, num_envs=8, reset_plan=plan, verbose=0, **kw)
+    env.reset()
+    a = torch.zeros(8, dtype=torch.int64, device=env.device)
+    for _ in range(9):
+        env.step(a)                                                      # second plan episode consumed by the auto-reset
+    env.check_errors()
+    for _ in range(9):
+        env.step(a)                                                      # third episode: plan exhausted
+    with pytest.raises(RuntimeError):
+        env.check_errors()
+    bad = plan.copy()
+    bad[3, 0] = (10_000_000, 7, 0)                                       # start row and position index out of range
+    env2 = gte.TradingVectorEnv(series, num_envs=8, reset_plan=bad, verbose=0, **kw)
+    env2.reset()
+    with pytest.raises(ValueError):
+        env2.check_errors()
+    assert 0 <= int(env2._ep_start[3]) <= 598 and 0 <= int(env2._pos_idx[3]) <= 1
