@@ -118,28 +118,38 @@ class ClockSampler:
                 "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
-def cpu_port_rate(wl, n_sample, seconds, threads, seed=0):
-    """Time the scalar C oracle port on host cores: lockstep iterations over n_sample envs."""
+CPU_SAMPLE_ENVS = 2048
+CPU_SAMPLE_NOTE = ("the %d-env sample's state and observation batch are cache-resident on the host (5 MB of observations against "
+                   "2 MB of L2 per core), which flatters the CPU; each env keeps its own private dynamic-feature columns like the "
+                   "reference (1.6 GB, pre-faulted)" % CPU_SAMPLE_ENVS)
+
+
+def make_cpu_port(wl, n_sample, threads, seed=0):
+    """The scalar C port of the reference (oracle/gte_oracle.c) set up on a bounded sample of the workload."""
     import gym_trading_env_b200 as gte
     import oracle as orc
     series = make_series(dict(wl, n_datasets=1, rows=min(wl["rows"], 100_000)), gte)[0]
     env = orc.OracleVecEnv(series.features, series.price, num_envs=n_sample, positions=wl["positions"],
                            windows=wl["windows"], trading_fees=FEE, borrow_interest_rate=RATE,
                            portfolio_initial_value=V0, max_episode_duration=wl["duration"], seed=seed,
-                           threads=threads)
+                           threads=threads, dyn_mode=0)
+    env.prefault()
     env.reset()
     rng = np.random.default_rng(1234)
     acts = rng.integers(0, len(wl["positions"]), size=(16, n_sample))
-    env.rollout(acts, 20)
-    t0 = time.perf_counter()
-    env.rollout(acts, 20)
-    per_iter = max((time.perf_counter() - t0) / 20, 1e-7)
-    iters = int(max(20, min(200000, seconds / per_iter)))
-    t0 = time.perf_counter()
-    env.rollout(acts, iters)
-    dt = time.perf_counter() - t0
-    return n_sample * iters / dt, iters, dt
+    return env, acts
 
+
+def cpu_port_rate(wl, n_sample, seconds, threads, seed=0, repeats=5):
+    """env-steps/s of the C port on `threads` pinned host threads (pthreads created and timed inside C):
+    median of `repeats` equal slices of ~`seconds` of work, with the spread."""
+    env, acts = make_cpu_port(wl, n_sample, threads, seed)
+    env.rollout_timed(acts, 50)                                     # warm-up
+    per_iter = max(env.rollout_timed(acts, 50) / 50, 1e-7)
+    iters = int(max(50, min(200000, seconds / repeats / per_iter)))
+    rates = [n_sample * iters / env.rollout_timed(acts, iters) for _ in range(repeats)]
+    return {"value": statistics.median(rates), "min": min(rates), "max": max(rates), "repeats": repeats,
+            "iters_per_repeat": iters, "spread": (max(rates) - min(rates)) / statistics.median(rates)}
 
 
 # ---- the UNMODIFIED Python reference, when the driver-style install under baseline/_ref is present -------------
@@ -184,8 +194,10 @@ def python_reference_rate(wl, workload_name, seconds=6.0):
     if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "gym_trading_env")):
         return None
     cores = len(os.sched_getaffinity(0))
-    out = {"driver": "sync-style lockstep loop over reference TradingEnv objects (gymnasium is not installed: "
-                     "4-name stub from oracle/gymnasium_stub)", "envs_per_process": 8, "cores": cores}
+    out = {"driver": "shim: gymnasium is not installed, so its two vector drivers are re-created — 'one_core' = the sequential "
+                     "SyncVectorEnv loop over reference TradingEnv objects in one process, 'all_cores' = one such worker "
+                     "process per core (AsyncVectorEnv-style); the env code is the unmodified reference (4-name gymnasium "
+                     "stub from oracle/gymnasium_stub)", "envs_per_process": 8, "cores": cores}
 
     def run(n_proc):
         cmd = [sys.executable, os.path.abspath(__file__), "--workload", workload_name, "--pyref-worker", str(seconds)]
@@ -210,35 +222,30 @@ def python_reference_rate(wl, workload_name, seconds=6.0):
 
 
 def run_reference_arm(args, wl, rank):
-    """`--impl reference`: the reference algorithm's CPU port (oracle/gte_oracle.c, scalar C, faithful
-    per-env private dynamic-feature columns) on all host cores.  Rank 0 only."""
+    """`--impl reference`: the reference algorithm's CPU port (oracle/gte_oracle.c, scalar C, faithful per-env private
+    dynamic-feature columns) on all host cores — pinned pthreads created and timed inside C, the same driver and the
+    same sample the GPU arm's `cpu_baseline` leg uses.  Rank 0 only.  One bench "step" = `inner` lockstep iterations
+    of the sample; `value` follows the MEDIAN step time (min / max in `spread`)."""
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    n_sample = 2048
-    import gym_trading_env_b200 as gte
-    import oracle as orc
-    series = make_series(dict(wl, n_datasets=1, rows=min(wl["rows"], 100_000)), gte)[0]
-    env = orc.OracleVecEnv(series.features, series.price, num_envs=n_sample, positions=wl["positions"],
-                           windows=wl["windows"], trading_fees=FEE, borrow_interest_rate=RATE,
-                           portfolio_initial_value=V0, max_episode_duration=wl["duration"], seed=0, threads=cores)
-    env.reset()
-    rng = np.random.default_rng(1234)
-    acts = rng.integers(0, len(wl["positions"]), size=(16, n_sample))
+    n_sample = CPU_SAMPLE_ENVS
+    env, acts = make_cpu_port(wl, n_sample, cores)
     inner = 1000                                  # lockstep iterations per bench "step" (bounded sample, ~50 ms)
-    for _ in range(args.warmup):
-        env.rollout(acts, inner)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        env.rollout(acts, inner)
-    dt = time.perf_counter() - t0
-    value = n_sample * inner * args.steps / dt
-    sample = f"{n_sample} envs x {inner} lockstep iterations per step, {cores} host threads, scalar C port of the reference"
+    for _ in range(max(args.warmup, 3)):
+        env.rollout_timed(acts, inner)
+    times = [env.rollout_timed(acts, inner) for _ in range(args.steps)]
+    med = statistics.median(times)
+    value = n_sample * inner / med
+    sample = (f"{n_sample} envs x {inner} lockstep iterations per step, {cores} pinned host threads (pthreads inside C), "
+              f"scalar C port of the reference; {CPU_SAMPLE_NOTE}")
+    spread = {"min": n_sample * inner / max(times), "max": n_sample * inner / min(times),
+              "rel": (max(times) - min(times)) / med, "steps": len(times)}
     _emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * med,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["label"], "sample": sample},
+        "config": {"workload": wl["label"], "sample": sample}, "spread": spread,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "python_reference": python_reference_rate(wl, args.workload)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -332,6 +339,7 @@ def main():
     gen.manual_seed(1234 + rank)
     actions = torch.randint(0, len(wl["positions"]), (n_sets, N), generator=gen, device=dev, dtype=torch.int64)
     env.reset()
+    launches_per_step = env.launches_per_step
 
     if world > 1:
         # C5: NCCL all-reduce(sum) of the 8 fp64 episode metrics EVERY iteration, issued by the env between its two
@@ -356,7 +364,8 @@ def main():
     # per-kernel CUDA events INSIDE the timed region: on every 4th (8th) iteration env.step() issues its two kernels
     # as two calls (the very kernels gte_step_obs launches) with events on the launching stream around each; the
     # event records cost ~3 us per iteration they bracket, hence not every iteration
-    env._kernel_events = [] if wl["windows"] is not None else None
+    fused = wl["windows"] is not None and env.launches_per_step == 1      # transition + gather in ONE launch (small batches)
+    env._kernel_events = [] if (wl["windows"] is not None and not fused) else None
     env._kernel_events_every = 1 if args.steps < 64 else (4 if wl["envs"] >= 2 ** 20 else 8)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -414,6 +423,8 @@ def main():
     kname = {"tma": "obs_tma_coop_kernel", "vec": "obs_vec_kernel", "generic": "obs_generic_kernel"}[env.obs_variant]
     if wl["windows"] is None:
         kname = "step_kernel (windows=None: writes the one-row observation itself)"
+    elif fused:
+        kname += "<fused> (ONE launch per iteration: every CTA advances its envs, then gathers their windows; timed as a whole)"
     elif not split:
         kname = "step_kernel + " + kname + " (graph replay: timed together)"
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
@@ -511,12 +522,14 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = len(os.sched_getaffinity(0))
-        n_sample = 2048
-        v_all, iters, dt = cpu_port_rate(wl, n_sample, args.cpu_seconds, cores)
-        v_one, _, _ = cpu_port_rate(wl, 256, 3.0, 1)
-        cpu = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n_sample} envs x {iters} lockstep iterations ({dt:.1f} s), same dataset/config, "
-                         f"oracle/gte_oracle.c on {cores} threads", "single_core_value": v_one,
+        n_sample = CPU_SAMPLE_ENVS
+        r_all = cpu_port_rate(wl, n_sample, args.cpu_seconds, cores)
+        r_one = cpu_port_rate(wl, 256, 3.0, 1, repeats=3)
+        cpu = {"value": r_all["value"], "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_sample} envs x {r_all['iters_per_repeat']} lockstep iterations, median of {r_all['repeats']} "
+                         f"repeats, same dataset/config, oracle/gte_oracle.c on {cores} pinned threads (pthreads inside C); "
+                         + CPU_SAMPLE_NOTE,
+               "spread": {k: r_all[k] for k in ("min", "max", "spread")}, "single_core_value": r_one["value"],
                "python_reference": python_reference_rate(wl, args.workload)}
 
     if rank == 0:
@@ -531,7 +544,7 @@ def main():
                        "host_bind": host_bind},
             "clocks": clocks, "e2e": e2e, "e2e_gymnasium_dtypes": e2e_i64, "e2e_other_host_io": e2e_mapped,
             "e2e_full_obs_to_host": e2e_full,
-            "gpu_launches": (1 if wl["windows"] is None else 2 * env.chunks) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu,
         }
         if latency is not None:
             out["latency"] = latency

@@ -105,7 +105,8 @@ class GteInfo(C.Structure):
 
 
 EXPORTS = ["gte_version", "gte_last_error", "gte_build_id", "gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs",
-           "gte_step_host", "gte_rollout", "gte_info", "gte_obs_variant_for", "gte_default_chunks", "gte_struct_size"]
+           "gte_step_host", "gte_rollout", "gte_info", "gte_obs_variant_for", "gte_default_chunks", "gte_struct_size",
+           "gte_step_obs_launches"]
 
 
 def source_hash() -> str:
@@ -186,6 +187,8 @@ def load():
                                 C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.gte_info.argtypes = [P(GteParams), P(GteData), P(GteState), P(GteInfo), C.c_void_p]
     lib.gte_obs_variant_for.argtypes = [P(GteParams), P(GteData)]
+    lib.gte_step_obs_launches.argtypes = [P(GteParams), P(GteData), C.c_int, C.c_int]
+    lib.gte_step_obs_launches.restype = C.c_int
     lib.gte_default_chunks.argtypes = [C.c_int]
     lib.gte_default_chunks.restype = C.c_int
     for name in ("gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs", "gte_step_host", "gte_rollout", "gte_info",

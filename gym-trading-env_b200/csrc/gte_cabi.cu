@@ -178,6 +178,13 @@ int gte_struct_size(int which) {
     }
 }
 
+int gte_step_obs_launches(const GteParams* params, const GteData* data, int variant, int n_chunks) {
+    if (params == nullptr || data == nullptr || n_chunks < 0 || n_chunks > 16) return GTE_ERR_ARG;
+    if (params->windows == 0) return 1;
+    if (n_chunks == 0 && gte::default_chunks(params->n_envs) == 1 && gte::step_obs_is_fused(*params, *data, variant)) return 1;
+    return 2 * (n_chunks == 0 ? gte::default_chunks(params->n_envs) : n_chunks);
+}
+
 int gte_default_chunks(int n_envs) { return n_envs > 0 ? gte::default_chunks(n_envs) : GTE_ERR_ARG; }
 
 int gte_obs_variant_for(const GteParams* params, const GteData* data) {

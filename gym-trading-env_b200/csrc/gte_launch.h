@@ -44,6 +44,12 @@ bool obs_vec_supported(const GteParams& P, const GteData& D);
 bool obs_tma_supported(const GteParams& P, const GteData& D);
 cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteState& S, float* obs, int variant,
                              int env_begin, int env_end, cudaStream_t stream);
+struct StepConsts;
+StepConsts make_step_consts(const GteParams& P);
+cudaError_t launch_fused_step_obs(const GteParams& P, const GteData& D, const GteState& S, const void* actions,
+                                  const StepConsts& K, const GteStepOut& O, float* obs, int autoreset, int variant,
+                                  cudaStream_t stream, bool* done);
+bool step_obs_is_fused(const GteParams& P, const GteData& D, int variant);
 int default_chunks(int n_envs);
 int host_io_mode(const GteParams& P, int mode);
 cudaError_t launch_step_obs(const GteParams& P, const GteData& D, const GteState& S, const void* actions,

@@ -13,6 +13,7 @@
 #include <cstdlib>
 
 #include "gte_tma.cuh"
+#include "gte_step_env.cuh"
 #include "gte_launch.h"
 
 namespace gte {
@@ -148,10 +149,23 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // saturating write stream) and only need the tile index, the windows come from L2 and need the envs'
 // metadata: ring tiles are requested a whole tile ahead, the big window buffers are only held for an L2
 // round trip + patch + store drain.
-template <int WS, int RT, int G, int UNIT = kTileEnvs>
-__global__ void __launch_bounds__(kCoopThreads)
+// FUSED (single-wave grids only, gte_step_obs): the CTA first advances ITS OWN envs by one transition — every thread one
+// env, the very step_env() of the step kernel — keeps each env's window address / first live row in shared memory,
+// takes part in the metric fold, and then runs the gather pipeline below on those envs.  One launch per lockstep
+// iteration and no grid-wide dependency between the transition and the gather: at 65 536 envs the two-launch form pays
+// the step kernel's tail (metric fold, drain) plus the gather's ramp between two latency-bound kernels.
+constexpr int kFusedMaxEnvs = 256;         // envs one CTA may own in the fused form (metadata kept in shared memory)
+struct FusedStep {
+    const void* actions;
+    StepConsts K;
+    GteStepOut O;
+    int autoreset;
+};
+
+template <int WS, int RT, int G, int UNIT = kTileEnvs, bool FUSED = false>
+__global__ void __launch_bounds__(kCoopThreads, FUSED ? 4 : 1)
 obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float* __restrict__ obs,
-                    const ObsShape sh, const int env_begin, const int env_end) {
+                    const ObsShape sh, const int env_begin, const int env_end, const FusedStep FS) {
     static_assert(RT >= 2, "a ring tile is requested while the previous one is being consumed");
     static_assert(UNIT % G == 0 && kTileEnvs % UNIT == 0, "a work unit is a whole number of groups inside one ring block");
     // work unit ("tile") = UNIT consecutive envs inside one 32-env ring block: 32 normally, 16 or 8 when the batch
@@ -166,6 +180,9 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_w[WS], ready_w[WS], empty_w[WS], full_r[RT], empty_r[RT];
     __shared__ int first_live[2][kTileEnvs];                     // per tile parity: first window row of the episode
+    __shared__ unsigned long long f_src[FUSED ? kFusedMaxEnvs : 1];   // FUSED: window address / first live row of every
+    __shared__ int f_live[FUSED ? kFusedMaxEnvs : 1];                 //        env this CTA owns, written by its step phase
+    __shared__ double f_pos[FUSED ? GTE_MAX_POSITIONS : 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool ring = sh.nd > 0;
     const uint32_t win_bytes = (uint32_t)sh.win_bytes;
@@ -182,11 +199,35 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
         for (int s = 0; s < RT; ++s) { mbar_init(&full_r[s], 1); mbar_init(&empty_r[s], kCoopConsumerWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (FUSED && tid < GTE_MAX_POSITIONS) f_pos[tid] = P.positions[tid];
     __syncthreads();
-    pdl_wait();                              // state / ring / clock below were written by the step kernel before us
+    pdl_wait();                              // state / ring / clock below were written by the kernel before us
 
     // tile k of this CTA = unit_envs consecutive envs, tiles strided over the grid; group gi of it = G envs
     auto tile_env0 = [&](int k) -> int64_t { return env_begin + ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * unit_envs; };
+    // ring slot of window row 0 AFTER this iteration's transition.  Two launches: the step kernel has advanced the clock.
+    // FUSED: the clock is advanced by the last CTA of THIS launch, after every CTA has read it here.
+    int s0 = 0;
+    if (FUSED) {
+        const uint64_t tick = *S.tick, clock = *S.ring_clock;
+        const int ring_slot = ring_slot_of(P, clock + 1ull);
+        s0 = (int)((clock + 2ull) % (uint64_t)sh.W);
+        MetricAcc acc;
+        for (int j = tid; j < kFusedMaxEnvs; j += kCoopThreads) {          // (the launcher guarantees the CTA owns <= 256 envs)
+            const int64_t env = tile_env0(j / unit_envs) + (j % unit_envs);
+            if (env < env_end) {
+                const StepThreadOut r = step_env(P, D, S, FS.actions, FS.K, FS.O, tick, ring_slot, FS.autoreset, (int)env, acc, f_pos);
+                f_live[j] = sh.W - 1 - (r.idx - r.ep_start);             // window row of ep_start (<= 0: the whole window is live)
+                f_src[j] = (unsigned long long)window_src(D, sh, r.ds, r.idx + 1 - sh.W);
+            }
+        }
+        // the ring entries just stored are read back below by the TMA unit (async proxy): order them across the proxies
+        asm volatile("fence.proxy.async;" ::: "memory");
+        reduce_metrics<kCoopThreads>(acc, FS.O, S, kChunkFirst | kChunkLast);   // ends with / contains CTA-wide barriers
+        __syncthreads();
+    } else if (sh.nd > 0) {
+        s0 = (int)((*S.ring_clock + 1ull) % (uint64_t)sh.W);
+    }
     auto group_env0 = [&](int k, int gi) -> int64_t { return tile_env0(k) + gi * G; };
     auto group_valid = [&](int k, int gi) -> int {               // envs of the group inside [env_begin, env_end)
         const int64_t left = (int64_t)env_end - group_env0(k, gi);
@@ -200,7 +241,10 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
             TilePre p;
             p.src = 0ull; p.first_live = 0;
             const int64_t env = tile_env0(k) + lane;
-            if (lane < unit_envs && env < env_end) {
+            if (FUSED) {
+                const int j = k * unit_envs + lane;
+                if (lane < unit_envs && env < env_end && j < kFusedMaxEnvs) { p.src = f_src[j]; p.first_live = f_live[j]; }
+            } else if (lane < unit_envs && env < env_end) {
                 // per-env state is WRITTEN by the step kernel this grid may overlap with (programmatic dependent launch): never
                 // through the non-coherent path (ld.global.nc is only defined for data that is read-only for the whole kernel)
                 const int ep = __ldcg(S.ep_start + env), st = __ldcg(S.step + env), ds = __ldcg(S.dataset_idx + env);
@@ -272,7 +316,6 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
         // the swizzled real_position row, lanes of different slots hit different chunks (banks).  The warps never
         // meet: each one signals the store warp (and, after a tile's last group, the producer) on its own.
         const int g = tid % G, t = tid / G;
-        const int s0 = ring ? (int)((*S.ring_clock + 1ull) % (uint64_t)sh.W) : 0;      // ring slot of window row 0
         int q = 0;
         for (int k = 0; tile_env0(k) < env_end; ++k) {
             const int rs = k % RT;
@@ -311,7 +354,7 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
     }
 }
 
-using ObsKernelFn = void (*)(const GteParams, const GteData, const GteState, float*, const ObsShape, int, int);
+using ObsKernelFn = void (*)(const GteParams, const GteData, const GteState, float*, const ObsShape, int, int, const FusedStep);
 
 struct TmaConfig { int wstages, rtiles, group; };
 
@@ -320,10 +363,26 @@ static size_t tma_smem_bytes(const ObsShape& sh, const TmaConfig& c) {
     return (size_t)c.group * c.wstages * sh.win_bytes + ring;
 }
 
-static ObsKernelFn tma_kernel(const TmaConfig& c, int unit = kTileEnvs) {
-    // (window stages, ring-tile stages, envs per group) combinations compiled in; smaller work units for the default shapes
+static ObsKernelFn tma_kernel(const TmaConfig& c, int unit = kTileEnvs, bool fused = false) {
+    // (window stages, ring-tile stages, envs per group) combinations compiled in; smaller work units and the fused
+    // step+gather form for the default shapes
+    const int key = c.wstages * 10000 + c.rtiles * 100 + c.group;
+    if (fused) {
+        switch (unit * 100000 + key) {
+            case 3230201: return obs_tma_coop_kernel<3, 2, 1, 32, true>;
+            case 3230202: return obs_tma_coop_kernel<3, 2, 2, 32, true>;
+            case 3230204: return obs_tma_coop_kernel<3, 2, 4, 32, true>;
+            case 1630201: return obs_tma_coop_kernel<3, 2, 1, 16, true>;
+            case 1630202: return obs_tma_coop_kernel<3, 2, 2, 16, true>;
+            case 1630204: return obs_tma_coop_kernel<3, 2, 4, 16, true>;
+            case 830201: return obs_tma_coop_kernel<3, 2, 1, 8, true>;
+            case 830202: return obs_tma_coop_kernel<3, 2, 2, 8, true>;
+            case 830204: return obs_tma_coop_kernel<3, 2, 4, 8, true>;
+            default: return nullptr;
+        }
+    }
     if (unit == 16) {
-        switch (c.wstages * 10000 + c.rtiles * 100 + c.group) {
+        switch (key) {
             case 30201: return obs_tma_coop_kernel<3, 2, 1, 16>;
             case 30202: return obs_tma_coop_kernel<3, 2, 2, 16>;
             case 30204: return obs_tma_coop_kernel<3, 2, 4, 16>;
@@ -331,14 +390,14 @@ static ObsKernelFn tma_kernel(const TmaConfig& c, int unit = kTileEnvs) {
         }
     }
     if (unit == 8) {
-        switch (c.wstages * 10000 + c.rtiles * 100 + c.group) {
+        switch (key) {
             case 30201: return obs_tma_coop_kernel<3, 2, 1, 8>;
             case 30202: return obs_tma_coop_kernel<3, 2, 2, 8>;
             case 30204: return obs_tma_coop_kernel<3, 2, 4, 8>;
             default: return nullptr;
         }
     }
-    switch (c.wstages * 10000 + c.rtiles * 100 + c.group) {
+    switch (key) {
         case 30201: return obs_tma_coop_kernel<3, 2, 1>;
         case 30202: return obs_tma_coop_kernel<3, 2, 2>;
         case 30204: return obs_tma_coop_kernel<3, 2, 4>;
@@ -388,6 +447,103 @@ bool obs_tma_supported(const GteParams& P, const GteData& D) {
     return (sh.nd == 0 || sh.nd == 2) && tma_smem_bytes(sh, tma_config(sh)) <= 200 * 1024;
 }
 
+// Grid / work-unit choice of the TMA gather for n_envs envs (and the one-time per-device kernel attribute opt-ins).
+struct TmaPlan {
+    ObsKernelFn kern;
+    int grid, unit, envs_per_cta;
+    size_t smem;
+};
+
+static cudaError_t plan_tma(const ObsShape& sh, int n_envs, bool fused, TmaPlan* out) {
+    const TmaConfig cfg = tma_config(sh);
+    const size_t smem = tma_smem_bytes(sh, cfg);
+    ObsKernelFn probe = tma_kernel(cfg, kTileEnvs, fused);
+    if (probe == nullptr) return cudaErrorInvalidValue;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    // opt-in to > 48 KB dynamic smem once per kernel AND device (the attribute is per device), and how many CTAs of the
+    // kernel an SM holds (registers, static + dynamic shared memory), asked of the runtime once
+    struct Slot { ObsKernelFn kern; size_t smem; int per_sm; };
+    static Slot slots[16][24] = {};
+    auto configure = [&](ObsKernelFn k, int* per_sm) -> cudaError_t {
+        Slot* sl = slots[dev & 15];
+        int i = 0;
+        while (i < 23 && sl[i].kern != nullptr && sl[i].kern != k) ++i;
+        if (sl[i].kern != k || smem > sl[i].smem) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            int n = 0;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, kCoopThreads, smem)) != cudaSuccess) return e;
+            sl[i].kern = k; sl[i].smem = smem; sl[i].per_sm = n < 1 ? 1 : n;
+        }
+        *per_sm = sl[i].per_sm;
+        return cudaSuccess;
+    };
+    int per_sm = 1;
+    cudaError_t e = configure(probe, &per_sm);
+    if (e != cudaSuccess) return e;
+    // work unit = one 32-env tile, or half / a quarter of one when that spreads a small batch more evenly (the time
+    // of the launch follows the units of the busiest CTA x the unit size); persistent grid of <= SMs x per_sm CTAs,
+    // sized so that every CTA gets the same number of units (no straggler wave at mid-size N)
+    const int64_t cap = (int64_t)num_sms() * per_sm;
+    int unit = 32;
+    int64_t best = -1;
+    for (int u = 32; u >= 8 && u >= cfg.group; u /= 2) {
+        if (tma_kernel(cfg, u, fused) == nullptr) continue;
+        const int64_t units = ((int64_t)n_envs + u - 1) / u;
+        const int64_t per_cta = (units + cap - 1) / cap;
+        if (u == 8 && per_cta > 1) break;                  // quarter tiles only while every CTA gets at most one
+        if (best < 0 || per_cta * u < best) { best = per_cta * u; unit = u; }
+    }
+    const int64_t need = ((int64_t)n_envs + unit - 1) / unit;
+    const int64_t waves = (need + cap - 1) / cap;
+    out->grid = (int)((need + waves - 1) / waves);
+    out->unit = unit;
+    out->envs_per_cta = (int)(((need + out->grid - 1) / out->grid) * unit);
+    out->smem = smem;
+    out->kern = tma_kernel(cfg, unit, fused);
+    int unused = 0;
+    return out->kern == probe ? cudaSuccess : configure(out->kern, &unused);
+}
+
+// Whether gte_step_obs runs this shape as ONE fused launch: the batch must be small enough for every CTA of the
+// single-wave grid to own at most kFusedMaxEnvs envs.  *plan is filled when it does.
+static cudaError_t fused_plan(const GteParams& P, const GteData& D, int variant, TmaPlan* plan, bool* eligible) {
+    static const bool enabled = [] { const char* e = getenv("GTE_FUSED"); return e == nullptr || atoi(e) != 0; }();
+    *eligible = false;
+    if (!enabled || P.windows <= 0 || (variant != GTE_OBS_AUTO && variant != GTE_OBS_TMA) || !obs_tma_supported(P, D))
+        return cudaSuccess;
+    const ObsShape sh = make_shape(P);
+    if (tma_kernel(tma_config(sh), kTileEnvs, true) == nullptr) return cudaSuccess;
+    // cheap pre-check before touching kernel attributes: even 8 CTAs per SM could not keep every CTA under the limit
+    if ((int64_t)P.n_envs > (int64_t)num_sms() * 8 * kFusedMaxEnvs) return cudaSuccess;
+    cudaError_t e = plan_tma(sh, P.n_envs, true, plan);
+    if (e != cudaSuccess) return e;
+    *eligible = plan->envs_per_cta <= kFusedMaxEnvs && plan->grid <= kMaxPartialRows;
+    return cudaSuccess;
+}
+
+bool step_obs_is_fused(const GteParams& P, const GteData& D, int variant) {
+    TmaPlan plan;
+    bool ok = false;
+    return fused_plan(P, D, variant, &plan, &ok) == cudaSuccess && ok;
+}
+
+// One lockstep iteration as ONE launch (transition + gather fused, see obs_tma_coop_kernel); *done = false -> the
+// caller issues the two plain launches.
+cudaError_t launch_fused_step_obs(const GteParams& P, const GteData& D, const GteState& S, const void* actions,
+                                  const StepConsts& K, const GteStepOut& O, float* obs, int autoreset, int variant,
+                                  cudaStream_t stream, bool* done) {
+    TmaPlan plan;
+    *done = false;
+    cudaError_t e = fused_plan(P, D, variant, &plan, done);
+    if (e != cudaSuccess || !*done) return e;
+    FusedStep fs;
+    fs.actions = actions; fs.K = K; fs.O = O; fs.autoreset = autoreset;
+    return launch_pdl(plan.kern, dim3(plan.grid), dim3(kCoopThreads), plan.smem, stream, P, D, S, obs, make_shape(P), 0,
+                      P.n_envs, fs);
+}
+
 cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteState& S, float* obs, int variant,
                              int env_begin, int env_end, cudaStream_t stream) {
     const ObsShape sh = make_shape(P);
@@ -422,47 +578,11 @@ cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteStat
     }
     if (variant == GTE_OBS_TMA) {
         if (!obs_tma_supported(P, D)) return cudaErrorInvalidValue;
-        const TmaConfig cfg = tma_config(sh);
-        const size_t smem = tma_smem_bytes(sh, cfg);
-        if (tma_kernel(cfg) == nullptr) return cudaErrorInvalidValue;
-        const int threads = kCoopThreads;
-        int per_sm = (int)((227 * 1024) / (smem + 2048));
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > 2048 / threads) per_sm = 2048 / threads;
-        if (per_sm > 32) per_sm = 32;
-        // work unit = one 32-env tile, or half / a quarter of one when that spreads a small batch more evenly (the time
-        // of the launch follows the units of the busiest CTA x the unit size); persistent grid of <= SMs x per_sm CTAs,
-        // sized so that every CTA gets the same number of units (no straggler wave at mid-size N)
-        const int64_t cap = (int64_t)sms * per_sm;
-        int unit = 32;
-        int64_t best = -1;
-        for (int u = 32; u >= 8 && u >= cfg.group; u /= 2) {
-            if (tma_kernel(cfg, u) == nullptr) continue;
-            const int64_t units = ((int64_t)n_envs + u - 1) / u;
-            const int64_t per_cta = (units + cap - 1) / cap;
-            if (u == 8 && per_cta > 1) break;                  // quarter tiles only while every CTA gets at most one
-            if (best < 0 || per_cta * u < best) { best = per_cta * u; unit = u; }
-        }
-        const int64_t need = ((int64_t)n_envs + unit - 1) / unit;
-        const int64_t waves = (need + cap - 1) / cap;
-        const int grid = (int)((need + waves - 1) / waves);
-        ObsKernelFn kern = tma_kernel(cfg, unit);
-        // opt-in to > 48 KB dynamic smem once per kernel AND device (the attribute is per device)
-        static ObsKernelFn configured_kern[16][8] = {};
-        static size_t configured_smem[16][8] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        ObsKernelFn* ck = configured_kern[dev & 15];
-        size_t* cs = configured_smem[dev & 15];
-        int slot = 0;
-        while (slot < 7 && ck[slot] != nullptr && ck[slot] != kern) ++slot;
-        if (ck[slot] != kern || smem > cs[slot]) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            ck[slot] = kern;
-            cs[slot] = smem;
-        }
-        return launch_pdl(kern, dim3(grid), dim3(threads), smem, stream, P, D, S, obs, sh, env_begin, env_end);
+        TmaPlan plan;
+        cudaError_t e = plan_tma(sh, n_envs, false, &plan);
+        if (e != cudaSuccess) return e;
+        return launch_pdl(plan.kern, dim3(plan.grid), dim3(kCoopThreads), plan.smem, stream, P, D, S, obs, sh, env_begin, env_end,
+                          FusedStep{});
     }
     return cudaErrorInvalidValue;
 }

@@ -46,7 +46,7 @@ step_kernel(const GteParams P, const GteData D, const GteState S, const void* __
             }
         }
     }
-    reduce_metrics(acc, O, S, chunk_flags);
+    reduce_metrics<kStepThreads>(acc, O, S, chunk_flags);
 }
 
 // TradingEnv.reset for the masked envs (environments.py:163-199, :393-400); `first` also performs
@@ -260,12 +260,16 @@ int default_chunks(int n_envs) {
 cudaError_t launch_step_obs(const GteParams& P, const GteData& D, const GteState& S, const void* actions,
                             const GteStepOut& O, float* obs, int autoreset, int variant, int n_chunks,
                             cudaStream_t stream) {
+    const bool may_fuse = n_chunks <= 0;     // an explicit n_chunks (1 = two plain launches) is honoured as given
     if (n_chunks <= 0) n_chunks = default_chunks(P.n_envs);
     if (n_chunks > 16) n_chunks = 16;
     cudaError_t e;
     if (P.windows == 0)            // windows=None: the step kernel writes the one-row observation itself
         return launch_step_range(P, D, S, actions, O, autoreset, 0, P.n_envs, kChunkFirst | kChunkLast, stream, obs);
     if (n_chunks == 1) {
+        bool fused = false;                  // small batches: transition + gather in ONE launch
+        if (may_fuse && (e = launch_fused_step_obs(P, D, S, actions, make_step_consts(P), O, obs, autoreset, variant, stream, &fused)) != cudaSuccess || fused)
+            return e;
         if ((e = launch_step(P, D, S, actions, O, autoreset, stream)) != cudaSuccess) return e;
         return launch_obs_range(P, D, S, obs, variant, 0, P.n_envs, stream);
     }
@@ -308,8 +312,12 @@ cudaError_t launch_rollout(const GteParams& P, const GteData& D, const GteState&
             e = launch_step_range(P, D, S, a, o, autoreset, 0, P.n_envs, kChunkFirst | kChunkLast, stream,
                                   want_obs ? obs_k : nullptr);
         } else {
-            e = launch_step(P, D, S, a, o, autoreset, stream);
-            if (e == cudaSuccess && want_obs) e = launch_obs_range(P, D, S, obs_k, variant, 0, P.n_envs, stream);
+            bool fused = false;
+            if (want_obs) e = launch_fused_step_obs(P, D, S, a, make_step_consts(P), o, obs_k, autoreset, variant, stream, &fused);
+            if (!fused) {
+                e = launch_step(P, D, S, a, o, autoreset, stream);
+                if (e == cudaSuccess && want_obs) e = launch_obs_range(P, D, S, obs_k, variant, 0, P.n_envs, stream);
+            }
         }
         if (e != cudaSuccess) return e;
     }
@@ -340,9 +348,12 @@ static cudaError_t hio_for_current_device(HostIOStreams** out) {
 }
 
 int host_io_mode(const GteParams& P, int mode) {
-    static const long long mapped_max = [] { const char* e = getenv("GTE_IO_MAPPED_MAX_BYTES"); return e ? atoll(e) : (1ll << 20); }();
+    // measured on B200 (tools/host_path_probe.py, profiles/r02_tuning.md): with a gather behind the step kernel the
+    // mapped writes delay it, so the copy engines win from ~40k envs on; without one mapped wins up to >= 64k envs
+    static const long long forced_max = [] { const char* e = getenv("GTE_IO_MAPPED_MAX_BYTES"); return e ? atoll(e) : -1ll; }();
     if (mode == GTE_IO_COPY || mode == GTE_IO_MAPPED) return mode;
     const int ab = P.action_bytes == 0 ? 8 : P.action_bytes;
+    const long long mapped_max = forced_max >= 0 ? forced_max : (P.windows > 0 ? 384ll << 10 : 1ll << 20);
     return (int64_t)P.n_envs * (ab + 10) <= mapped_max ? GTE_IO_MAPPED : GTE_IO_COPY;
 }
 

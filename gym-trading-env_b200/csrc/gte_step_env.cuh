@@ -160,10 +160,13 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // CTA-level metric reduction -> metric_partials[blockIdx.x]; the last CTA to arrive folds all
-// partial rows in a fixed order (deterministic) into metrics_step / metrics_total.
+// partial rows in a fixed order (deterministic) into metrics_step / metrics_total.  NT = threads of the CTA, all of
+// which must call it (step kernel: 256; fused step+gather kernel: 192).
+template <int NT>
 static __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O, const GteState& S, int chunk_flags) {
-    __shared__ double s_part[kStepThreads / 32][GTE_N_METRICS];
-    __shared__ double s_fold[32][GTE_N_METRICS];
+    constexpr int NW = NT / 32, NG = NT / GTE_N_METRICS;
+    __shared__ double s_part[NW][GTE_N_METRICS];
+    __shared__ double s_fold[NG][GTE_N_METRICS];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -194,7 +197,7 @@ static __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O,
     if (threadIdx.x < GTE_N_METRICS) {
         double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < kStepThreads / 32; ++w) t = dadd(t, s_part[w][threadIdx.x]);
+        for (int w = 0; w < NW; ++w) t = dadd(t, s_part[w][threadIdx.x]);
         O.metric_partials[(int64_t)blockIdx.x * GTE_N_METRICS + threadIdx.x] = t;
         __threadfence();
     }
@@ -203,15 +206,15 @@ static __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O,
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const int m = threadIdx.x % GTE_N_METRICS, g = threadIdx.x / GTE_N_METRICS;   // 32 groups x 8 metrics
+    const int m = threadIdx.x % GTE_N_METRICS, g = threadIdx.x / GTE_N_METRICS;   // NG groups x 8 metrics
     double t = 0.0;
-    for (int b = g; b < (int)gridDim.x; b += kStepThreads / GTE_N_METRICS)
+    for (int b = g; b < (int)gridDim.x; b += NG)
         t = dadd(t, __ldcg(O.metric_partials + (int64_t)b * GTE_N_METRICS + m));
     s_fold[g][m] = t;
     __syncthreads();
     if (threadIdx.x < GTE_N_METRICS) {
         double tot = 0.0;
-        for (int k = 0; k < kStepThreads / GTE_N_METRICS; ++k) tot = dadd(tot, s_fold[k][threadIdx.x]);
+        for (int k = 0; k < NG; ++k) tot = dadd(tot, s_fold[k][threadIdx.x]);
         // env chunks of one lockstep iteration run as consecutive launches: the first one overwrites
         // metrics_step, later ones add to it in launch order (deterministic)
         O.metrics_step[threadIdx.x] = (chunk_flags & kChunkFirst) ? tot : dadd(O.metrics_step[threadIdx.x], tot);

@@ -88,11 +88,16 @@ def _fn_name(f):
     return getattr(f, "__name__", None)
 
 
-# ---- spaces: gymnasium's when importable, else shape/dtype stand-ins --------------------------------
-try:  # pragma: no cover - gymnasium is absent from the build image
+# ---- gymnasium's VectorEnv base class and spaces when importable, else duck-typed stand-ins ---------
+# ("inherit from gymnasium.vector.VectorEnv only if importable"; gymnasium is absent from the build image)
+try:
+    import gymnasium as _gym
     from gymnasium import spaces as _spaces
+    _VectorEnvBase = _gym.vector.VectorEnv
     _Discrete, _Box, _MultiDiscrete = _spaces.Discrete, _spaces.Box, _spaces.MultiDiscrete
 except Exception:  # noqa: BLE001
+    _gym, _VectorEnvBase = None, object
+
     class _Discrete:
         def __init__(self, n):
             self.n, self.shape, self.dtype = int(n), (), np.dtype(np.int64)
@@ -125,23 +130,43 @@ def shard_envs(total_envs: int, rank: int, world_size: int):
 
 
 class LazyInfos(Mapping):
-    """History's last row (environments.py:253-264) as a dict of [N] device tensors, computed by
-    one `gte_info` launch on first access after each step/reset."""
+    """History's last row (environments.py:186-197 after a reset, :253-264 after a step) for every env, as a dict of
+    [N] columns computed on first access after each step/reset (one `gte_info` launch; the ``data_*`` columns and
+    ``date`` are looked up from the staged frames).  Same keys as the reference's info dict: ``idx, step, date,
+    position_index, position, real_position, data_<every numeric non-feature column>, portfolio_valuation,
+    portfolio_distribution_*, reward`` — plus ``dataset_idx`` and ``episode_metrics``.  Values are CUDA tensors, except
+    ``date`` (numpy datetime64, a host-side lookup) and, in the host-output modes, ``reward``.
 
-    KEYS = ["idx", "step", "position_index", "position", "real_position", "portfolio_valuation",
-            "data_close", "dataset_idx", "portfolio_distribution_asset", "portfolio_distribution_fiat",
-            "portfolio_distribution_borrowed_asset", "portfolio_distribution_borrowed_fiat",
-            "portfolio_distribution_interest_asset", "portfolio_distribution_interest_fiat",
-            "reward", "episode_metrics"]
+    As in a SAME_STEP vector env the row describes the CURRENT state: for an env whose episode just ended it is the
+    row `reset()` wrote for the new episode.  ``position_index`` is what the reference records: the action of the step
+    (hold -> -1, the reference's None) for envs that stepped, ``positions.index(position)`` for envs that were just
+    reset — read it before overwriting the action buffer passed to `step()`."""
+
+    BASE_KEYS = ["idx", "step", "position_index", "position", "real_position", "portfolio_valuation",
+                 "dataset_idx", "portfolio_distribution_asset", "portfolio_distribution_fiat",
+                 "portfolio_distribution_borrowed_asset", "portfolio_distribution_borrowed_fiat",
+                 "portfolio_distribution_interest_asset", "portfolio_distribution_interest_fiat",
+                 "reward", "episode_metrics"]
+    _DIST = ["asset", "fiat", "borrowed_asset", "borrowed_fiat", "interest_asset", "interest_fiat"]
 
     def __init__(self, env):
         self._env = env
         self._version = -1
+        self._cache = {}
+        series = env._series
+        cols = [c for c in series[0].info if all(c in srs.info for srs in series)]      # History's data_<column> (:131-134)
+        if "close" not in cols:
+            cols.append("close")                                                          # the price column always exists
+        self._data_cols = cols
+        self.KEYS = self.BASE_KEYS + ["data_" + c for c in cols]
+        if all(srs.index is not None for srs in series):
+            self.KEYS.append("date")
 
     def _materialise(self):
         if self._version != self._env._tick:
             self._env._launch_info()
             self._version = self._env._tick
+            self._cache = {}
 
     def __getitem__(self, key):
         e = self._env
@@ -152,9 +177,28 @@ class LazyInfos(Mapping):
         if key not in self.KEYS:
             raise KeyError(key)
         self._materialise()
+        if key in self._cache:
+            return self._cache[key]
         if key.startswith("portfolio_distribution_"):
-            names = ["asset", "fiat", "borrowed_asset", "borrowed_fiat", "interest_asset", "interest_fiat"]
-            return e._info_dist[names.index(key[len("portfolio_distribution_"):])]
+            return e._info_dist[self._DIST.index(key[len("portfolio_distribution_"):])]
+        if key == "data_close":
+            return e._info_t["data_close"]
+        if key == "position_index":
+            v = self._cache[key] = e._info_position_index()
+            return v
+        if key.startswith("data_"):
+            col = e._info_column(key[5:])                                   # f64 [n_datasets, t_stride] on the device
+            v = self._cache[key] = col[e._info_t["dataset_idx"].long(), e._info_t["idx"].long()]
+            return v
+        if key == "date":
+            idx, ds = e._info_t["idx"].cpu().numpy(), e._info_t["dataset_idx"].cpu().numpy()
+            out = np.empty(idx.shape, dtype=e._series[0].index.dtype)
+            for k, srs in enumerate(e._series):
+                m = ds == k
+                if m.any():
+                    out[m] = srs.index[idx[m]]
+            self._cache[key] = out
+            return out
         return e._info_t[key]
 
     def __iter__(self):
@@ -164,7 +208,7 @@ class LazyInfos(Mapping):
         return len(self.KEYS)
 
 
-class TradingVectorEnv:
+class TradingVectorEnv(_VectorEnvBase):
     """N independent reference-semantics ``TradingEnv`` instances advanced in lockstep on one B200.
 
     Reference parameters (same names, defaults and meaning as environments.py:79-93): ``df, positions,
@@ -184,9 +228,11 @@ class TradingVectorEnv:
     for small batches, no copy at all: the step kernel reads / writes the pinned host memory itself;
     ``host_io`` = "auto" | "copy" | "mapped" picks the mechanism); ``autoreset`` (True = in-place); ``cuda_graph``
     (capture one lockstep iteration and replay it: removes the launch overhead at small N; actions
-    are then read from the env's own buffer); ``n_chunks`` (0 = library default = 1; k > 1 cuts the envs
-    into k ranges and runs the step kernel of range c+1 beside the gather of range c on a side stream —
-    measured: no gain on B200, kept as an option);
+    are then read from the env's own buffer); ``n_chunks`` (0 = the library's choice: ONE fused launch per
+    iteration — every CTA advances its own envs, then gathers their windows — while the batch fits a single wave
+    (~100k envs), else two plain launches; 1 = always two plain launches; k > 1 cuts the envs into k ranges and
+    runs the step kernel of range c+1 beside the gather of range c on a side stream — measured: no gain on B200,
+    kept as an option);
     ``debug_outputs`` (also write the terminal step's idx/step/real_position/portfolio, +48 B/env);
     ``final_obs`` (gymnasium's SAME_STEP ``final_obs``: ``env.final_obs`` keeps, for every env whose episode
     ended in this step, the observation ``step()`` itself returned before the in-place reset
@@ -287,6 +333,7 @@ class TradingVectorEnv:
         self._graph = None
         self._copy_in = None
         self._pin_ident = {}                 # id(array) -> (array, pointer, itemsize) of pinned action arrays seen by step()
+        self._last_actions = None            # the actions of the last step (infos["position_index"]); None after a reset
         self._track_ids = None
         self._limit_price = None
         self._red_stream = None              # enable_metric_allreduce(): side stream of the per-iteration all-reduce
@@ -311,6 +358,11 @@ class TradingVectorEnv:
         self.observation_space = _Box(-np.inf, np.inf, shape=(self.num_envs,) + shape, dtype=np.float32)
         self.single_action_space = _Discrete(len(self.positions))
         self.action_space = _MultiDiscrete([len(self.positions)] * self.num_envs)
+        self.closed = False
+        if _gym is not None:                    # a real gymnasium.vector.VectorEnv: say how episodes restart (SAME_STEP)
+            mode = getattr(getattr(_gym.vector, "AutoresetMode", None), "SAME_STEP", None)
+            if mode is not None:
+                self.metadata = dict(self.metadata, autoreset_mode=mode)
 
     # ------------------------------------------------------------------ data staging (_set_df, :128-143)
     def _set_series(self, series):
@@ -590,6 +642,7 @@ class TradingVectorEnv:
                 mask_ptr = C.c_void_p(keep.data_ptr())
             self._launch_reset(mask_ptr, first=False)
             self._launch_obs()
+            self._last_actions = None
             if self._track_ids is not None:
                 self._track_append(after_reset=True)
             return self._emit_obs(), self.infos
@@ -604,6 +657,7 @@ class TradingVectorEnv:
             # the common on-device loop: one C call, nothing else
             a = self._fast_args
             self._tick += 1
+            self._last_actions = actions
             rc = self._lib.gte_step_obs(a[0], a[1], a[2], actions.data_ptr(), a[3], a[4], self.autoreset,
                                         self._obs_variant, self.n_chunks,
                                         torch.cuda.current_stream(self.device).cuda_stream)
@@ -641,6 +695,7 @@ class TradingVectorEnv:
             if self._track_ids is not None:
                 self._track_pre = (self._pos_idx[self._track_ids].clone(), self._dataset_idx[self._track_ids].clone())
             self._P.action_bytes = act_bytes
+            self._last_actions = src if host_in else act
             try:
                 ret = self._step_launch(act, main)
             finally:
@@ -655,11 +710,13 @@ class TradingVectorEnv:
         ent = self._pin_ident.get(id(actions))
         if ent is not None and ent[0] is actions:            # a pinned array seen before (kept alive by the cache)
             ptr, nb = ent[1], ent[2]
+            self._last_actions = actions
         else:
             a = self._stage_host_actions(actions)
             ptr, nb = a.ctypes.data, a.dtype.itemsize
             if a is actions and len(self._pin_ident) < 64:
                 self._pin_ident[id(actions)] = (actions, ptr, nb)
+            self._last_actions = a
         hb, io, red = self._host, self._io, self._red_stream
         if hb is None:
             hb = self._host_buffers()
@@ -767,7 +824,11 @@ class TradingVectorEnv:
             return h["obs"]
         return self._obs
 
-    def close(self):
+    def close(self, **kwargs):
+        self.close_extras(**kwargs)
+        self.closed = True
+
+    def close_extras(self, **kwargs):
         self._host = None
         self._pin_ident = {}
         self._graph = None
@@ -843,6 +904,7 @@ class TradingVectorEnv:
             o.real_position = o.info_idx = o.info_step = o.pre_reset_portfolio = None
             obs_buf = out["obs"] if keep_obs else self._obs
             self._tick += K
+            self._last_actions = actions[-1]
             _cabi.check(self._lib.gte_rollout(C.byref(self._P), C.byref(self._D), C.byref(self._S),
                                               C.c_void_p(actions.data_ptr()), K, C.byref(o),
                                               C.c_void_p(obs_buf.data_ptr()), int(keep_obs), 1,
@@ -988,6 +1050,32 @@ class TradingVectorEnv:
         render_df.to_pickle(path)
         return path
 
+    def _info_column(self, name):
+        """A numeric non-feature column of the staged frames (History's ``data_<name>``) as f64 [n_datasets, t_stride] on
+        the device, uploaded on first use."""
+        cols = self.__dict__.setdefault("_info_cols_dev", {})
+        if name not in cols:
+            host = np.ones((self._n_ds, self._t_stride), dtype=np.float64)
+            for k, srs in enumerate(self._series):
+                host[k, :srs.length] = srs.price if name == "close" and name not in srs.info else srs.info[name]
+            cols[name] = torch.from_numpy(host).to(self.device)
+        return cols[name]
+
+    def _info_position_index(self):
+        """``position_index`` as the reference records it: the step's action (hold = None -> -1) for envs that stepped
+        (:257), ``positions.index(position)`` on the row reset() writes (:189)."""
+        state = self._info_t["position_index"]
+        la = self._last_actions
+        if la is None:
+            return state
+        if isinstance(la, np.ndarray):
+            act = torch.from_numpy(np.ascontiguousarray(la)).to(self.device)
+        else:
+            act = la
+        act = act.to(torch.int64)
+        act = torch.where((act >= 0) & (act < len(self.positions)), act, torch.full_like(act, -1)).to(torch.int32)
+        return torch.where(self._info_t["step"] > 0, act, state)
+
     # ------------------------------------------------------------------ metrics / errors / state
     def get_metrics(self, total=True):
         """Numeric episode metrics (environments.py:279-283) as a name -> 0-d tensor dict."""
@@ -1092,6 +1180,12 @@ class TradingVectorEnv:
     def chunks(self):
         """Env ranges one `step()` is pipelined over (step kernel of range c+1 beside gather of range c)."""
         return self.n_chunks if self.n_chunks > 0 else int(self._lib.gte_default_chunks(self.num_envs))
+
+    @property
+    def launches_per_step(self):
+        """Kernel launches one `step()` of the on-device loop issues: 1 (windows=None, or transition + gather fused
+        into one launch for batches that fit a single wave), else 2 per env range."""
+        return int(self._lib.gte_step_obs_launches(C.byref(self._P), C.byref(self._D), self._obs_variant, self.n_chunks))
 
     @property
     def obs_variant(self):

@@ -204,7 +204,7 @@ typedef struct GteStepOut {
 /* Host side of one lockstep iteration for a HOST policy (gte_step_host): actions come from pinned host memory,
  * reward / terminated / truncated / error flag land in ONE pinned host block, observations stay in HBM. */
 enum GteHostIOMode {
-    GTE_IO_AUTO = 0,                 /* MAPPED while N * (action_bytes + 10) <= 1 MiB, else COPY            */
+    GTE_IO_AUTO = 0,                 /* MAPPED while N * (action_bytes + 10) <= 384 KiB (1 MiB with windows == 0), else COPY */
     GTE_IO_COPY = 1,                 /* copy engines: ONE cudaMemcpyAsync per direction, beside the gather  */
     GTE_IO_MAPPED = 2                /* zero-copy: the step kernel reads the actions from, and writes its
                                         10 B/env of results straight into, the pinned (UVA-mapped) host memory:
@@ -260,7 +260,9 @@ int gte_gather_obs(const GteParams* params, const GteData* data, const GteState*
                    float* obs, int variant, void* stream);
 
 /* One whole lockstep iteration — what a vector env's step() returns: gte_step + gte_gather_obs.
- * n_chunks: 0 or 1 = two plain launches (the default: measured fastest on B200, profiles/r01_tuning.md).  n_chunks > 1
+ * n_chunks: 0 = the library's choice: ONE fused launch (every CTA advances its own envs, then gathers their windows)
+ * while the batch fits a single wave with <= 256 envs per CTA (~100k envs on a B200), else two plain launches;
+ * 1 = always two plain launches (measured fastest for large batches, profiles/r01_tuning.md).  n_chunks > 1
  * is an opt-in experiment: the envs are cut into that many ranges and the step kernel of range c+1 runs beside the
  * gather of range c on a library-owned side stream (forked from and joined back into `stream` with events, so the
  * call is still stream-ordered and graph-capturable).  With windows == 0 the call is ONE launch: the step kernel
@@ -299,6 +301,10 @@ int gte_info(const GteParams* params, const GteData* data, const GteState* state
 /* sizeof() of the ABI structs as compiled: 0 GteParams, 1 GteData, 2 GteState, 3 GteStepOut, 4 GteInfo, 5 GteHostIO
  * (bindings assert their own layout against it). */
 int gte_struct_size(int which);
+
+/* Kernel launches one gte_step_obs call issues for this shape: 1 (windows == 0, or the fused form), else 2 per env
+ * range (host-only helper; asks the CUDA runtime for the gather kernel's occupancy, so it needs a device). */
+int gte_step_obs_launches(const GteParams* params, const GteData* data, int variant, int n_chunks);
 
 /* How many env ranges gte_step_obs uses for n_chunks = 0 (host-only helper). */
 int gte_default_chunks(int n_envs);

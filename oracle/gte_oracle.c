@@ -18,9 +18,13 @@
  * Plain scalar C on purpose: one env at a time, like the reference, so it also serves as the
  * "port" CPU baseline (one thread per env slice; bench.py splits envs over host threads).
  */
+#define _GNU_SOURCE
 #include <math.h>
+#include <pthread.h>
+#include <sched.h>
 #include <stdint.h>
 #include <string.h>
+#include <time.h>
 
 #define ORC_N_METRICS 8
 /* metric slots (sums over finished episodes unless noted) */
@@ -385,6 +389,70 @@ void orc_rollout_range(OrcEnv* e, int lo, int hi, const int64_t* actions, int n_
     for (int k = 0; k < iters; ++k)
         orc_step_range(e, lo, hi, actions + (int64_t)(k % n_sets) * e->n_envs, tick0 + (uint64_t)k, obs, reward,
                        terminated, truncated, 0, 0, 0, 0, 0, 0, metrics);
+}
+
+/* ------------------------------------------------------------------ CPU baseline driver (bench.py only) */
+/* The same rollout on n_threads host threads, each PINNED to one of the process's allowed CPUs and owning a contiguous
+ * env slice (envs are independent: no barrier between iterations, like per-env worker processes of an
+ * AsyncVectorEnv).  All threads start together behind a barrier; the return value is the wall time in seconds from
+ * that barrier to the last thread's exit, measured here so that no interpreter overhead is inside it.
+ * metrics: [n_threads][ORC_N_METRICS] partial sums. */
+typedef struct OrcWork {
+    OrcEnv* e; int lo, hi; const int64_t* actions; int n_sets, iters; uint64_t tick0;
+    float* obs; double* reward; uint8_t* terminated; uint8_t* truncated; double* metrics;
+    int cpu; pthread_barrier_t* bar;
+} OrcWork;
+
+static void* orc_worker(void* arg) {
+    OrcWork* w = (OrcWork*)arg;
+    if (w->cpu >= 0) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        CPU_SET(w->cpu, &set);
+        pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+    }
+    pthread_barrier_wait(w->bar);
+    orc_rollout_range(w->e, w->lo, w->hi, w->actions, w->n_sets, w->iters, w->tick0, w->obs, w->reward,
+                      w->terminated, w->truncated, w->metrics);
+    return 0;
+}
+
+static double orc_now(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+double orc_rollout_threads(OrcEnv* e, const int64_t* actions, int n_sets, int iters, uint64_t tick0,
+                           float* obs, double* reward, uint8_t* terminated, uint8_t* truncated,
+                           double* metrics, int n_threads, int pin) {
+    enum { MAX_T = 256 };
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > MAX_T) n_threads = MAX_T;
+    pthread_t th[MAX_T];
+    OrcWork w[MAX_T];
+    int cpus[1024], n_cpus = 0;
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    if (pin && sched_getaffinity(0, sizeof(allowed), &allowed) == 0)
+        for (int c = 0; c < 1024 && c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &allowed)) cpus[n_cpus++] = c;
+    pthread_barrier_t bar;
+    pthread_barrier_init(&bar, 0, (unsigned)n_threads + 1);
+    for (int t = 0; t < n_threads; ++t) {
+        w[t].e = e; w[t].lo = (int)(((int64_t)e->n_envs * t) / n_threads); w[t].hi = (int)(((int64_t)e->n_envs * (t + 1)) / n_threads);
+        w[t].actions = actions; w[t].n_sets = n_sets; w[t].iters = iters; w[t].tick0 = tick0;
+        w[t].obs = obs; w[t].reward = reward; w[t].terminated = terminated; w[t].truncated = truncated;
+        w[t].metrics = metrics + (int64_t)t * ORC_N_METRICS;
+        w[t].cpu = n_cpus > 0 ? cpus[t % n_cpus] : -1;
+        w[t].bar = &bar;
+        pthread_create(&th[t], 0, orc_worker, &w[t]);
+    }
+    pthread_barrier_wait(&bar);
+    double t0 = orc_now();
+    for (int t = 0; t < n_threads; ++t) pthread_join(th[t], 0);
+    double dt = orc_now() - t0;
+    pthread_barrier_destroy(&bar);
+    return dt;
 }
 
 int orc_struct_size(void) { return (int)sizeof(OrcEnv); }

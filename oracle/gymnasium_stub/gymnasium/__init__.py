@@ -7,7 +7,9 @@ there is no network, so `oracle/make_golden.py` puts this directory on ``sys.pat
 UNMODIFIED reference import and run.  It is only used when the real gymnasium is missing.
 """
 from . import spaces  # noqa: F401
+from . import vector  # noqa: F401
 from .envs import registration  # noqa: F401
+from .envs.registration import make_vec, register  # noqa: F401
 
 
 class Env:

@@ -14,3 +14,10 @@ class Box:
         self.low, self.high = low, high
         self.shape = tuple(shape) if shape is not None else ()
         self.dtype = dtype
+
+
+class MultiDiscrete:
+    def __init__(self, nvec, dtype=None, seed=None, start=None):
+        import numpy as np
+        self.nvec = np.asarray(nvec, dtype=np.int64)
+        self.shape, self.dtype = self.nvec.shape, np.dtype(np.int64)

@@ -78,6 +78,8 @@ def lib():
         _lib.orc_step.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 11
         _lib.orc_step_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64] + [C.c_void_p] * 11
         _lib.orc_rollout_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64] + [C.c_void_p] * 5
+        _lib.orc_rollout_threads.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64] + [C.c_void_p] * 5 + [C.c_int, C.c_int]
+        _lib.orc_rollout_threads.restype = C.c_double
     return _lib
 
 
@@ -252,9 +254,28 @@ class OracleVecEnv:
             self.metrics[:] = parts.sum(0)
         return self.obs, self.reward, self.terminated, self.truncated
 
+    def prefault(self):
+        """Touch every page of the per-env private dynamic columns (the reference materialises each env's arrays at
+        construction): keeps first-touch page faults out of a timed region."""
+        self.dyn_cols.fill(0)
+
+    def rollout_timed(self, action_sets, iters, pin=True):
+        """`iters` lockstep iterations on `self.threads` PINNED pthreads created inside C (orc_rollout_threads), each
+        rolling its own env slice forward; returns the wall seconds measured in C (bench.py's CPU baseline)."""
+        a = np.ascontiguousarray(action_sets, dtype=np.int64)
+        assert a.ndim == 2 and a.shape[1] == self.num_envs
+        nt = max(1, self.threads)
+        parts = np.zeros((nt, N_METRICS), np.float64)
+        tick0 = self.tick
+        self.tick += iters
+        dt = self._lib.orc_rollout_threads(C.byref(self._e), _p(a), a.shape[0], int(iters), tick0, _p(self.obs),
+                                           _p(self.reward), _p(self.terminated), _p(self.truncated), _p(parts), nt, int(pin))
+        self.metrics[:] = parts.sum(0)
+        return dt
+
     def rollout(self, action_sets, iters):
         """`iters` lockstep iterations with actions cycling through action_sets[A, N]; each host thread
-        rolls its own env slice forward inside C (bench.py's CPU baseline — envs are independent)."""
+        rolls its own env slice forward inside C (envs are independent)."""
         a = np.ascontiguousarray(action_sets, dtype=np.int64)
         assert a.ndim == 2 and a.shape[1] == self.num_envs
         N, nt = self.num_envs, max(1, self.threads)

@@ -16,7 +16,9 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert len(lines) == 1, p.stdout[:500]
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "env-steps/s" and d["higher_is_better"] is True
-    assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["steps"] == 2 and d["warmup"] == 3 and d["n_gpus"] == 1      # never fewer than 3 warm-up steps
+    assert d["spread"]["steps"] == 2 and d["spread"]["min"] <= d["value"] <= d["spread"]["max"]
+    assert d["value"] > 0 and d["ms_per_step"] > 0
     assert d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic" and "workload" in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]

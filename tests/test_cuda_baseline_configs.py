@@ -259,3 +259,33 @@ def test_reset_plan_rows_are_range_checked_and_exhaustion_is_flagged():
     with pytest.raises(ValueError):
         env2.check_errors()
     assert 0 <= int(env2._ep_start[3]) <= 598 and 0 <= int(env2._pos_idx[3]) <= 1
+
+
+@pytest.mark.parametrize("n_envs,windows,pos", [(2500, 64, [-3, -2, -1, 0, 1, 2, 3]), (65_536, 64, [-1, 0, 0.5, 1]),
+                                                (100_000, 64, [-1, 0, 1]), (9_000, 16, [0, 1])])
+def test_fused_single_launch_equals_two_plain_launches(n_envs, windows, pos):
+    """gte_step_obs runs small batches as ONE fused launch (transition + gather per CTA); n_chunks=1 forces the two plain
+    launches.  Both must produce the same bits: observations, rewards, flags, portfolio state, Philox resets."""
+    import gym_trading_env_b200 as gte
+    series = gte.frame_to_arrays(gte.make_gbm_ohlcv(20_000, seed=4))
+    kw = dict(positions=pos, windows=windows, max_episode_duration=20, num_envs=n_envs, seed=21, verbose=0,
+              debug_outputs=True, **FEES)
+    fused, plain = gte.TradingVectorEnv(series, n_chunks=0, **kw), gte.TradingVectorEnv(series, n_chunks=1, **kw)
+    assert fused.launches_per_step == 1 and plain.launches_per_step == 2
+    o0, _ = fused.reset()
+    o1, _ = plain.reset()
+    assert torch.equal(o0.view(torch.int32), o1.view(torch.int32))
+    acts = _acts(n_envs, 50, len(pos), fused.device, seed=5)
+    acts[:, ::17] = -1                                                   # holds
+    for k in range(50):
+        fused.step(acts[k])
+        plain.step(acts[k])
+        assert torch.equal(fused._obs.view(torch.int32), plain._obs.view(torch.int32)), k
+        for nm in ("reward", "valuation", "real_position", "terminated", "truncated", "asset", "fiat", "interest_asset",
+                   "interest_fiat", "pos_idx", "step", "ep_start", "info_idx", "info_step", "dyn_ring"):
+            assert torch.equal(getattr(fused, "_" + nm), getattr(plain, "_" + nm)), (k, nm)
+        assert torch.equal(fused._metrics_step[:3], plain._metrics_step[:3])
+        torch.testing.assert_close(fused._metrics_step, plain._metrics_step, rtol=1e-9, atol=1e-9)
+    assert float(fused._metrics_total[0]) >= 2 * n_envs
+    assert int(fused._ring_clock) == int(plain._ring_clock) == 50 and int(fused._tick_dev) == int(plain._tick_dev)
+    fused.check_errors()

@@ -335,7 +335,10 @@ def test_rollout_equals_stepping_one_by_one(windows):
     assert torch.equal(torch.cat([last["terminated"], last2["terminated"]]), out["terminated"])
     for e in (a, c):
         assert torch.equal(e._obs.view(torch.int32), b._obs.view(torch.int32))
-        assert torch.equal(e._metrics_total, b._metrics_total)
+        # counts are exact; the fp64 sums are folded in a fixed order PER LAUNCH SHAPE (one fused launch when the
+        # observation is gathered, the plain step kernel when it is not), so they agree to rounding, not to the bit
+        assert torch.equal(e._metrics_total[:3], b._metrics_total[:3]) and torch.equal(e._metrics_total[5], b._metrics_total[5])
+        torch.testing.assert_close(e._metrics_total, b._metrics_total, rtol=1e-12, atol=1e-12)
         for name in ("_asset", "_fiat", "_pos_idx", "_step", "_ep_start", "_reward", "_terminated", "_valuation"):
             assert torch.equal(getattr(e, name), getattr(b, name)), name
     assert "obs" not in last and out["obs"].shape[0] == 40
