@@ -292,6 +292,8 @@ def main():
     ap.add_argument("--pyref-seed", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short C2 / C3 / C4 legs of the default run")
+    ap.add_argument("--repeats", type=int, default=3, help="the timed region of K steps is repeated this many times; the median counts")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = {"c3": 2000, "c2": 5000}.get(args.workload, 200) if args.impl == "b200" else 200
@@ -324,65 +326,18 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    N = wl["envs"]
-    series = make_series(wl, gte)
-    kw = dict(positions=wl["positions"], windows=wl["windows"], trading_fees=FEE, borrow_interest_rate=RATE,
-              portfolio_initial_value=V0, max_episode_duration=wl["duration"], num_envs=N, device=dev,
-              seed=2024, env_id_offset=rank * N, obs_variant=args.obs_variant, verbose=0,
-              cuda_graph=args.cuda_graph)
-    if wl["n_datasets"] > 1:
-        env = gte.MultiDatasetTradingVectorEnv(datasets=series, **kw)
-    else:
-        env = gte.TradingVectorEnv(series[0], **kw)
-    n_sets = 8
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    actions = torch.randint(0, len(wl["positions"]), (n_sets, N), generator=gen, device=dev, dtype=torch.int64)
-    env.reset()
-    launches_per_step = env.launches_per_step
+    ctx = Ctx(torch=torch, dist=dist, gte=gte, dev=dev, rank=rank, world=world, local_rank=local_rank, args=args)
 
+    sampler = ClockSampler(local_rank)
+    env, actions = build_env(ctx, wl, args.workload)
     if world > 1:
         # C5: NCCL all-reduce(sum) of the 8 fp64 episode metrics EVERY iteration, issued by the env between its two
         # kernels on a side stream (overlaps the gather; the next iteration only waits for the 64-byte snapshot)
         env.enable_metric_allreduce()
-
-    def lockstep(k):
-        env.step(actions[k % n_sets])
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                      # already running (and past its start-up) when the timed region begins
-    for k in range(max(args.warmup, 3)):
-        lockstep(k)
-    barrier()
-    # per-kernel CUDA events INSIDE the timed region: on every 4th (8th) iteration env.step() issues its two kernels
-    # as two calls (the very kernels gte_step_obs launches) with events on the launching stream around each; the
-    # event records cost ~3 us per iteration they bracket, hence not every iteration
-    fused = wl["windows"] is not None and env.launches_per_step == 1      # transition + gather in ONE launch (small batches)
-    env._kernel_events = [] if (wl["windows"] is not None and not fused) else None
-    env._kernel_events_every = 1 if args.steps < 64 else (4 if wl["envs"] >= 2 ** 20 else 8)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_host0 = time.time()
-    e0.record()
-    for k in range(args.steps):
-        lockstep(k)
-    env.wait_metric_allreduce()              # the timed region ends when the last all-reduce has landed
-    e1.record()
-    barrier()
-    clocks = sampler.stop(t_host0, time.time()) if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    env.check_errors()
+    m = measure(ctx, env, actions, wl, args.workload, args.steps, max(args.warmup, 3), repeats=args.repeats, sampler=sampler)
+    N = wl["envs"]
     if world > 1:
         # the per-iteration all-reduces must add up to the all-reduced local totals (counts exactly, fp sums to rounding)
         torch.cuda.synchronize()
@@ -391,132 +346,22 @@ def main():
         got = env.global_metrics_total
         if not (torch.equal(got[:3], tot[:3]) and torch.equal(got[5], tot[5]) and torch.allclose(got, tot, rtol=1e-9, atol=1e-9)):
             raise RuntimeError(f"per-iteration metric all-reduce disagrees with the local totals: {got.tolist()} vs {tot.tolist()}")
-    value = world * N * args.steps / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (window gather; the step kernel when windows=None) ----
-    a_step, a_obs = algorithmic_bytes(wl["windows"])
-    env_events = env._kernel_events
-    if env_events:
-        step_ms = [ev[0].elapsed_time(ev[1]) for ev in env._kernel_events]
-        obs_ms = [ev[1].elapsed_time(ev[2]) for ev in env._kernel_events]
-    else:                                    # windows=None: one fused launch per iteration = the whole step
-        step_ms, obs_ms = [ms / args.steps], [ms / args.steps]
-    env._kernel_events = None
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    obs_ms_avg = sum(obs_ms) / max(len(obs_ms), 1)
-    step_ms_avg = sum(step_ms) / max(len(step_ms), 1)
-    split = wl["windows"] is not None and bool(env_events)               # per-kernel events were recorded
-    dom_bytes = a_obs if split else a_step + a_obs                       # else one timing for the whole iteration
-    achieved = (dom_bytes * N) / (obs_ms_avg * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"{args.workload}:{env.obs_variant}:{N}")
-    whole = (a_step + a_obs) * N * args.steps / (ms * 1e-3) / 1e9
-    # C4: the 1.28 GB feature table is not L2-resident, so the static window read is HBM traffic too
-    # (SURVEY.md §8d "5 218 B" accounting) — reported beside the conservative figure
-    a_static = (wl["windows"] or 1) * 8 * 4 if wl["n_datasets"] > 1 else 0
-    kname = {"tma": "obs_tma_coop_kernel", "vec": "obs_vec_kernel", "generic": "obs_generic_kernel"}[env.obs_variant]
-    if wl["windows"] is None:
-        kname = "step_kernel (windows=None: writes the one-row observation itself)"
-    elif fused:
-        kname += "<fused> (ONE launch per iteration: every CTA advances its envs, then gathers their windows; timed as a whole)"
-    elif not split:
-        kname = "step_kernel + " + kname + " (graph replay: timed together)"
-    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_env": dom_bytes, "kernel_ms": obs_ms_avg,
-                "timing": "CUDA events on the launching stream around the launches of every %s iteration of the timed region" % {1: "single", 4: "4th", 8: "8th"}[env._kernel_events_every],
-                "step_kernel_ms": step_ms_avg,
-                "step_kernel": {"algorithmic_bytes_per_env": a_step, "achieved": a_step * N / (step_ms_avg * 1e-3) / 1e9,
-                                "frac": a_step * N / (step_ms_avg * 1e-3) / 1e9 / peak},
-                "whole_step": {"algorithmic_bytes_per_env_step": a_step + a_obs, "achieved": whole,
-                               "frac": whole / peak, "frac_of_nominal_8TBs": whole / 8000.0,
-                               "with_static_window_read": None if not a_static else {
-                                   "algorithmic_bytes_per_env_step": a_step + a_obs + a_static,
-                                   "achieved": whole * (a_step + a_obs + a_static) / (a_step + a_obs),
-                                   "frac": whole * (a_step + a_obs + a_static) / (a_step + a_obs) / peak}}}
+    latency = latency_probe(ctx, env, actions, wl, m) if (wl["envs"] < 2 ** 20 and world == 1 and not args.cuda_graph) else None
+    e2e = e2e_legs(ctx, env, actions, wl) if not args.no_e2e else {}
+    env.close()
+    del env
 
-    # ---- launch / latency floor at small N (BASELINE config 2): the same iterations enqueued by ONE host call
-    # (env.rollout -> gte_rollout: a C loop of kernel launches, no Python between iterations) ----
-    latency = None
-    if wl["envs"] < 2 ** 20 and world == 1 and not args.cuda_graph:
-        K = 2000
-        acts_k = actions[torch.arange(K, device=dev) % n_sets]
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        us_open = float("inf")
-        for _ in range(4):                   # the GPU idled while the clocks were read: let the SM clock ramp up again
-            r0.record()
-            env.rollout(acts_k, keep_obs=False)
-            r1.record()
-            torch.cuda.synchronize()
-            us_open = min(us_open, 1e3 * r0.elapsed_time(r1) / K)
-        latency = {"step_call_us": 1e3 * ms / args.steps,
-                   "rollout_us_per_iteration": us_open, "rollout_env_steps_per_s": N / (us_open * 1e-6),
-                   "note": "step_call = env.step() per iteration from Python (one ctypes call, step + gather kernels); rollout = "
-                           "%d iterations enqueued by one gte_rollout call (open-loop actions; only the last observation is "
-                           "gathered, so with windows this is the step kernel's rate), best of 4" % K}
-
-    # ---- e2e: public API with HOST numpy actions in and HOST numpy reward/terminated/truncated out.
-    # "hybrid" (headline): observations stay device-resident for an on-device policy;
-    # "numpy": the full observation windows also cross PCIe (2.5 KB per env-step: PCIe-bound). ----
-    e2e = e2e_full = e2e_i64 = e2e_mapped = None
-    if not args.no_e2e:
-        wire = {}
-        for dt in (torch.int8, torch.int64):                 # action sets staged in pinned host memory, both wire widths
-            t = torch.empty(actions.shape, dtype=dt, pin_memory=True)
-            t.copy_(actions)
-            wire[dt] = (t, t.numpy())
-
-        def time_e2e(mode, host_io, dt, n_it):
-            env.output, env.host_io, env._host = mode, host_io, None
-            acts_h = wire[dt][1]
-            rows = [acts_h[i] for i in range(n_sets)]        # the caller's pinned action arrays, one per action set
-            for k in range(3):
-                env.step(rows[k % n_sets])                   # allocates + warms the pinned buffers
-            barrier()
-            t0 = time.perf_counter()
-            for k in range(n_it):
-                env.step(rows[k % n_sets])
-            env.wait_metric_allreduce()
-            torch.cuda.synchronize()
-            dt_s = time.perf_counter() - t0
-            tt = torch.tensor([dt_s], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ab = acts_h.dtype.itemsize
-            rbytes = host_result_bytes(N)
-            return {"value": world * N * n_it / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": N * ab,
-                    "d2h_bytes_per_step": rbytes + (env._obs.numel() * 4 if mode == "numpy" else 0), "steps": n_it,
-                    "timing": "host wall clock around the step() calls, max over ranks", "mode": mode,
-                    "host_io": ("copy" if mode == "numpy" else {1: "copy", 2: "mapped"}.get(env._io_mode_used.value, "?")),
-                    "action_dtype": str(acts_h.dtype)}
-
-        from gym_trading_env_b200._cabi import host_result_layout
-        host_result_bytes = lambda n: host_result_layout(n)[3]   # noqa: E731
-        n_it = min(max(args.steps, 10), 200)
-        # headline: the documented default wire format of a host policy — int8 actions (Discrete(P) fits, widened by the
-        # step kernel: lossless), fp64 rewards + terminated + truncated + error flag back in ONE block
-        e2e = time_e2e("hybrid", "auto", torch.int8, n_it)
-        e2e["note"] = ("VectorEnv(output='hybrid').step(pinned int8 numpy actions) -> numpy f64 reward / bool terminated / bool "
-                       "truncated every step through ONE gte_step_host call (one copy per direction, or mapped host memory at "
-                       "small N); the observation tensor stays in HBM for the policy's forward pass")
-        e2e_i64 = time_e2e("hybrid", "auto", torch.int64, n_it)
-        e2e_i64["note"] = "same call with gymnasium's own dtypes on the wire (int64 actions in, f64 reward + bool flags out)"
-        if world == 1:
-            other = "mapped" if e2e["host_io"] == "copy" else "copy"
-            e2e_mapped = time_e2e("hybrid", other, torch.int8, min(n_it, 50))
-            e2e_mapped["note"] = ("the OTHER host-IO mechanism forced, for comparison (mapped = the step kernel reads the actions "
-                                  "from, and writes its results into, pinned host memory; copy = copy engines)")
-            e2e_full = time_e2e("numpy", "auto", torch.int8, args.e2e_steps)
-            e2e_full["note"] = ("VectorEnv(output='numpy'): the full observation batch is also copied to pinned host memory every "
-                                "step; bounded by PCIe (~52 GB/s), reported for transparency")
-        env.output, env.host_io, env._host = "torch", "auto", None
-        env.close()
+    # ---- the other BASELINE configs, short legs in the same process (N=1 default run only) ----
+    configs = None
+    if rank == 0 and world == 1 and args.workload == "c5" and not args.no_configs and not args.envs_per_gpu:
+        configs = {}
+        for name in ("c2", "c3", "c4"):
+            try:
+                configs[name] = config_leg(ctx, name)
+            except Exception as e:  # noqa: BLE001
+                configs[name] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
 
     # ---- CPU baseline (rank 0, N=1 only): scalar C port of the reference on the host cores ----
     cpu = None
@@ -534,23 +379,272 @@ def main():
 
     if rank == 0:
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": m["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["label"], "envs_per_gpu": N, "obs_variant": env.obs_variant, "chunks": env.chunks, "cuda_graph": bool(args.cuda_graph),
-                       "l2_policy": "inputs larger than L2 (obs %.0f MB + state/ring %.0f MB per step vs 126 MB L2)"
-                                    % (env._obs.numel() * 4 / 1e6, (N * 44 + env._dyn_ring.numel()) / 1e6),
+            "config": {"workload": wl["label"], "envs_per_gpu": N, "obs_variant": m["obs_variant"], "chunks": m["chunks"],
+                       "cuda_graph": bool(args.cuda_graph), "l2_policy": m["l2_policy"],
                        "parallelism": f"env-sharded x{world}, dataset replicated, NCCL allreduce of 8 fp64 metrics per iteration",
                        "host_bind": host_bind},
-            "clocks": clocks, "e2e": e2e, "e2e_gymnasium_dtypes": e2e_i64, "e2e_other_host_io": e2e_mapped,
-            "e2e_full_obs_to_host": e2e_full,
-            "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "repeats": m["repeats"], "spread": m["spread"],
+            "clocks": m["clocks"], "e2e": e2e.get("e2e"), "e2e_gymnasium_dtypes": e2e.get("e2e_gymnasium_dtypes"),
+            "e2e_other_host_io": e2e.get("e2e_other_host_io"), "e2e_full_obs_to_host": e2e.get("e2e_full_obs_to_host"),
+            "gpu_launches": m["launches_per_step"] * args.steps * m["repeats"]["n"], "roofline": m["roofline"], "cpu_baseline": cpu,
         }
         if latency is not None:
             out["latency"] = latency
+        if configs is not None:
+            out["configs"] = configs
         _emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+class Ctx:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def build_env(ctx, wl, workload_name, **over):
+    gte, torch = ctx.gte, ctx.torch
+    N = wl["envs"]
+    series = make_series(wl, gte)
+    kw = dict(positions=wl["positions"], windows=wl["windows"], trading_fees=FEE, borrow_interest_rate=RATE,
+              portfolio_initial_value=V0, max_episode_duration=wl["duration"], num_envs=N, device=ctx.dev,
+              seed=2024, env_id_offset=ctx.rank * N, obs_variant=ctx.args.obs_variant, verbose=0,
+              cuda_graph=ctx.args.cuda_graph)
+    kw.update(over)
+    if wl["n_datasets"] > 1:
+        env = gte.MultiDatasetTradingVectorEnv(datasets=series, **kw)
+    else:
+        env = gte.TradingVectorEnv(series[0], **kw)
+    gen = torch.Generator(device=ctx.dev)
+    gen.manual_seed(1234 + ctx.rank)
+    actions = torch.randint(0, len(wl["positions"]), (N_ACTION_SETS, N), generator=gen, device=ctx.dev, dtype=torch.int64)
+    env.reset()
+    return env, actions
+
+
+N_ACTION_SETS = 8
+
+
+def _barrier(ctx):
+    ctx.torch.cuda.synchronize()
+    if ctx.world > 1:
+        ctx.dist.barrier()
+    ctx.torch.cuda.synchronize()
+
+
+def measure(ctx, env, actions, wl, workload_name, steps, warmup, repeats=3, sampler=None):
+    """Device-timed throughput of `steps` lockstep iterations (CUDA events, barrier + synchronize on both sides, max over
+    ranks), repeated `repeats` times: `value` follows the MEDIAN repetition, the spread is reported.  The dominant
+    kernel is timed live inside the timed regions with its own CUDA events (see `roofline.timing`)."""
+    torch, dist, world = ctx.torch, ctx.dist, ctx.world
+    N, n_sets = wl["envs"], actions.shape[0]
+    for k in range(warmup):
+        env.step(actions[k % n_sets])
+    _barrier(ctx)
+    # per-kernel CUDA events INSIDE the timed region: on every 4th (8th) iteration env.step() issues its two kernels
+    # as two calls (the very kernels gte_step_obs launches) with events on the launching stream around each; the
+    # event records cost ~3 us per iteration they bracket, hence not every iteration
+    launches_per_step = env.launches_per_step
+    fused = wl["windows"] is not None and launches_per_step == 1      # transition + gather in ONE launch (small batches)
+    env._kernel_events = [] if (wl["windows"] is not None and not fused and not ctx.args.cuda_graph) else None
+    env._kernel_events_every = 1 if steps < 64 else (4 if N >= 2 ** 20 else 8)
+    times = []
+    t_host0 = time.time()
+    for _ in range(repeats):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _barrier(ctx)
+        e0.record()
+        for k in range(steps):
+            env.step(actions[k % n_sets])
+        env.wait_metric_allreduce()          # the timed region ends when the last all-reduce has landed
+        e1.record()
+        _barrier(ctx)
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+    clocks = sampler.stop(t_host0, time.time()) if (sampler is not None and ctx.rank == 0) else None
+    env.check_errors()
+    ms = statistics.median(times)
+    value = world * N * steps / (ms * 1e-3)
+    spread = {"ms_per_step_min": min(times) / steps, "ms_per_step_max": max(times) / steps,
+              "rel": (max(times) - min(times)) / ms}
+
+    # ---- roofline of the dominant kernel (window gather; the whole launch when there is only one) ----
+    a_step, a_obs = algorithmic_bytes(wl["windows"])
+    env_events = env._kernel_events
+    if env_events:
+        step_ms = [ev[0].elapsed_time(ev[1]) for ev in env_events]
+        obs_ms = [ev[1].elapsed_time(ev[2]) for ev in env_events]
+    else:                                    # one launch per iteration = the whole step
+        step_ms, obs_ms = [ms / steps], [ms / steps]
+    every = env._kernel_events_every
+    env._kernel_events = None
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    obs_ms_avg = sum(obs_ms) / max(len(obs_ms), 1)
+    step_ms_avg = sum(step_ms) / max(len(step_ms), 1)
+    split = wl["windows"] is not None and bool(env_events)               # per-kernel events were recorded
+    dom_bytes = a_obs if split else a_step + a_obs                       # else one timing for the whole iteration
+    achieved = (dom_bytes * N) / (obs_ms_avg * 1e-3) / 1e9
+    traffic, traffic_step = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = tj.get(f"{workload_name}:{env.obs_variant}{':fused' if fused else ''}:{N}")
+        traffic_step = tj.get(f"{workload_name}:step:{N}")
+    whole = (a_step + a_obs) * N * steps / (ms * 1e-3) / 1e9
+    # C4: the 1.28 GB feature table is not L2-resident, so the static window read is HBM traffic too
+    # (SURVEY.md §8d "5 218 B" accounting) — reported beside the conservative figure
+    a_static = (wl["windows"] or 1) * 8 * 4 if wl["n_datasets"] > 1 else 0
+    kname = {"tma": "obs_tma_coop_kernel", "vec": "obs_vec_kernel", "generic": "obs_generic_kernel"}[env.obs_variant]
+    if wl["windows"] is None:
+        kname = "step_kernel (windows=None: writes the one-row observation itself)"
+    elif fused:
+        kname += "<fused> (ONE launch per iteration: every CTA advances its envs, then gathers their windows; timed as a whole)"
+    elif not split:
+        kname = "step_kernel + " + kname + " (graph replay: timed together)"
+    timing = ("CUDA events on the launching stream around the launches of every %s iteration of the timed regions"
+              % {1: "single", 4: "4th", 8: "8th"}[every]) if split else "the timed regions themselves (one launch per iteration)"
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_env": dom_bytes, "kernel_ms": obs_ms_avg,
+                "timing": timing, "step_kernel_ms": step_ms_avg if split else None,
+                "step_kernel": None if not split else {
+                    "algorithmic_bytes_per_env": a_step, "achieved": a_step * N / (step_ms_avg * 1e-3) / 1e9,
+                    "frac": a_step * N / (step_ms_avg * 1e-3) / 1e9 / peak, "traffic": traffic_step},
+                "whole_step": {"algorithmic_bytes_per_env_step": a_step + a_obs, "achieved": whole,
+                               "frac": whole / peak, "frac_of_nominal_8TBs": whole / 8000.0,
+                               "with_static_window_read": None if not a_static else {
+                                   "algorithmic_bytes_per_env_step": a_step + a_obs + a_static,
+                                   "achieved": whole * (a_step + a_obs + a_static) / (a_step + a_obs),
+                                   "frac": whole * (a_step + a_obs + a_static) / (a_step + a_obs) / peak}}}
+    return {"value": value, "ms_per_step": ms / steps, "spread": spread, "clocks": clocks, "roofline": roofline,
+            "repeats": {"n": repeats, "steps_each": steps, "statistic": "median"},
+            "launches_per_step": launches_per_step, "obs_variant": env.obs_variant, "chunks": env.chunks,
+            "l2_policy": "inputs larger than L2 (obs %.0f MB + state/ring %.0f MB per step vs 126 MB L2)"
+                         % (env._obs.numel() * 4 / 1e6, (N * 44 + env._dyn_ring.numel()) / 1e6)}
+
+
+def latency_probe(ctx, env, actions, wl, m):
+    """Launch / latency floor at small N (BASELINE config 2): the same iterations enqueued by ONE host call
+    (env.rollout -> gte_rollout: a C loop of kernel launches, no Python between iterations), and the cost of an
+    empty stream round trip on this box."""
+    torch = ctx.torch
+    K, N, n_sets = 2000, wl["envs"], actions.shape[0]
+    acts_k = actions[torch.arange(K, device=ctx.dev) % n_sets]
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    us_open = float("inf")
+    for _ in range(4):                   # the GPU idled while the clocks were read: let the SM clock ramp up again
+        r0.record()
+        env.rollout(acts_k, keep_obs=False)
+        r1.record()
+        torch.cuda.synchronize()
+        us_open = min(us_open, 1e3 * r0.elapsed_time(r1) / K)
+    # the floor under any synchronous host call: one step() + stream synchronize (launch -> completion -> host wake-up)
+    stream = torch.cuda.current_stream()
+    for _ in range(50):
+        env.step(actions[0]); stream.synchronize()
+    t0 = time.perf_counter()
+    for k in range(500):
+        env.step(actions[k % n_sets]); stream.synchronize()
+    sync_us = 1e6 * (time.perf_counter() - t0) / 500
+    return {"step_call_us": 1e3 * m["ms_per_step"],
+            "rollout_us_per_iteration": us_open, "rollout_env_steps_per_s": N / (us_open * 1e-6),
+            "step_plus_stream_sync_us": sync_us,
+            "note": "step_call = env.step() per iteration from Python, back to back (one ctypes call per iteration); rollout = "
+                    "%d iterations enqueued by one gte_rollout call (open-loop actions; only the last observation is "
+                    "gathered, so with windows this is the step kernel's rate), best of 4; step_plus_stream_sync = one "
+                    "iteration followed by a stream synchronize (launch -> completion -> host wake-up): the floor under "
+                    "any synchronous host-policy step on this box" % K}
+
+
+def e2e_legs(ctx, env, actions, wl):
+    """e2e: the public API with HOST numpy actions in and HOST numpy reward / terminated / truncated out, wall clock
+    around the step() calls.  "hybrid" (headline): observations stay device-resident for the policy's forward pass;
+    "numpy": the full observation windows also cross PCIe (2.5 KB per env-step: PCIe-bound)."""
+    torch, dist, world, dev, args = ctx.torch, ctx.dist, ctx.world, ctx.dev, ctx.args
+    from gym_trading_env_b200._cabi import host_result_layout
+    N, n_sets = wl["envs"], actions.shape[0]
+    wire = {}
+    for dt in (torch.int8, torch.int64):                 # action sets staged in pinned host memory, both wire widths
+        t = torch.empty(actions.shape, dtype=dt, pin_memory=True)
+        t.copy_(actions)
+        wire[dt] = (t, t.numpy())
+
+    def time_e2e(mode, host_io, dt, n_it):
+        env.output, env.host_io, env._host = mode, host_io, None
+        acts_h = wire[dt][1]
+        rows = [acts_h[i] for i in range(n_sets)]        # the caller's pinned action arrays, one per action set
+        for k in range(3):
+            env.step(rows[k % n_sets])                   # allocates + warms the pinned buffers
+        _barrier(ctx)
+        t0 = time.perf_counter()
+        for k in range(n_it):
+            env.step(rows[k % n_sets])
+        env.wait_metric_allreduce()
+        torch.cuda.synchronize()
+        dt_s = time.perf_counter() - t0
+        tt = torch.tensor([dt_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ab = acts_h.dtype.itemsize
+        return {"value": world * N * n_it / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": N * ab,
+                "d2h_bytes_per_step": host_result_layout(N)[3] + (env._obs.numel() * 4 if mode == "numpy" else 0),
+                "steps": n_it, "us_per_step": 1e6 * float(tt.item()) / n_it,
+                "timing": "host wall clock around the step() calls, max over ranks", "mode": mode,
+                "host_io": ("copy" if mode == "numpy" else {1: "copy", 2: "mapped"}.get(env._io_mode_used.value, "?")),
+                "action_dtype": str(acts_h.dtype)}
+
+    out = {}
+    n_it = min(max(args.steps, 10), 200) if N >= 2 ** 20 else 2000
+    # headline: the documented default wire format of a host policy — int8 actions (Discrete(P) fits, widened by the
+    # step kernel: lossless), fp64 rewards + terminated + truncated + error flag back in ONE block
+    out["e2e"] = time_e2e("hybrid", "auto", torch.int8, n_it)
+    out["e2e"]["note"] = ("VectorEnv(output='hybrid').step(pinned int8 numpy actions) -> numpy f64 reward / bool terminated / bool "
+                          "truncated every step through ONE gte_step_host call (one copy per direction, or mapped host memory at "
+                          "small N); the observation tensor stays in HBM for the policy's forward pass")
+    out["e2e_gymnasium_dtypes"] = time_e2e("hybrid", "auto", torch.int64, n_it)
+    out["e2e_gymnasium_dtypes"]["note"] = "same call with gymnasium's own dtypes on the wire (int64 actions in, f64 reward + bool flags out)"
+    if world == 1:
+        other = "mapped" if out["e2e"]["host_io"] == "copy" else "copy"
+        out["e2e_other_host_io"] = time_e2e("hybrid", other, torch.int8, min(n_it, 50) if N >= 2 ** 20 else n_it)
+        out["e2e_other_host_io"]["note"] = ("the OTHER host-IO mechanism forced, for comparison (mapped = the step kernel reads the "
+                                            "actions from, and writes its results into, pinned host memory; copy = copy engines)")
+        out["e2e_full_obs_to_host"] = time_e2e("numpy", "auto", torch.int8, args.e2e_steps if N >= 2 ** 20 else 50)
+        out["e2e_full_obs_to_host"]["note"] = ("VectorEnv(output='numpy'): the full observation batch is also copied to pinned host "
+                                               "memory every step; bounded by PCIe (~52 GB/s), reported for transparency")
+    env.output, env.host_io, env._host = "torch", "auto", None
+    return out
+
+
+def config_leg(ctx, name):
+    """A short leg of another BASELINE config inside the default run: value, time per iteration, whole-step fraction of
+    the HBM roofline, the dominant kernel's fraction, and for the small configs the latency floor and the host path."""
+    wl = dict(WORKLOADS[name])
+    steps = {"c2": 3000, "c3": 1500, "c4": 60}[name]
+    env, actions = build_env(ctx, wl, name)
+    m = measure(ctx, env, actions, wl, name, steps, 5, repeats=3)
+    r = m["roofline"]
+    leg = {"workload": wl["label"], "value": m["value"], "unit": UNIT, "ms_per_step": m["ms_per_step"], "steps": steps,
+           "repeats": m["repeats"], "spread": m["spread"], "launches_per_step": m["launches_per_step"],
+           "whole_step_frac": r["whole_step"]["frac"], "whole_step_frac_with_static_window_read":
+               (r["whole_step"]["with_static_window_read"] or {}).get("frac"),
+           "kernel": r["kernel"], "kernel_ms": r["kernel_ms"], "kernel_frac": r["frac"], "step_kernel_ms": r["step_kernel_ms"],
+           "traffic": r["traffic"], "algorithmic_bytes_per_env_step": r["whole_step"]["algorithmic_bytes_per_env_step"]}
+    if wl["envs"] < 2 ** 20:
+        leg["latency"] = latency_probe(ctx, env, actions, wl, m)
+        e = e2e_legs(ctx, env, actions, wl)
+        leg["e2e"] = {k: {kk: v[kk] for kk in ("value", "us_per_step", "host_io", "action_dtype", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+                      for k, v in e.items() if v}
+    env.close()
+    return leg
 
 
 if __name__ == "__main__":

@@ -183,6 +183,7 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
     __shared__ unsigned long long f_src[FUSED ? kFusedMaxEnvs : 1];   // FUSED: window address / first live row of every
     __shared__ int f_live[FUSED ? kFusedMaxEnvs : 1];                 //        env this CTA owns, written by its step phase
     __shared__ double f_pos[FUSED ? GTE_MAX_POSITIONS : 1];
+    __shared__ int f_T0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool ring = sh.nd > 0;
     const uint32_t win_bytes = (uint32_t)sh.win_bytes;
@@ -200,6 +201,7 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (FUSED && tid < GTE_MAX_POSITIONS) f_pos[tid] = P.positions[tid];
+    if (FUSED && tid == 0) f_T0 = D.lengths[0];
     __syncthreads();
     pdl_wait();                              // state / ring / clock below were written by the kernel before us
 
@@ -213,10 +215,12 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
         const int ring_slot = ring_slot_of(P, clock + 1ull);
         s0 = (int)((clock + 2ull) % (uint64_t)sh.W);
         MetricAcc acc;
+        StepConsts K = FS.K;
+        K.T0 = f_T0;
         for (int j = tid; j < kFusedMaxEnvs; j += kCoopThreads) {          // (the launcher guarantees the CTA owns <= 256 envs)
             const int64_t env = tile_env0(j / unit_envs) + (j % unit_envs);
             if (env < env_end) {
-                const StepThreadOut r = step_env(P, D, S, FS.actions, FS.K, FS.O, tick, ring_slot, FS.autoreset, (int)env, acc, f_pos);
+                const StepThreadOut r = step_env_now(P, D, S, FS.actions, K, FS.O, tick, ring_slot, FS.autoreset, (int)env, acc, f_pos);
                 f_live[j] = sh.W - 1 - (r.idx - r.ep_start);             // window row of ep_start (<= 0: the whole window is live)
                 f_src[j] = (unsigned long long)window_src(D, sh, r.ds, r.idx + 1 - sh.W);
             }
@@ -493,7 +497,9 @@ static cudaError_t plan_tma(const ObsShape& sh, int n_envs, bool fused, TmaPlan*
         const int64_t units = ((int64_t)n_envs + u - 1) / u;
         const int64_t per_cta = (units + cap - 1) / cap;
         if (u == 8 && per_cta > 1) break;                  // quarter tiles only while every CTA gets at most one
-        if (best < 0 || per_cta * u < best) { best = per_cta * u; unit = u; }
+        // a smaller unit re-fetches the 32-env ring block once per unit (+5 % traffic per halving): it has to buy
+        // more than that in balance (C4: 1792 -> 1776 envs on the busiest CTA is not worth it, C3: 128 -> 112 is)
+        if (best < 0 || per_cta * u * 100 < best * 95) { best = per_cta * u; unit = u; }
     }
     const int64_t need = ((int64_t)n_envs + unit - 1) / unit;
     const int64_t waves = (need + cap - 1) / cap;

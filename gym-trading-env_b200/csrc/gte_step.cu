@@ -17,15 +17,19 @@ namespace gte {
 // (see step_tiles_per_cta).
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(kStepThreads, MIN_CTAS)
-step_kernel(const GteParams P, const GteData D, const GteState S, const void* __restrict__ actions, const StepConsts K,
+step_kernel(const GteParams P, const GteData D, const GteState S, const void* __restrict__ actions, const StepConsts K0,
             const GteStepOut O, int autoreset, int tiles_per_cta, int env_begin, int env_end, int chunk_flags,
             float* __restrict__ obs_rows) {
     // the positions table in shared memory: a per-lane index into the kernel-parameter constant bank would be
     // replayed once per distinct address
     __shared__ double s_pos[GTE_MAX_POSITIONS];
+    __shared__ int s_T0;
     if (threadIdx.x < GTE_MAX_POSITIONS) s_pos[threadIdx.x] = P.positions[threadIdx.x];
+    if (threadIdx.x == 0) s_T0 = D.lengths[0];          // static data: may be read before the dependency wait
     __syncthreads();
     pdl_wait();                              // everything below reads what the previous kernel of the stream wrote
+    StepConsts K = K0;
+    K.T0 = s_T0;
     MetricAcc acc;
     const uint64_t tick = *S.tick;
     // the slot this iteration's row goes to: the first env range of an iteration still sees the old clock
@@ -34,7 +38,7 @@ step_kernel(const GteParams P, const GteData D, const GteState S, const void* __
     for (int t = 0; t < tiles_per_cta; ++t) {
         const int64_t i = base0 + (int64_t)t * kStepThreads + threadIdx.x;
         if (i < env_end) {
-            const StepThreadOut r = step_env(P, D, S, actions, K, O, tick, ring_slot, autoreset, (int)i, acc, s_pos);
+            const StepThreadOut r = step_env_now(P, D, S, actions, K, O, tick, ring_slot, autoreset, (int)i, acc, s_pos);
             if (obs_rows != nullptr) {
                 // windows=None (environments.py:156-157): the observation is the single row idx, written by the
                 // env's own thread -> one launch per lockstep iteration at small N
@@ -146,6 +150,7 @@ StepConsts make_step_consts(const GteParams& P) {
     StepConsts K;
     K.done_thr = no_thr ? NAN : done_threshold(P.v0, P.done_ratio);
     K.action_bytes = P.action_bytes == 0 ? 8 : P.action_bytes;
+    K.T0 = 0;                                // filled in on the device
     return K;
 }
 
@@ -200,10 +205,8 @@ cudaError_t launch_step_range(const GteParams& P, const GteData& D, const GteSta
     }
     // 4 CTAs/SM (64 registers, a few spills) pays once the grid runs in several waves; a grid that is resident at once
     // is latency-bound and runs the spill-free 3-CTA build a little faster (C3: 47.3 -> 46.6 us per iteration)
-    if (min_ctas >= 4 && grid > num_sms() * 3)
-        return launch_pdl(step_kernel<4>, dim3(grid), dim3(kStepThreads), 0, stream, P, D, S, actions, K, O, autoreset, tpc,
-                          env_begin, env_end, chunk_flags, obs_rows);
-    return launch_pdl(step_kernel<3>, dim3(grid), dim3(kStepThreads), 0, stream, P, D, S, actions, K, O, autoreset, tpc,
+    auto kern = (min_ctas >= 4 && grid > num_sms() * 3) ? step_kernel<4> : step_kernel<3>;
+    return launch_pdl(kern, dim3(grid), dim3(kStepThreads), 0, stream, P, D, S, actions, K, O, autoreset, tpc,
                       env_begin, env_end, chunk_flags, obs_rows);
 }
 

@@ -35,35 +35,59 @@ struct StepConsts {
     double done_thr;      // largest double x with fl(x / v0) <= done_ratio (IEEE division is monotonic in x), or NaN:
                           // `valuation <= done_thr` is then bit-for-bit `valuation / v0 <= done_ratio` (:246) without the divide
     int action_bytes;     // 1, 2, 4 or 8
+    int T0;               // len(df) of dataset 0, filled in ON THE DEVICE by the kernel prologue (lengths is device memory)
 };
 
-__device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteData& D, const GteState& S,
-                                                  const void* __restrict__ actions, const StepConsts& K,
-                                                  const GteStepOut& O, uint64_t tick, int ring_slot, int autoreset,
-                                                  int i, MetricAcc& acc, const double* __restrict__ pos_tab) {
+// What one transition reads: the env's state, its action (already range-checked) and the two prices it trades /
+// is valued at, split from the arithmetic.
+struct EnvIn {
     EnvRegs e;
-    e.pf.asset = S.asset[i];
-    e.pf.fiat = S.fiat[i];
-    e.pf.ia = S.interest_asset[i];
-    e.pf.ifi = S.interest_fiat[i];
-    e.pos_idx = S.pos_idx[i];
-    e.step = S.step[i];
-    e.ep_start = S.ep_start[i];
-    e.ds = (P.n_datasets > 1) ? S.dataset_idx[i] : 0;
-    int64_t a = load_action(actions, K.action_bytes, i);
+    int a;                // action: index into positions, or -1 = hold (out-of-range and negative actions included)
+    int idx, T;           // row before advancing (clamped to T-2 when the caller stepped past the data), dataset length
+};
 
-    const double* __restrict__ price = D.price + (int64_t)e.ds * P.t_stride;
-    const int T = D.lengths[e.ds];
-    int idx = e.ep_start + e.step;
-    if (idx + 1 >= T) {              // stepping past the end of the data without a reset (caller bug)
-        atomicOr(S.error_flag, GTE_E_PAST_END);
-        idx = T - 2;
-    }
-    if (a >= (int64_t)P.n_positions) { atomicOr(S.error_flag, GTE_E_ACTION_RANGE); a = -1; }
+__device__ __forceinline__ EnvIn load_env(const GteParams& P, const GteData& D, const GteState& S,
+                                          const void* __restrict__ actions, const StepConsts& K, int64_t i) {
+    EnvIn in;
+    in.e.pf.asset = S.asset[i];
+    in.e.pf.fiat = S.fiat[i];
+    in.e.pf.ia = S.interest_asset[i];
+    in.e.pf.ifi = S.interest_fiat[i];
+    in.e.pos_idx = S.pos_idx[i];
+    in.e.step = S.step[i];
+    in.e.ep_start = S.ep_start[i];
+    in.e.ds = (P.n_datasets > 1) ? S.dataset_idx[i] : 0;
+    const int64_t a = load_action(actions, K.action_bytes, i);
+    if (a >= (int64_t)P.n_positions) atomicOr(S.error_flag, GTE_E_ACTION_RANGE);
     if (P.strict_actions && a < -1) atomicOr(S.error_flag, GTE_E_NEGATIVE_ACTION);
+    in.a = (a < 0 || a >= (int64_t)P.n_positions) ? -1 : (int)a;           // :234 None = hold
+    // one dataset: its length was read once per CTA (K.T0) instead of once per env behind the state loads
+    in.T = (P.n_datasets > 1) ? D.lengths[in.e.ds] : K.T0;
+    in.idx = in.e.ep_start + in.e.step;
+    if (in.idx + 1 >= in.T) {        // stepping past the end of the data without a reset (caller bug)
+        atomicOr(S.error_flag, GTE_E_PAST_END);
+        in.idx = in.T - 2;
+    }
+    return in;
+}
 
-    const double p0 = __ldg(price + idx);                                    // price BEFORE advancing (:204-207)
-    const double p1 = __ldg(price + idx + 1);
+// price BEFORE advancing (:204-207) and the price the new row is valued at (:239)
+__device__ __forceinline__ void load_prices(const GteParams& P, const GteData& D, const EnvIn& in, double& p0, double& p1) {
+    const double* __restrict__ price = D.price + (int64_t)in.e.ds * P.t_stride;
+    p0 = __ldg(price + in.idx);
+    p1 = __ldg(price + in.idx + 1);
+}
+
+// The arithmetic of one transition.
+__device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteData& D, const GteState& S,
+                                                  const StepConsts& K, const GteStepOut& O, uint64_t tick, int ring_slot,
+                                                  int autoreset, int i, const EnvIn& in, const double p0, const double p1,
+                                                  MetricAcc& acc, const double* __restrict__ pos_tab) {
+    EnvRegs e = in.e;
+    const int a = in.a;
+    const int T = in.T;
+    int idx = in.idx;
+    const double* __restrict__ price = D.price + (int64_t)e.ds * P.t_stride;
     // history["portfolio_valuation", -2]: the previous row's valuation.  The state on entry is exactly
     // the state that row was valued with, at the same price, so it is recomputed bit-identically
     // instead of being stored; the first row of an episode holds portfolio_initial_value (:194).
@@ -74,7 +98,7 @@ __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteD
         const double target = pos_tab[a];
         if (target != pos_tab[e.pos_idx]) {                              // :213-215 value compare
             trade_to_position(e.pf, target, p0, P.fee, val0);                // :204-211
-            e.pos_idx = (int)a;
+            e.pos_idx = a;
         }
     }
     idx += 1;                                                                // :235
@@ -151,6 +175,17 @@ __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteD
     r.idx = idx; r.ep_start = e.ep_start; r.ds = e.ds;
     r.dyn_pos = dyn_pos; r.dyn_rp = dyn_rp;
     return r;
+}
+
+// load + transition of env i in one go (fused step+gather kernel)
+__device__ __forceinline__ StepThreadOut step_env_now(const GteParams& P, const GteData& D, const GteState& S,
+                                                      const void* __restrict__ actions, const StepConsts& K,
+                                                      const GteStepOut& O, uint64_t tick, int ring_slot, int autoreset,
+                                                      int i, MetricAcc& acc, const double* __restrict__ pos_tab) {
+    const EnvIn in = load_env(P, D, S, actions, K, i);
+    double p0, p1;
+    load_prices(P, D, in, p0, p1);
+    return step_env(P, D, S, K, O, tick, ring_slot, autoreset, i, in, p0, p1, acc, pos_tab);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -392,15 +392,18 @@ void orc_rollout_range(OrcEnv* e, int lo, int hi, const int64_t* actions, int n_
 }
 
 /* ------------------------------------------------------------------ CPU baseline driver (bench.py only) */
-/* The same rollout on n_threads host threads, each PINNED to one of the process's allowed CPUs and owning a contiguous
- * env slice (envs are independent: no barrier between iterations, like per-env worker processes of an
- * AsyncVectorEnv).  All threads start together behind a barrier; the return value is the wall time in seconds from
- * that barrier to the last thread's exit, measured here so that no interpreter overhead is inside it.
+/* The same rollout on n_threads host threads, each PINNED to one of the process's allowed CPUs.  Envs are independent,
+ * so there is no barrier between iterations (like the per-env worker processes of an AsyncVectorEnv): the envs are cut
+ * into chunks of ORC_CHUNK_ENVS that the threads claim from a shared counter and roll forward all `iters` iterations —
+ * a core that is briefly taken by something else then simply claims fewer chunks instead of holding the whole run up.
+ * All threads start together behind a barrier; the return value is the wall time in seconds from that barrier to the
+ * last thread's exit, measured here so that no interpreter overhead is inside it.
  * metrics: [n_threads][ORC_N_METRICS] partial sums. */
+#define ORC_CHUNK_ENVS 16
 typedef struct OrcWork {
-    OrcEnv* e; int lo, hi; const int64_t* actions; int n_sets, iters; uint64_t tick0;
+    OrcEnv* e; const int64_t* actions; int n_sets, iters; uint64_t tick0;
     float* obs; double* reward; uint8_t* terminated; uint8_t* truncated; double* metrics;
-    int cpu; pthread_barrier_t* bar;
+    int cpu; pthread_barrier_t* bar; int* next_chunk; int n_chunks;
 } OrcWork;
 
 static void* orc_worker(void* arg) {
@@ -412,8 +415,14 @@ static void* orc_worker(void* arg) {
         pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
     }
     pthread_barrier_wait(w->bar);
-    orc_rollout_range(w->e, w->lo, w->hi, w->actions, w->n_sets, w->iters, w->tick0, w->obs, w->reward,
-                      w->terminated, w->truncated, w->metrics);
+    for (;;) {
+        int c = __atomic_fetch_add(w->next_chunk, 1, __ATOMIC_RELAXED);
+        if (c >= w->n_chunks) break;
+        int lo = c * ORC_CHUNK_ENVS, hi = lo + ORC_CHUNK_ENVS;
+        if (hi > w->e->n_envs) hi = w->e->n_envs;
+        orc_rollout_range(w->e, lo, hi, w->actions, w->n_sets, w->iters, w->tick0, w->obs, w->reward,
+                          w->terminated, w->truncated, w->metrics);
+    }
     return 0;
 }
 
@@ -438,13 +447,14 @@ double orc_rollout_threads(OrcEnv* e, const int64_t* actions, int n_sets, int it
         for (int c = 0; c < 1024 && c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &allowed)) cpus[n_cpus++] = c;
     pthread_barrier_t bar;
     pthread_barrier_init(&bar, 0, (unsigned)n_threads + 1);
+    int next_chunk = 0;
+    int n_chunks = (e->n_envs + ORC_CHUNK_ENVS - 1) / ORC_CHUNK_ENVS;
     for (int t = 0; t < n_threads; ++t) {
-        w[t].e = e; w[t].lo = (int)(((int64_t)e->n_envs * t) / n_threads); w[t].hi = (int)(((int64_t)e->n_envs * (t + 1)) / n_threads);
-        w[t].actions = actions; w[t].n_sets = n_sets; w[t].iters = iters; w[t].tick0 = tick0;
+        w[t].e = e; w[t].actions = actions; w[t].n_sets = n_sets; w[t].iters = iters; w[t].tick0 = tick0;
         w[t].obs = obs; w[t].reward = reward; w[t].terminated = terminated; w[t].truncated = truncated;
         w[t].metrics = metrics + (int64_t)t * ORC_N_METRICS;
         w[t].cpu = n_cpus > 0 ? cpus[t % n_cpus] : -1;
-        w[t].bar = &bar;
+        w[t].bar = &bar; w[t].next_chunk = &next_chunk; w[t].n_chunks = n_chunks;
         pthread_create(&th[t], 0, orc_worker, &w[t]);
     }
     pthread_barrier_wait(&bar);

@@ -61,9 +61,9 @@ def test_make_vec_builds_a_stepping_vector_env_on_the_gpu():
                                  trading_fees=1e-4, max_episode_duration=40, verbose=0)
         assert isinstance(env, gymnasium.vector.VectorEnv) and env.unwrapped is env and env.num_envs == 256
         assert isinstance(env.single_action_space, gymnasium.spaces.Discrete) and env.single_action_space.n == 3
-        assert env.observation_space.shape == (256, 8, 7) and env.single_observation_space.shape == (8, 7)
+        assert env.observation_space.shape == (256, 8, 10) and env.single_observation_space.shape == (8, 10)
         obs, infos = env.reset(seed=3)
-        assert obs.shape == (256, 8, 7)
+        assert obs.shape == (256, 8, 10)
         for k in range(50):
             obs, rew, term, trunc, infos = env.step(torch.randint(0, 3, (256,), device=obs.device))
         assert float(env.get_metrics()["episodes"]) >= 256
