@@ -9,8 +9,8 @@ hand-written sm_100a CUDA kernels behind a C-ABI library (`include/gte_b200.h`).
     obs, infos = env.reset()
     obs, reward, terminated, truncated, infos = env.step(actions)     # CUDA tensors
 """
-from .data import (SeriesArrays, build_window_tables, frame_to_arrays, make_gbm_arrays,  # noqa: F401
-                   make_gbm_ohlcv, window_table_classes)
+from .data import (SeriesArrays, build_window_tables, frame_to_arrays, load_frame, make_gbm_arrays,  # noqa: F401
+                   make_gbm_ohlcv, reconcile_series, window_table_classes)
 
 __version__ = "0.1.0"
 

@@ -54,6 +54,56 @@ def frame_to_arrays(df: pd.DataFrame) -> SeriesArrays:
     return SeriesArrays(feats, price, feature_names, info, index)
 
 
+def load_frame(path: str) -> pd.DataFrame:
+    """One dataset file -> DataFrame.  ``*.pkl`` / ``*.pickle`` as the reference reads them (``pd.read_pickle``,
+    environments.py:391 — what its downloader writes, downloader.py:63-70); ``*.csv`` / ``*.csv.gz`` the way the
+    reference's examples load the bundled file (examples/example_environnement.py:11-14): a ``date`` column (or
+    ``timestamp`` / ``datetime``) becomes the parsed, sorted DatetimeIndex; ``*.parquet`` via pandas."""
+    low = path.lower()
+    if low.endswith((".pkl", ".pickle")):
+        return pd.read_pickle(path)
+    if low.endswith((".csv", ".csv.gz")):
+        df = pd.read_csv(path)
+        for c in ("date", "timestamp", "datetime", "Date"):
+            if c in df.columns:
+                df[c] = pd.to_datetime(df[c])
+                df = df.set_index(c).sort_index()
+                df.index.name = "date"
+                break
+        return df
+    if low.endswith(".parquet"):
+        return pd.read_parquet(path)
+    raise ValueError(f"unsupported dataset file type: {path} (expected .pkl, .csv or .parquet)")
+
+
+def reconcile_series(series, names=None):
+    """Make a list of staged datasets stackable into one device table: same static feature columns in the SAME order.
+
+    The reference builds one observation space from whatever frame it loaded first and simply breaks (shape mismatch in
+    ``_get_obs``) when a later frame has other feature columns.  Here the first dataset's feature names are the schema;
+    every other dataset is re-ordered BY NAME to match it, and a dataset that lacks one of them (or carries an extra
+    one) is refused with a message that names it.  Lengths may differ (ragged: each dataset keeps its own T); the info
+    columns (``data_*`` of the info dict) are reduced to those every dataset has.  Non-numeric columns never reach
+    this point (``frame_to_arrays`` keeps numeric columns only)."""
+    if not series:
+        return series
+    names = names or [f"dataset {k}" for k in range(len(series))]
+    schema = list(series[0].feature_names)
+    out = []
+    for srs, nm in zip(series, names):
+        have = list(srs.feature_names)
+        if have != schema:
+            missing, extra = [c for c in schema if c not in have], [c for c in have if c not in schema]
+            if missing or extra or len(have) != len(schema):
+                raise ValueError(f"{nm}: feature columns differ from the first dataset's — missing {missing}, "
+                                 f"unexpected {extra} (expected {schema})")
+            order = [have.index(c) for c in schema]
+            srs = SeriesArrays(np.ascontiguousarray(srs.features[:, order]), srs.price, schema, srs.info, srs.index)
+        out.append(srs)
+    common = [c for c in out[0].info if all(c in s.info for s in out)]
+    return [SeriesArrays(s.features, s.price, s.feature_names, {c: s.info[c] for c in common}, s.index) for s in out]
+
+
 def make_gbm_ohlcv(T: int = 100_000, seed: int = 0, sigma: float = 0.002) -> pd.DataFrame:
     """Synthetic GBM OHLCV frame with 8 static ``feature_*`` columns.
 

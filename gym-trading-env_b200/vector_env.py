@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .data import SeriesArrays, build_window_tables, frame_to_arrays
+from .data import SeriesArrays, build_window_tables, frame_to_arrays, load_frame, reconcile_series
 
 
 # host action arrays cross PCIe in their own width and are widened by the step kernel's load (GteParams.action_bytes)
@@ -1199,7 +1199,11 @@ class MultiDatasetTradingVectorEnv(TradingVectorEnv):
     index and least-used rotation state (`next_dataset`, :380-391) and switches every
     ``episodes_between_dataset_switch`` episodes inside the in-kernel auto-reset.
 
-    ``datasets=[DataFrame | SeriesArrays, ...]`` may be given instead of ``dataset_dir``.
+    ``dataset_dir`` is a glob like the reference's (``"data/*.pkl"``); ``.csv`` / ``.parquet`` files are accepted too.
+    The datasets may have different lengths (each keeps its own T) and their columns in different orders: feature
+    columns are matched by name against the first dataset, non-numeric columns are ignored, and a dataset whose feature
+    set differs is refused by name (``reconcile_series``).  ``datasets=[DataFrame | SeriesArrays, ...]`` may be given
+    instead of ``dataset_dir``.
     """
 
     def __init__(self, dataset_dir=None, *args, preprocess=lambda df: df, episodes_between_dataset_switch=1,
@@ -1210,14 +1214,17 @@ class MultiDatasetTradingVectorEnv(TradingVectorEnv):
         if self.episodes_between_dataset_switch < 1:
             raise ValueError("episodes_between_dataset_switch must be >= 1")
         if datasets is None:
-            import pandas as pd
             self.dataset_pathes = sorted(_glob.glob(self.dataset_dir))
             if len(self.dataset_pathes) == 0:
                 raise FileNotFoundError(f"No dataset found with the path : {self.dataset_dir}")   # :376
-            datasets = [self.preprocess(pd.read_pickle(p)) for p in self.dataset_pathes]         # :391
+            # :391 read_pickle -> preprocess; .csv / .parquet files are read the way the reference's examples do
+            frames = [self.preprocess(load_frame(p)) for p in self.dataset_pathes]
             self.dataset_names = [Path(p).name for p in self.dataset_pathes]
         else:
-            datasets = [d if isinstance(d, SeriesArrays) else self.preprocess(d) for d in datasets]
-            self.dataset_names = [f"dataset_{k}" for k in range(len(datasets))]
+            frames = [d if isinstance(d, SeriesArrays) else self.preprocess(d) for d in datasets]
+            self.dataset_names = [f"dataset_{k}" for k in range(len(frames))]
+        # ragged lengths are fine (per-dataset T); feature columns are matched by NAME across the datasets
+        datasets = reconcile_series([d if isinstance(d, SeriesArrays) else frame_to_arrays(d) for d in frames],
+                                    self.dataset_names)
         super().__init__(list(datasets), *args, _multi_dataset=True,
                          _episodes_between_dataset_switch=self.episodes_between_dataset_switch, **kwargs)

@@ -289,3 +289,26 @@ def test_fused_single_launch_equals_two_plain_launches(n_envs, windows, pos):
     assert float(fused._metrics_total[0]) >= 2 * n_envs
     assert int(fused._ring_clock) == int(plain._ring_clock) == 50 and int(fused._tick_dev) == int(plain._tick_dev)
     fused.check_errors()
+
+
+def test_dataset_dir_with_mixed_files_and_shuffled_columns_equals_in_memory_datasets(tmp_path):
+    """Ragged ingestion end to end: a directory holding a pickle and a CSV of different lengths whose columns come in
+    different orders gives the same env as the reconciled in-memory frames."""
+    import gym_trading_env_b200 as gte
+    a, b = gte.make_gbm_ohlcv(400, seed=31), gte.make_gbm_ohlcv(650, seed=32)
+    a.to_pickle(tmp_path / "0_a.pkl")
+    shuffled = b[list(reversed(b.columns))]
+    shuffled.to_pickle(tmp_path / "1_b.pkl")
+    kw = dict(positions=[-1, 0, 1], windows=8, max_episode_duration=25, num_envs=512, seed=9, verbose=0, **FEES)
+    disk = gte.MultiDatasetTradingVectorEnv(str(tmp_path / "*.pkl"), **kw)
+    mem = gte.MultiDatasetTradingVectorEnv(datasets=[a, b], **kw)
+    assert disk.dataset_names == ["0_a.pkl", "1_b.pkl"] and disk._lengths_np.tolist() == [400, 650]
+    o0, _ = disk.reset()
+    o1, _ = mem.reset()
+    assert torch.equal(o0.view(torch.int32), o1.view(torch.int32))
+    acts = _acts(512, 60, 3, disk.device, seed=3)
+    for k in range(60):
+        r0, r1 = disk.step(acts[k]), mem.step(acts[k])
+        assert torch.equal(r0[0].view(torch.int32), r1[0].view(torch.int32)) and torch.equal(r0[1], r1[1])
+        assert torch.equal(disk._dataset_idx, mem._dataset_idx)
+    assert set(disk._dataset_idx.cpu().tolist()) == {0, 1}

@@ -106,3 +106,32 @@ def test_sb3_view_exposes_the_vecenv_surface_without_touching_the_gpu():
     assert v.env_is_wrapped(object) == [False] * 3 and v.get_attr("num_envs", 1) == [3]
     v.close()
     assert env.closed
+
+
+def test_dataset_files_are_loaded_and_reconciled_by_column_name(tmp_path):
+    """f4 ingestion (reference: MultiDatasetTradingEnv glob + read_pickle + preprocess, environments.py:365-391;
+    examples/example_environnement.py:11-14 for the CSV form): pickles and CSVs, ragged lengths, shuffled column
+    order, a non-numeric column — staged into arrays that share one feature schema; a dataset with another feature
+    set is refused by name."""
+    import pandas as pd
+    a = gte.make_gbm_ohlcv(300, seed=1)
+    b = gte.make_gbm_ohlcv(450, seed=2)
+    b = b[list(reversed(b.columns))].copy()                      # same columns, other order
+    b["exchange"] = "binance"                                    # non-numeric: ignored
+    a.to_pickle(tmp_path / "a.pkl")
+    b.reset_index().rename(columns={"index": "date"}).to_csv(tmp_path / "b.csv", index=False)
+    fa, fb = gte.load_frame(str(tmp_path / "a.pkl")), gte.load_frame(str(tmp_path / "b.csv"))
+    assert isinstance(fb.index, pd.DatetimeIndex) and fb.index.is_monotonic_increasing and len(fb) == 450
+    sa, sb = gte.frame_to_arrays(fa), gte.frame_to_arrays(fb)
+    assert sb.feature_names == list(reversed(sa.feature_names)) and "exchange" not in sb.info
+    ra, rb = gte.reconcile_series([sa, sb], ["a.pkl", "b.csv"])
+    assert ra.feature_names == rb.feature_names == sa.feature_names and (ra.length, rb.length) == (300, 450)
+    want = gte.frame_to_arrays(gte.make_gbm_ohlcv(450, seed=2))
+    np.testing.assert_allclose(rb.features, want.features, rtol=1e-6)      # CSV text round trip: to float32 rounding
+    np.testing.assert_allclose(rb.price, want.price, rtol=1e-12)
+    assert set(ra.info) == set(rb.info) == {"open", "high", "low", "close", "volume"}
+    c = gte.frame_to_arrays(gte.make_gbm_ohlcv(200, seed=3).drop(columns=["feature_vol_64"]))
+    with pytest.raises(ValueError, match="c.pkl.*feature_vol_64"):
+        gte.reconcile_series([sa, c], ["a.pkl", "c.pkl"])
+    with pytest.raises(ValueError, match="unsupported dataset file type"):
+        gte.load_frame(str(tmp_path / "x.xlsx"))
