@@ -388,7 +388,8 @@ def main():
                        "host_bind": host_bind},
             "repeats": m["repeats"], "spread": m["spread"],
             "clocks": m["clocks"], "e2e": e2e.get("e2e"), "e2e_gymnasium_dtypes": e2e.get("e2e_gymnasium_dtypes"),
-            "e2e_other_host_io": e2e.get("e2e_other_host_io"), "e2e_full_obs_to_host": e2e.get("e2e_full_obs_to_host"),
+            "e2e_other_host_io": e2e.get("e2e_other_host_io"), "e2e_server": e2e.get("e2e_server"),
+            "e2e_full_obs_to_host": e2e.get("e2e_full_obs_to_host"),
             "gpu_launches": m["launches_per_step"] * args.steps * m["repeats"]["n"], "roofline": m["roofline"], "cpu_baseline": cpu,
         }
         if latency is not None:
@@ -599,7 +600,7 @@ def e2e_legs(ctx, env, actions, wl):
                 "d2h_bytes_per_step": host_result_layout(N)[3] + (env._obs.numel() * 4 if mode == "numpy" else 0),
                 "steps": n_it, "us_per_step": 1e6 * float(tt.item()) / n_it,
                 "timing": "host wall clock around the step() calls, max over ranks", "mode": mode,
-                "host_io": ("copy" if mode == "numpy" else {1: "copy", 2: "mapped"}.get(env._io_mode_used.value, "?")),
+                "host_io": ("copy" if mode == "numpy" else {1: "copy", 2: "mapped", 3: "server"}.get(env._io_mode_used.value, "?")),
                 "action_dtype": str(acts_h.dtype)}
 
     out = {}
@@ -617,6 +618,11 @@ def e2e_legs(ctx, env, actions, wl):
         out["e2e_other_host_io"] = time_e2e("hybrid", other, torch.int8, min(n_it, 50) if N >= 2 ** 20 else n_it)
         out["e2e_other_host_io"]["note"] = ("the OTHER host-IO mechanism forced, for comparison (mapped = the step kernel reads the "
                                             "actions from, and writes its results into, pinned host memory; copy = copy engines)")
+        if wl["windows"] is None and N <= 32768:
+            out["e2e_server"] = time_e2e("hybrid", "server", torch.int8, n_it)
+            out["e2e_server"]["note"] = ("host_io='server': a RESIDENT kernel answers every step through mapped host memory — no kernel "
+                                         "launch, driver call or interrupt per step (opt-in: it occupies its SMs while it waits)")
+            env._lib.gte_serve_stop()
         out["e2e_full_obs_to_host"] = time_e2e("numpy", "auto", torch.int8, args.e2e_steps if N >= 2 ** 20 else 50)
         out["e2e_full_obs_to_host"]["note"] = ("VectorEnv(output='numpy'): the full observation batch is also copied to pinned host "
                                                "memory every step; bounded by PCIe (~52 GB/s), reported for transparency")

@@ -85,8 +85,8 @@ class GteHostIO(C.Structure):
     ]
 
 
-IO_AUTO, IO_COPY, IO_MAPPED = 0, 1, 2
-IO_MODES = {"auto": IO_AUTO, "copy": IO_COPY, "mapped": IO_MAPPED}
+IO_AUTO, IO_COPY, IO_MAPPED, IO_SERVER = 0, 1, 2, 3
+IO_MODES = {"auto": IO_AUTO, "copy": IO_COPY, "mapped": IO_MAPPED, "server": IO_SERVER}
 E_ACTION_RANGE, E_PAST_END, E_PLAN_RANGE, E_PLAN_EXHAUSTED, E_NEGATIVE_ACTION = 1, 2, 4, 8, 16
 
 
@@ -105,7 +105,7 @@ class GteInfo(C.Structure):
 
 
 EXPORTS = ["gte_version", "gte_last_error", "gte_build_id", "gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs",
-           "gte_step_host", "gte_rollout", "gte_info", "gte_obs_variant_for", "gte_default_chunks", "gte_struct_size",
+           "gte_step_host", "gte_serve_stop", "gte_rollout", "gte_info", "gte_obs_variant_for", "gte_default_chunks", "gte_struct_size",
            "gte_step_obs_launches"]
 
 
@@ -189,9 +189,11 @@ def load():
     lib.gte_obs_variant_for.argtypes = [P(GteParams), P(GteData)]
     lib.gte_step_obs_launches.argtypes = [P(GteParams), P(GteData), C.c_int, C.c_int]
     lib.gte_step_obs_launches.restype = C.c_int
+    lib.gte_serve_stop.argtypes = []
+    lib.gte_serve_stop.restype = C.c_int
     lib.gte_default_chunks.argtypes = [C.c_int]
     lib.gte_default_chunks.restype = C.c_int
-    for name in ("gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs", "gte_step_host", "gte_rollout", "gte_info",
+    for name in ("gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs", "gte_step_host", "gte_serve_stop", "gte_rollout", "gte_info",
                  "gte_obs_variant_for"):
         getattr(lib, name).restype = C.c_int
     lib.gte_struct_size.argtypes = [C.c_int]

@@ -51,6 +51,9 @@ int check_common(const char* fn, const GteParams* p, const GteData* d, const Gte
     GTE_REQUIRE(fn, p->action_bytes == 0 || p->action_bytes == 1 || p->action_bytes == 2 || p->action_bytes == 4 || p->action_bytes == 8);
     for (int c = 0; c < 4; ++c)          // copy c starts 4c bytes before a 16-byte boundary (cp.async.bulk / ld.v4 fault otherwise)
         GTE_REQUIRE(fn, d->window_table[c] == nullptr || ((reinterpret_cast<uintptr_t>(d->window_table[c]) + 4u * c) & 15u) == 0);
+    // a resident server kernel (GTE_IO_SERVER) owns the env state: every entry point but gte_step_host stops it first
+    if (std::strcmp(fn, "gte_step_host") != 0)
+        if (int rc = check_cuda(fn, gte::serve_quiesce())) return rc;
     return GTE_OK;
 }
 
@@ -126,7 +129,7 @@ int gte_step_host(const GteParams* params, const GteData* data, const GteState* 
     if (int rc = check_common("gte_step_host", params, data, state)) return rc;
     GTE_REQUIRE("gte_step_host", io != nullptr && io->actions != nullptr && io->results != nullptr);
     if (int rc = check_step_out("gte_step_host", io->actions, out, true)) return rc;
-    GTE_REQUIRE("gte_step_host", io->mode >= GTE_IO_AUTO && io->mode <= GTE_IO_MAPPED);
+    GTE_REQUIRE("gte_step_host", io->mode >= GTE_IO_AUTO && io->mode <= GTE_IO_SERVER);
     GTE_REQUIRE("gte_step_host", (reinterpret_cast<uintptr_t>(io->results) & 7u) == 0);
     if (gte::host_io_mode(*params, io->mode) == GTE_IO_COPY)
         GTE_REQUIRE("gte_step_host", io->dev_actions != nullptr && io->dev_results != nullptr &&
@@ -136,6 +139,8 @@ int gte_step_host(const GteParams* params, const GteData* data, const GteState* 
     return check_cuda("gte_step_host", gte::launch_step_host(*params, *data, *state, *io, *out, obs, autoreset, variant,
                                                              mode_used, static_cast<cudaStream_t>(stream)));
 }
+
+int gte_serve_stop(void) { return check_cuda("gte_serve_stop", gte::serve_quiesce()); }
 
 int gte_rollout(const GteParams* params, const GteData* data, const GteState* state, const void* actions,
                 int n_steps, const GteStepOut* out, float* obs, int keep_obs, int autoreset, int variant, void* stream) {

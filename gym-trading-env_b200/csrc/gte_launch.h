@@ -52,6 +52,7 @@ cudaError_t launch_fused_step_obs(const GteParams& P, const GteData& D, const Gt
 bool step_obs_is_fused(const GteParams& P, const GteData& D, int variant);
 int default_chunks(int n_envs);
 int host_io_mode(const GteParams& P, int mode);
+cudaError_t serve_quiesce();
 cudaError_t launch_step_obs(const GteParams& P, const GteData& D, const GteState& S, const void* actions,
                             const GteStepOut& O, float* obs, int autoreset, int variant, int n_chunks,
                             cudaStream_t stream);

@@ -6,6 +6,7 @@
 // include/gte_b200.h for the boundary and DESIGN.md for the data layout / roofline.
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <immintrin.h>
 
 #include "gte_step_env.cuh"
@@ -51,6 +52,170 @@ step_kernel(const GteParams P, const GteData D, const GteState S, const void* __
         }
     }
     reduce_metrics<kStepThreads>(acc, O, S, chunk_flags);
+}
+
+// K lockstep iterations in ONE launch (open-loop action stream, batches that fit the GPU at once): one thread per env,
+// the env's state stays in REGISTERS for all K iterations and nothing is exchanged between the CTAs on the way — the
+// Philox tick and the ring slot of iteration k are tick0 + k / clock0 + 1 + k, and the episode metrics are folded once
+// at the end (all iterations but the last into metrics_total, the last one into metrics_step as well).  An iteration
+// then costs the transition's own dependency chain (~1.5 us) instead of a kernel launch (~8 us).
+// Every per-env output array of O holds n_steps consecutive copies, iteration k writing copy k (gte_rollout).
+// obs_rows (windows == 0 only): the one-row observations, every iteration (keep_obs) or the last one.
+__global__ void __launch_bounds__(kStepThreads, 2)
+rollout_kernel(const GteParams P, const GteData D, const GteState S, const void* __restrict__ actions, const StepConsts K0,
+               const GteStepOut O, int autoreset, int n_steps, int keep_obs, float* __restrict__ obs_rows) {
+    __shared__ double s_pos[GTE_MAX_POSITIONS];
+    __shared__ int s_T0;
+    if (threadIdx.x < GTE_MAX_POSITIONS) s_pos[threadIdx.x] = P.positions[threadIdx.x];
+    if (threadIdx.x == 0) s_T0 = D.lengths[0];
+    __syncthreads();
+    pdl_wait();
+    StepConsts K = K0;
+    K.T0 = s_T0;
+    const int64_t N = P.n_envs;
+    const int64_t i = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
+    const bool valid = i < N;
+    const int64_t ii = valid ? i : N - 1;                    // out-of-range threads shadow the last env and store nothing
+    const uint64_t tick0 = __ldcg(S.tick), clock0 = __ldcg(S.ring_clock);
+    const int ab = K.action_bytes, F = P.n_static + P.n_dyn;
+    MetricAcc acc, acc_prev;
+    EnvRegs e = load_env_regs(P, S, ii);
+    int64_t a_next = load_action(actions, ab, ii);
+    for (int k = 0; k < n_steps; ++k) {
+        const int64_t a = a_next;
+        if (k + 1 < n_steps) a_next = load_action(actions, ab, (int64_t)(k + 1) * N + ii);   // in flight during the transition
+        if (k == n_steps - 1) { acc_prev = acc; acc = MetricAcc(); }
+        if (valid) {
+            const EnvIn in = make_env_in(P, D, S, K, e, a);
+            double p0, p1;
+            load_prices(P, D, in, p0, p1);
+            GteStepOut o = O;
+            o.reward += (int64_t)k * N; o.terminated += (int64_t)k * N; o.truncated += (int64_t)k * N;
+            if (o.valuation) o.valuation += (int64_t)k * N;
+            if (o.real_position) o.real_position += (int64_t)k * N;
+            if (o.info_idx) o.info_idx += (int64_t)k * N;
+            if (o.info_step) o.info_step += (int64_t)k * N;
+            if (o.pre_reset_portfolio) o.pre_reset_portfolio += (int64_t)k * 4 * N;
+            const StepThreadOut r = step_env<false>(P, D, S, K, o, tick0 + (uint64_t)k, ring_slot_of(P, clock0 + 1ull + (uint64_t)k),
+                                                    autoreset, (int)i, in, p0, p1, acc, s_pos, &e);
+            if (obs_rows != nullptr && (keep_obs || k == n_steps - 1)) {
+                const float* __restrict__ f = D.features + ((int64_t)r.ds * P.t_stride + r.idx) * P.n_static;
+                float* __restrict__ orow = obs_rows + (keep_obs ? (int64_t)k * N * F : 0) + i * F;
+                for (int c = 0; c < P.n_static; ++c) orow[c] = __ldg(f + c);
+                if (P.n_dyn > 0) { orow[P.n_static] = r.dyn_pos; orow[P.n_static + 1] = r.dyn_rp; }
+            }
+        }
+    }
+    if (valid) store_env(S, i, e);
+    reduce_metrics<kStepThreads>(acc_prev, O, S, kChunkTotalOnly, 0);
+    reduce_metrics<kStepThreads>(acc, O, S, kChunkFirst | kChunkLast, 1, (unsigned)n_steps);
+}
+
+// ---- resident "env server" for a HOST policy at small N (gte_step_host, GTE_IO_SERVER) -----------------------------
+// A synchronous host step costs launch -> run -> completion -> wake-up (~20 us on this box) however small the kernel.
+// The server kernel is launched ONCE and stays resident: every iteration the host writes its actions into mapped pinned
+// memory and bumps ctl->go; CTA 0 polls that word over PCIe and hands the command to the other CTAs through a word in
+// device memory; every thread advances its env (actions read from, results written straight into, mapped host memory)
+// and the last CTA publishes the iteration's sequence number to the host, which polls it.  No launch, no driver call
+// and no interrupt on the path.  The kernel leaves by itself when told to (ctl->stop), or when no request arrived for
+// idle_ns — so a cudaDeviceSynchronize() elsewhere in the process waits at most that long — and tells the host
+// (ctl->alive = 0), which simply launches it again with the next request.
+struct ServeCtl {                // pinned, mapped host memory, owned by the library (one per device)
+    volatile uint32_t go;        // host -> device: sequence number of the requested iteration
+    volatile uint32_t stop;      // host -> device: leave now
+    volatile uint32_t alive;     // host sets 1 before a launch, the kernel sets 0 on its way out
+    uint32_t pad[13];
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const volatile uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// an element of the host's action array: never through a cache that could hold last iteration's line
+__device__ __forceinline__ int64_t load_action_volatile(const void* actions, int bytes, int64_t i) {
+    switch (bytes) {
+        case 1: return (int64_t) __ldcv(reinterpret_cast<const signed char*>(actions) + i);
+        case 2: return (int64_t) __ldcv(reinterpret_cast<const short*>(actions) + i);
+        case 4: return (int64_t) __ldcv(reinterpret_cast<const int*>(actions) + i);
+        default: return (int64_t) __ldcv(reinterpret_cast<const long long*>(actions) + i);
+    }
+}
+
+__global__ void __launch_bounds__(kStepThreads, 2)
+serve_kernel(const GteParams P, const GteData D, const GteState S, const void* actions, const StepConsts K0,
+             const GteStepOut O, int autoreset, float* __restrict__ obs_rows, ServeCtl* ctl, unsigned long long* dctl,
+             uint32_t first_seq, unsigned long long idle_ns) {
+    __shared__ double s_pos[GTE_MAX_POSITIONS];
+    __shared__ int s_T0;
+    __shared__ int s_cmd;
+    if (threadIdx.x < GTE_MAX_POSITIONS) s_pos[threadIdx.x] = P.positions[threadIdx.x];
+    if (threadIdx.x == 0) s_T0 = D.lengths[0];
+    __syncthreads();
+    StepConsts K = K0;
+    K.T0 = s_T0;
+    const int64_t i = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
+    const bool valid = i < P.n_envs;
+    const int F = P.n_static + P.n_dyn;
+    for (uint32_t seq = first_seq;; ++seq) {
+        // ---- wait for the host: CTA 0 watches the mapped control block, the others a word in device memory
+        if (threadIdx.x == 0) {
+            int cmd = 0;
+            if (blockIdx.x == 0) {
+                const unsigned long long t0 = global_timer_ns();
+                for (;;) {
+                    if (ld_acquire_sys_u32(&ctl->go) == seq) { cmd = 1; break; }
+                    if (ld_acquire_sys_u32(&ctl->stop) != 0u || global_timer_ns() - t0 > idle_ns) { cmd = 2; break; }
+                }
+                st_release_gpu_u64(dctl, ((unsigned long long)seq << 2) | (unsigned long long)cmd);
+            } else {
+                for (;;) {
+                    const unsigned long long v = ld_acquire_gpu_u64(dctl);
+                    if ((uint32_t)(v >> 2) == seq) { cmd = (int)(v & 3ull); break; }
+                }
+            }
+            s_cmd = cmd;
+        }
+        __syncthreads();
+        if (s_cmd != 1) break;
+        // ---- one lockstep iteration
+        MetricAcc acc;
+        const uint64_t tick = __ldcg(S.tick);
+        const int ring_slot = ring_slot_of(P, __ldcg(S.ring_clock) + 1ull);
+        if (valid) {
+            const int64_t a = load_action_volatile(actions, K.action_bytes, i);       // over PCIe, beside the state loads
+            const EnvIn in = make_env_in(P, D, S, K, load_env_regs<true>(P, S, i), a);
+            double p0, p1;
+            load_prices(P, D, in, p0, p1);
+            const StepThreadOut r = step_env(P, D, S, K, O, tick, ring_slot, autoreset, (int)i, in, p0, p1, acc, s_pos);
+            if (obs_rows != nullptr) {
+                const float* __restrict__ f = D.features + ((int64_t)r.ds * P.t_stride + r.idx) * P.n_static;
+                float* __restrict__ o = obs_rows + i * F;
+                for (int c = 0; c < P.n_static; ++c) o[c] = __ldg(f + c);
+                if (P.n_dyn > 0) { o[P.n_static] = r.dyn_pos; o[P.n_static + 1] = r.dyn_rp; }
+            }
+        }
+        GteStepOut o = O;
+        o.seq_value = seq;                               // what the last CTA publishes to the host when all is visible
+        reduce_metrics<kStepThreads>(acc, o, S, kChunkFirst | kChunkLast);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        __threadfence_system();
+        ctl->alive = 0u;
+    }
 }
 
 // TradingEnv.reset for the masked envs (environments.py:163-199, :393-400); `first` also performs
@@ -294,12 +459,28 @@ cudaError_t launch_step_obs(const GteParams& P, const GteData& D, const GteState
 }
 
 // ---- n_steps iterations from one host call (open-loop action stream) ------------------------------
+// Whether gte_rollout runs as ONE persistent launch (rollout_kernel): the batch must fit the GPU at once (every env owns
+// a thread for the whole call) and windowed observations must not be wanted for every iteration.
+bool rollout_is_persistent(const GteParams& P, int n_steps, int keep_obs) {
+    static const bool enabled = [] { const char* e = getenv("GTE_ROLLOUT_PERSISTENT"); return e == nullptr || atoi(e) != 0; }();
+    const int64_t grid = ((int64_t)P.n_envs + kStepThreads - 1) / kStepThreads;
+    return enabled && n_steps >= 2 && grid <= (int64_t)num_sms() * 2 && 2 * grid <= kMaxPartialRows &&
+           (P.windows == 0 || !keep_obs);
+}
+
 cudaError_t launch_rollout(const GteParams& P, const GteData& D, const GteState& S, const void* actions,
                            int n_steps, const GteStepOut& O, float* obs, int keep_obs, int autoreset, int variant,
                            cudaStream_t stream) {
     const int64_t N = P.n_envs;
     const int64_t obs_elems = N * (int64_t)(P.windows > 0 ? P.windows : 1) * (P.n_static + P.n_dyn);
     cudaError_t e;
+    if (rollout_is_persistent(P, n_steps, keep_obs)) {
+        const int grid = (int)((N + kStepThreads - 1) / kStepThreads);
+        e = launch_pdl(rollout_kernel, dim3(grid), dim3(kStepThreads), 0, stream, P, D, S, actions, make_step_consts(P), O,
+                       autoreset, n_steps, keep_obs, P.windows == 0 ? obs : (float*)nullptr);
+        if (e != cudaSuccess || P.windows == 0) return e;
+        return launch_obs_range(P, D, S, obs, variant, 0, P.n_envs, stream);     // the last iteration's windows
+    }
     for (int k = 0; k < n_steps; ++k) {
         GteStepOut o = O;                                   // iteration k writes copy k of every per-env array
         o.reward += k * N; o.terminated += k * N; o.truncated += k * N;
@@ -331,7 +512,14 @@ cudaError_t launch_rollout(const GteParams& P, const GteData& D, const GteState&
 struct HostIOStreams {
     cudaStream_t in = nullptr, out = nullptr;
     cudaEvent_t ev_in = nullptr, ev_step = nullptr;
-    uint32_t seq = 0;                // MAPPED mode: number of the last call (what its kernel writes into the block)
+    uint32_t seq = 0;                // MAPPED / SERVER mode: number of the last call (what its kernel writes into the block)
+    // SERVER mode: the resident kernel's stream, its mapped control block, the device-side command word, and what the
+    // running instance was launched for (a call with anything else quiesces it and launches a new one)
+    cudaStream_t serve = nullptr;
+    ServeCtl* ctl = nullptr;
+    unsigned long long* dctl = nullptr;
+    bool serving = false;
+    GteParams sp; GteData sd; GteState ss; GteStepOut so; const void* sa = nullptr; float* sobs = nullptr; int sauto = 0;
 };
 static HostIOStreams g_hio[16];
 
@@ -350,7 +538,34 @@ static cudaError_t hio_for_current_device(HostIOStreams** out) {
     return cudaSuccess;
 }
 
+// Stop the resident server kernel of the current device, if any: every other entry point of the library calls this
+// first, so the server never runs beside a kernel that touches the same env state.
+cudaError_t serve_quiesce() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return cudaSuccess;
+    HostIOStreams& h = g_hio[dev & 15];
+    if (!h.serving) return cudaSuccess;
+    h.ctl->stop = 1u;
+    const cudaError_t e = cudaStreamSynchronize(h.serve);
+    h.ctl->stop = 0u;
+    h.serving = false;
+    return e;
+}
+
+static unsigned long long serve_idle_ns() {
+    static const unsigned long long ns = [] { const char* e = getenv("GTE_SERVER_IDLE_US"); return (unsigned long long)(e ? atoll(e) : 2000) * 1000ull; }();
+    return ns;
+}
+
+bool serve_supported(const GteParams& P) {
+    // the whole batch must be resident at once (every env owns a thread for as long as the kernel lives), and the
+    // observation must be the step kernel's own one-row write (windows == 0)
+    const int64_t grid = ((int64_t)P.n_envs + kStepThreads - 1) / kStepThreads;
+    return P.windows == 0 && grid <= (int64_t)num_sms() && grid <= kMaxPartialRows;
+}
+
 int host_io_mode(const GteParams& P, int mode) {
+    if (mode == GTE_IO_SERVER) return serve_supported(P) ? GTE_IO_SERVER : GTE_IO_MAPPED;
     // measured on B200 (tools/host_path_probe.py, profiles/r02_tuning.md): with a gather behind the step kernel the
     // mapped writes delay it, so the copy engines win from ~40k envs on; without one mapped wins up to >= 64k envs
     static const long long forced_max = [] { const char* e = getenv("GTE_IO_MAPPED_MAX_BYTES"); return e ? atoll(e) : -1ll; }();
@@ -371,7 +586,7 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
     cudaError_t e;
     if ((e = hio_for_current_device(&h)) != cudaSuccess) return e;
     // the results of this iteration: one block, on the device (COPY) or straight in the mapped host memory (MAPPED)
-    char* blk = static_cast<char*>(mode == GTE_IO_MAPPED ? io.results : io.dev_results);
+    char* blk = static_cast<char*>(mode != GTE_IO_COPY ? io.results : io.dev_results);
     GteStepOut o = O;
     o.reward = reinterpret_cast<double*>(blk);
     o.terminated = reinterpret_cast<uint8_t*>(blk + GTE_HOST_RESULT_TERM_OFFSET(N));
@@ -379,7 +594,7 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
     o.error_out = reinterpret_cast<int32_t*>(blk + GTE_HOST_RESULT_ERROR_OFFSET(N));
     volatile uint32_t* seq_word = reinterpret_cast<volatile uint32_t*>(static_cast<char*>(io.results) + GTE_HOST_RESULT_SEQ_OFFSET(N));
     uint32_t seq = 0;
-    if (mode == GTE_IO_MAPPED) {
+    if (mode == GTE_IO_MAPPED || mode == GTE_IO_SERVER) {
         seq = ++h->seq ? h->seq : ++h->seq;                  // never 0
         *seq_word = 0;
         o.seq_out = const_cast<uint32_t*>(seq_word);
@@ -387,6 +602,51 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
     } else {
         o.seq_out = nullptr;
     }
+    if (mode == GTE_IO_SERVER) {
+        // ---- resident server: (re)launch it if it is not running for exactly these buffers, then hand it the request
+        if (h->serve == nullptr) {
+            if ((e = cudaStreamCreateWithFlags(&h->serve, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaHostAlloc(reinterpret_cast<void**>(&h->ctl), sizeof(ServeCtl), cudaHostAllocMapped)) != cudaSuccess) return e;
+            memset(h->ctl, 0, sizeof(ServeCtl));
+            if ((e = cudaMalloc(reinterpret_cast<void**>(&h->dctl), 64)) != cudaSuccess) return e;
+        }
+        const bool same = h->serving && memcmp(&h->sp, &P, sizeof(P)) == 0 && memcmp(&h->sd, &D, sizeof(D)) == 0 &&
+                          memcmp(&h->ss, &S, sizeof(S)) == 0 && h->so.metrics_step == O.metrics_step &&
+                          h->so.reward == o.reward && h->sa == io.actions && h->sobs == obs && h->sauto == autoreset;
+        if (h->serving && !same && (e = serve_quiesce()) != cudaSuccess) return e;
+        auto launch = [&]() -> cudaError_t {
+            cudaError_t le;
+            // behind whatever the caller enqueued on its stream so far (reset, previous iterations ...)
+            if ((le = cudaEventRecord(h->ev_step, stream)) != cudaSuccess) return le;
+            if ((le = cudaStreamWaitEvent(h->serve, h->ev_step, 0)) != cudaSuccess) return le;
+            if ((le = cudaMemsetAsync(h->dctl, 0, 64, h->serve)) != cudaSuccess) return le;
+            h->ctl->alive = 1u;
+            const int grid = (int)((N + kStepThreads - 1) / kStepThreads);
+            serve_kernel<<<grid, kStepThreads, 0, h->serve>>>(P, D, S, io.actions, make_step_consts(P), o, autoreset, obs, h->ctl,
+                                                              h->dctl, seq, serve_idle_ns());
+            if ((le = cudaGetLastError()) != cudaSuccess) return le;
+            h->serving = true;
+            h->sp = P; h->sd = D; h->ss = S; h->so = O; h->so.reward = o.reward; h->sa = io.actions; h->sobs = obs; h->sauto = autoreset;
+            return cudaSuccess;
+        };
+        if ((!h->serving || h->ctl->alive == 0u) && (e = launch()) != cudaSuccess) return e;
+        __atomic_thread_fence(__ATOMIC_RELEASE);             // the caller's action writes before the request
+        h->ctl->go = seq;
+        for (uint32_t spins = 1; *seq_word != seq; ++spins) {
+            _mm_pause();
+            if (h->ctl->alive == 0u) {                       // it left (idle time-out) — possibly without seeing this request
+                __atomic_thread_fence(__ATOMIC_ACQUIRE);
+                if (*seq_word == seq) break;
+                if ((e = cudaStreamSynchronize(h->serve)) != cudaSuccess) return e;
+                if ((e = launch()) != cudaSuccess) return e;
+            } else if ((spins & 0x3fffu) == 0 && (e = cudaStreamQuery(h->serve)) != cudaErrorNotReady && e != cudaSuccess) {
+                return e;                                    // a faulted kernel never answers
+            }
+        }
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
+        return cudaSuccess;
+    }
+    if ((e = serve_quiesce()) != cudaSuccess) return e;
     const void* actions = io.actions;
     if (mode == GTE_IO_COPY) {
         // the previous call returned only after ITS step kernel's results had reached the host, so dev_actions is

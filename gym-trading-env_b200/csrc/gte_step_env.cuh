@@ -6,7 +6,7 @@
 
 namespace gte {
 
-constexpr int kChunkFirst = 1, kChunkLast = 2;
+constexpr int kChunkFirst = 1, kChunkLast = 2, kChunkTotalOnly = 4;
 
 struct StepThreadOut {       // what the gather phase of the fused kernel needs from the step phase
     int idx, ep_start, ds;   // post-reset row index, episode start, dataset
@@ -38,6 +38,16 @@ struct StepConsts {
     int T0;               // len(df) of dataset 0, filled in ON THE DEVICE by the kernel prologue (lengths is device memory)
 };
 
+__device__ __forceinline__ void store_env(const GteState& S, int64_t i, const EnvRegs& e) {
+    S.asset[i] = e.pf.asset;
+    S.fiat[i] = e.pf.fiat;
+    S.interest_asset[i] = e.pf.ia;
+    S.interest_fiat[i] = e.pf.ifi;
+    S.pos_idx[i] = e.pos_idx;
+    S.step[i] = e.step;
+    S.ep_start[i] = e.ep_start;
+}
+
 // What one transition reads: the env's state, its action (already range-checked) and the two prices it trades /
 // is valued at, split from the arithmetic.
 struct EnvIn {
@@ -46,18 +56,34 @@ struct EnvIn {
     int idx, T;           // row before advancing (clamped to T-2 when the caller stepped past the data), dataset length
 };
 
-__device__ __forceinline__ EnvIn load_env(const GteParams& P, const GteData& D, const GteState& S,
-                                          const void* __restrict__ actions, const StepConsts& K, int64_t i) {
+// CG: load through L2 only — a kernel that stays resident across iterations (server kernel) must not find a line in
+// its L1 that another kernel has rewritten since.
+template <bool CG = false>
+__device__ __forceinline__ EnvRegs load_env_regs(const GteParams& P, const GteState& S, int64_t i) {
+    EnvRegs e;
+    if (CG) {
+        e.pf.asset = __ldcg(S.asset + i); e.pf.fiat = __ldcg(S.fiat + i);
+        e.pf.ia = __ldcg(S.interest_asset + i); e.pf.ifi = __ldcg(S.interest_fiat + i);
+        e.pos_idx = __ldcg(S.pos_idx + i); e.step = __ldcg(S.step + i); e.ep_start = __ldcg(S.ep_start + i);
+        e.ds = (P.n_datasets > 1) ? __ldcg(S.dataset_idx + i) : 0;
+        return e;
+    }
+    e.pf.asset = S.asset[i];
+    e.pf.fiat = S.fiat[i];
+    e.pf.ia = S.interest_asset[i];
+    e.pf.ifi = S.interest_fiat[i];
+    e.pos_idx = S.pos_idx[i];
+    e.step = S.step[i];
+    e.ep_start = S.ep_start[i];
+    e.ds = (P.n_datasets > 1) ? S.dataset_idx[i] : 0;
+    return e;
+}
+
+// state in registers + the raw action -> what the transition consumes (range checks, row index)
+__device__ __forceinline__ EnvIn make_env_in(const GteParams& P, const GteData& D, const GteState& S, const StepConsts& K,
+                                             const EnvRegs& e, int64_t a) {
     EnvIn in;
-    in.e.pf.asset = S.asset[i];
-    in.e.pf.fiat = S.fiat[i];
-    in.e.pf.ia = S.interest_asset[i];
-    in.e.pf.ifi = S.interest_fiat[i];
-    in.e.pos_idx = S.pos_idx[i];
-    in.e.step = S.step[i];
-    in.e.ep_start = S.ep_start[i];
-    in.e.ds = (P.n_datasets > 1) ? S.dataset_idx[i] : 0;
-    const int64_t a = load_action(actions, K.action_bytes, i);
+    in.e = e;
     if (a >= (int64_t)P.n_positions) atomicOr(S.error_flag, GTE_E_ACTION_RANGE);
     if (P.strict_actions && a < -1) atomicOr(S.error_flag, GTE_E_NEGATIVE_ACTION);
     in.a = (a < 0 || a >= (int64_t)P.n_positions) ? -1 : (int)a;           // :234 None = hold
@@ -71,6 +97,11 @@ __device__ __forceinline__ EnvIn load_env(const GteParams& P, const GteData& D, 
     return in;
 }
 
+__device__ __forceinline__ EnvIn load_env(const GteParams& P, const GteData& D, const GteState& S,
+                                          const void* __restrict__ actions, const StepConsts& K, int64_t i) {
+    return make_env_in(P, D, S, K, load_env_regs(P, S, i), load_action(actions, K.action_bytes, i));
+}
+
 // price BEFORE advancing (:204-207) and the price the new row is valued at (:239)
 __device__ __forceinline__ void load_prices(const GteParams& P, const GteData& D, const EnvIn& in, double& p0, double& p1) {
     const double* __restrict__ price = D.price + (int64_t)in.e.ds * P.t_stride;
@@ -78,11 +109,14 @@ __device__ __forceinline__ void load_prices(const GteParams& P, const GteData& D
     p1 = __ldg(price + in.idx + 1);
 }
 
-// The arithmetic of one transition.
+// The arithmetic of one transition.  STORE_STATE = false: the caller keeps the env's state in registers across iterations
+// (rollout / server kernels) and takes it back through e_out.
+template <bool STORE_STATE = true>
 __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteData& D, const GteState& S,
                                                   const StepConsts& K, const GteStepOut& O, uint64_t tick, int ring_slot,
                                                   int autoreset, int i, const EnvIn& in, const double p0, const double p1,
-                                                  MetricAcc& acc, const double* __restrict__ pos_tab) {
+                                                  MetricAcc& acc, const double* __restrict__ pos_tab,
+                                                  EnvRegs* e_out = nullptr) {
     EnvRegs e = in.e;
     const int a = in.a;
     const int T = in.T;
@@ -164,13 +198,8 @@ __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteD
             if (P.n_datasets > 1) S.dataset_idx[i] = e.ds;
         }
     }
-    S.asset[i] = e.pf.asset;
-    S.fiat[i] = e.pf.fiat;
-    S.interest_asset[i] = e.pf.ia;
-    S.interest_fiat[i] = e.pf.ifi;
-    S.pos_idx[i] = e.pos_idx;
-    S.step[i] = e.step;
-    S.ep_start[i] = e.ep_start;
+    if (STORE_STATE) store_env(S, i, e);
+    if (e_out != nullptr) *e_out = e;
     StepThreadOut r;
     r.idx = idx; r.ep_start = e.ep_start; r.ds = e.ds;
     r.dyn_pos = dyn_pos; r.dyn_rp = dyn_rp;
@@ -197,13 +226,21 @@ __device__ __forceinline__ double warp_sum(double v) {
 // CTA-level metric reduction -> metric_partials[blockIdx.x]; the last CTA to arrive folds all
 // partial rows in a fixed order (deterministic) into metrics_step / metrics_total.  NT = threads of the CTA, all of
 // which must call it (step kernel: 256; fused step+gather kernel: 192).
+//   flags   kChunkFirst: overwrite metrics_step (else add to it) and advance the ring clock; kChunkLast: advance the
+//           Philox tick; kChunkTotalOnly: only add to metrics_total (no metrics_step, no counters, nothing published);
+//   phase   0 / 1: a kernel that reduces twice (rollout kernel: all iterations but the last, then the last) uses the two
+//           halves of the ticket word and two sets of partial rows, so that CTAs already in the second reduction do not
+//           disturb the first (needs 2 * gridDim.x <= GTE_MAX_PARTIAL_ROWS);
+//   n_iter  how many lockstep iterations the launch covered (what the tick / ring clock advance by).
 template <int NT>
-static __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O, const GteState& S, int chunk_flags) {
+static __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O, const GteState& S, int flags,
+                                      int phase = 0, unsigned n_iter = 1u) {
     constexpr int NW = NT / 32, NG = NT / GTE_N_METRICS;
     __shared__ double s_part[NW][GTE_N_METRICS];
     __shared__ double s_fold[NG][GTE_N_METRICS];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* __restrict__ rows = O.metric_partials + (int64_t)phase * gridDim.x * GTE_N_METRICS;
 
     const double w_rew = warp_sum(acc.sum_rew);
     const int w_ep = __reduce_add_sync(0xffffffffu, acc.episodes);
@@ -216,6 +253,7 @@ static __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O,
         w_trunc = __reduce_add_sync(0xffffffffu, acc.truncated);
         w_len = __reduce_add_sync(0xffffffffu, acc.sum_len);
     }
+    __syncthreads();                                     // a second reduction of the same CTA: s_part is free again
     if (lane == 0) {
         s_part[warp][GTE_M_EPISODES] = (double)w_ep;
         s_part[warp][GTE_M_TERMINATED] = (double)w_term;
@@ -233,18 +271,19 @@ static __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O,
         double t = 0.0;
 #pragma unroll
         for (int w = 0; w < NW; ++w) t = dadd(t, s_part[w][threadIdx.x]);
-        O.metric_partials[(int64_t)blockIdx.x * GTE_N_METRICS + threadIdx.x] = t;
+        rows[(int64_t)blockIdx.x * GTE_N_METRICS + threadIdx.x] = t;
         __threadfence();
     }
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(O.block_counter, 1u) == gridDim.x - 1);
+    const unsigned one = phase ? 0x10000u : 1u;
+    if (threadIdx.x == 0) s_last = (((atomicAdd(O.block_counter, one) >> (16 * phase)) & 0xffffu) == gridDim.x - 1);
     __syncthreads();
     if (!s_last) return;
     __threadfence();
     const int m = threadIdx.x % GTE_N_METRICS, g = threadIdx.x / GTE_N_METRICS;   // NG groups x 8 metrics
     double t = 0.0;
     for (int b = g; b < (int)gridDim.x; b += NG)
-        t = dadd(t, __ldcg(O.metric_partials + (int64_t)b * GTE_N_METRICS + m));
+        t = dadd(t, __ldcg(rows + (int64_t)b * GTE_N_METRICS + m));
     s_fold[g][m] = t;
     __syncthreads();
     if (threadIdx.x < GTE_N_METRICS) {
@@ -252,22 +291,27 @@ static __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O,
         for (int k = 0; k < NG; ++k) tot = dadd(tot, s_fold[k][threadIdx.x]);
         // env chunks of one lockstep iteration run as consecutive launches: the first one overwrites
         // metrics_step, later ones add to it in launch order (deterministic)
-        O.metrics_step[threadIdx.x] = (chunk_flags & kChunkFirst) ? tot : dadd(O.metrics_step[threadIdx.x], tot);
+        if (!(flags & kChunkTotalOnly))
+            O.metrics_step[threadIdx.x] = (flags & kChunkFirst) ? tot : dadd(O.metrics_step[threadIdx.x], tot);
         if (O.metrics_total) O.metrics_total[threadIdx.x] = dadd(O.metrics_total[threadIdx.x], tot);
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        // every CTA OR-ed its error bits before it took its ticket: the flag is complete here (may be mapped host memory)
-        if (O.error_out != nullptr) *O.error_out = __ldcg(S.error_flag);
-        if (O.seq_out != nullptr) {                      // every CTA fenced its results system-wide before its ticket
-            __threadfence_system();
-            *reinterpret_cast<volatile uint32_t*>(O.seq_out) = O.seq_value;
-        }
-        *O.block_counter = 0u;                           // self-resetting for the next launch
+        atomicSub(O.block_counter, one * gridDim.x);     // self-resetting for the next launch (this phase's half only)
+        if (flags & kChunkTotalOnly) return;
         // every CTA of this launch has read the tick / ring clock by now.  The Philox event counter advances with
         // the LAST env range of an iteration; the ring clock with the FIRST one, so that the later ranges and
         // every gather of the iteration (all stream-ordered behind this launch) read the new value
-        if (chunk_flags & kChunkLast) *S.tick = *S.tick + 1ull;
-        if (chunk_flags & kChunkFirst) *S.ring_clock = *S.ring_clock + 1ull;
+        if (flags & kChunkLast) *S.tick = *S.tick + (uint64_t)n_iter;
+        if (flags & kChunkFirst) *S.ring_clock = *S.ring_clock + (uint64_t)n_iter;
+        // every CTA OR-ed its error bits before it took its ticket: the flag is complete here (may be mapped host memory)
+        if (O.error_out != nullptr) *O.error_out = __ldcg(S.error_flag);
+        if (O.seq_out != nullptr) {
+            // LAST: a host thread polling this word may hand the next iteration to a kernel that is still resident, so
+            // everything above (and every CTA's results, fenced before its ticket) must be visible first
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t*>(O.seq_out) = O.seq_value;
+        }
     }
 }
 

@@ -226,7 +226,10 @@ class TradingVectorEnv(_VectorEnvBase):
     terminated / truncated on the host, observations stay device-resident for the policy's forward pass:
     one blocking ``gte_step_host`` C call per step — ONE copy per direction beside the gather kernel, or,
     for small batches, no copy at all: the step kernel reads / writes the pinned host memory itself;
-    ``host_io`` = "auto" | "copy" | "mapped" picks the mechanism); ``autoreset`` (True = in-place); ``cuda_graph``
+    ``host_io`` = "auto" | "copy" | "mapped" | "server" picks the mechanism — "server" (windows=None, batches up to
+    256 x SMs envs) keeps a kernel RESIDENT that answers each `step()` through mapped host memory, with no kernel
+    launch or driver call per step: the lowest step latency for a host policy; any other call on the env (reset,
+    infos, rollout ...) or 2 ms without a step make it leave, and the next step launches it again); ``autoreset`` (True = in-place); ``cuda_graph``
     (capture one lockstep iteration and replay it: removes the launch overhead at small N; actions
     are then read from the env's own buffer); ``n_chunks`` (0 = the library's choice: ONE fused launch per
     iteration — every CTA advances its own envs, then gathers their windows — while the batch fits a single wave
@@ -829,6 +832,8 @@ class TradingVectorEnv(_VectorEnvBase):
         self.closed = True
 
     def close_extras(self, **kwargs):
+        if getattr(self, "host_io", None) == "server" and getattr(self, "_lib", None) is not None:
+            self._lib.gte_serve_stop()           # the resident server kernel, if it is still waiting for requests
         self._host = None
         self._pin_ident = {}
         self._graph = None

@@ -206,9 +206,18 @@ typedef struct GteStepOut {
 enum GteHostIOMode {
     GTE_IO_AUTO = 0,                 /* MAPPED while N * (action_bytes + 10) <= 384 KiB (1 MiB with windows == 0), else COPY */
     GTE_IO_COPY = 1,                 /* copy engines: ONE cudaMemcpyAsync per direction, beside the gather  */
-    GTE_IO_MAPPED = 2                /* zero-copy: the step kernel reads the actions from, and writes its
+    GTE_IO_MAPPED = 2,               /* zero-copy: the step kernel reads the actions from, and writes its
                                         10 B/env of results straight into, the pinned (UVA-mapped) host memory:
-                                        no copy to enqueue, the small-N latency floor                      */
+                                        no copy to enqueue                                                 */
+    GTE_IO_SERVER = 3                /* MAPPED without the launch: a resident kernel (launched by the first call, on a
+                                        library-owned stream) waits for each call's request in mapped host memory and
+                                        answers into the result block — no kernel launch, driver call or interrupt per
+                                        step: the small-N latency floor.  Needs windows == 0 and a batch that is
+                                        resident at once (n_envs <= 256 x SMs), else the call runs as MAPPED.  The kernel
+                                        leaves when any other entry point of the library is called, on gte_serve_stop(),
+                                        or after GTE_SERVER_IDLE_US (default 2000) without a request, and is launched
+                                        again by the next call.  While it is resident the env state belongs to it: do
+                                        not touch the state buffers from other streams.                      */
 };
 typedef struct GteHostIO {
     const void* actions;             /* HOST, pinned: [N] signed ints of params->action_bytes bytes each              */
@@ -281,6 +290,10 @@ int gte_step_obs(const GteParams* params, const GteData* data, const GteState* s
  * at all (see GteHostIOMode).  *mode_used (may be NULL) receives the mode the call resolved to. */
 int gte_step_host(const GteParams* params, const GteData* data, const GteState* state, const GteHostIO* io,
                   const GteStepOut* out, float* obs, int autoreset, int variant, int* mode_used, void* stream);
+
+/* Stop the resident server kernel of the current device (GTE_IO_SERVER), if one is running, and wait for it.  Every
+ * other entry point does this implicitly before it enqueues anything. */
+int gte_serve_stop(void);
 
 /* n_steps lockstep iterations from a device-resident action stream, enqueued by ONE host call (the open-loop driver:
  * replay of recorded actions, random-policy baselines, back-tests; at small N an iteration then costs a kernel launch

@@ -312,3 +312,56 @@ def test_dataset_dir_with_mixed_files_and_shuffled_columns_equals_in_memory_data
         assert torch.equal(r0[0].view(torch.int32), r1[0].view(torch.int32)) and torch.equal(r0[1], r1[1])
         assert torch.equal(disk._dataset_idx, mem._dataset_idx)
     assert set(disk._dataset_idx.cpu().tolist()) == {0, 1}
+
+
+def test_resident_server_kernel_matches_the_oracle_and_survives_interruptions():
+    """host_io="server" (C2 shape: 4096 envs, windows=None): a resident kernel answers each step through mapped host
+    memory.  Same bits as the oracle, across the events that make the kernel leave and come back: an info read and a
+    masked reset (other entry points stop it), an idle pause longer than its time-out, and close()."""
+    import time
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    from gym_trading_env_b200 import _cabi
+    N = 4096
+    series = gte.frame_to_arrays(gte.make_gbm_ohlcv(5000, seed=6))
+    pos = [-1, 0, 0.5, 1]
+    kw = dict(positions=pos, windows=None, max_episode_duration=40, **FEES)
+    env = gte.TradingVectorEnv(series, num_envs=N, seed=3, verbose=0, output="hybrid", host_io="server", **kw)
+    o = orc.OracleVecEnv(series.features, series.price, num_envs=N, seed=3, **kw)
+    obs, _ = env.reset()
+    H.assert_bits(obs.cpu().numpy(), o.reset(), "reset obs")
+    rng = np.random.default_rng(1)
+    pin = env.pinned_actions()
+    mask = np.zeros(N, dtype=bool)
+    mask[::7] = True
+    for k in range(160):
+        a = rng.integers(0, len(pos), size=N)
+        a[rng.random(N) < 0.05] = -1
+        pin[...] = a
+        obs, rew, term, trunc, infos = env.step(pin)
+        assert env._io_mode_used.value == _cabi.IO_SERVER
+        o.step(a)
+        H.assert_bits(obs.cpu().numpy(), o.obs, f"step {k} obs")
+        H.assert_close64(rew, o.reward, f"step {k} reward")
+        H.assert_bits(term.view(np.uint8), o.terminated, f"step {k} terminated")
+        H.assert_bits(trunc.view(np.uint8), o.truncated, f"step {k} truncated")
+        H.assert_bits(env._valuation.cpu().numpy(), o.valuation, f"step {k} valuation")
+        H.assert_bits(env._asset.cpu().numpy(), o.asset, f"step {k} asset")
+        H.assert_bits(env._step.cpu().numpy(), o.step_, f"step {k} step state")
+        if k == 40:                                                      # gte_info stops the server; the next step relaunches it
+            H.assert_bits(infos["idx"].cpu().numpy(), o.idx, "infos idx")
+        if k == 80:                                                      # so does a (masked) reset
+            env.reset(options={"mask": mask})
+            o.reset(mask=mask)
+        if k == 120:
+            time.sleep(0.02)                                             # longer than the idle time-out: it left by itself
+    m = env._metrics_total.cpu().numpy()
+    assert m[0] >= 3 * N
+    env.close()
+    assert env.closed
+    bad = gte.TradingVectorEnv(series, num_envs=64, seed=3, verbose=0, output="hybrid", host_io="server", **kw)
+    bad.reset()
+    with pytest.raises(IndexError):
+        bad.step(np.full(64, 9, np.int8))
+    bad.step(np.zeros(64, np.int8))
+    bad.close()
