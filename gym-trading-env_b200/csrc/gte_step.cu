@@ -114,23 +114,25 @@ rollout_kernel(const GteParams P, const GteData D, const GteState S, const void*
 // ---- resident "env server" for a HOST policy at small N (gte_step_host, GTE_IO_SERVER) -----------------------------
 // A synchronous host step costs launch -> run -> completion -> wake-up (~20 us on this box) however small the kernel.
 // The server kernel is launched ONCE and stays resident: every iteration the host writes its actions into mapped pinned
-// memory and bumps ctl->go; CTA 0 polls that word over PCIe and hands the command to the other CTAs through a word in
+// memory and writes a request word (ctl->req); CTA 0 polls that word over PCIe and hands the command to the other CTAs through a word in
 // device memory; every thread advances its env (actions read from, results written straight into, mapped host memory)
 // and the last CTA publishes the iteration's sequence number to the host, which polls it.  No launch, no driver call
-// and no interrupt on the path.  The kernel leaves by itself when told to (ctl->stop), or when no request arrived for
+// and no interrupt on the path.  The kernel leaves by itself when told to (req = kServeStop), or when no request arrived for
 // idle_ns — so a cudaDeviceSynchronize() elsewhere in the process waits at most that long — and tells the host
 // (ctl->alive = 0), which simply launches it again with the next request.
 struct ServeCtl {                // pinned, mapped host memory, owned by the library (one per device)
-    volatile uint32_t go;        // host -> device: sequence number of the requested iteration
-    volatile uint32_t stop;      // host -> device: leave now
-    volatile uint32_t alive;     // host sets 1 before a launch, the kernel sets 0 on its way out
-    uint32_t pad[13];
+    // host -> device, ONE 16-byte word pair the kernel fetches with a single PCIe read per poll:
+    volatile unsigned long long req;      // (sequence number of the requested iteration << 8) | action_bytes; kServeStop = leave
+    volatile unsigned long long actions;  // the request's action array (mapped host memory), written BEFORE req
+    volatile uint32_t alive;              // host sets 1 before a launch, the kernel sets 0 on its way out
+    uint32_t pad[11];
 };
+constexpr unsigned long long kServeStop = ~0ull;
 
-__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const volatile uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+// one 16-byte system-scope read of {req, actions}: the host writes `actions` first, so a snapshot that shows the new
+// request also shows its action pointer
+__device__ __forceinline__ void ld_ctl(const ServeCtl* c, unsigned long long& req, unsigned long long& actions) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(req), "=l"(actions) : "l"(c) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
     unsigned long long v;
@@ -156,12 +158,12 @@ __device__ __forceinline__ int64_t load_action_volatile(const void* actions, int
 }
 
 __global__ void __launch_bounds__(kStepThreads, 2)
-serve_kernel(const GteParams P, const GteData D, const GteState S, const void* actions, const StepConsts K0,
-             const GteStepOut O, int autoreset, float* __restrict__ obs_rows, ServeCtl* ctl, unsigned long long* dctl,
-             uint32_t first_seq, unsigned long long idle_ns) {
+serve_kernel(const GteParams P, const GteData D, const GteState S, const StepConsts K0, const GteStepOut O, int autoreset,
+             float* __restrict__ obs_rows, ServeCtl* ctl, unsigned long long* dctl, uint32_t first_seq,
+             unsigned long long idle_ns) {
     __shared__ double s_pos[GTE_MAX_POSITIONS];
     __shared__ int s_T0;
-    __shared__ int s_cmd;
+    __shared__ unsigned long long s_cmd[2];
     if (threadIdx.x < GTE_MAX_POSITIONS) s_pos[threadIdx.x] = P.positions[threadIdx.x];
     if (threadIdx.x == 0) s_T0 = D.lengths[0];
     __syncthreads();
@@ -171,32 +173,42 @@ serve_kernel(const GteParams P, const GteData D, const GteState S, const void* a
     const bool valid = i < P.n_envs;
     const int F = P.n_static + P.n_dyn;
     for (uint32_t seq = first_seq;; ++seq) {
-        // ---- wait for the host: CTA 0 watches the mapped control block, the others a word in device memory
+        // ---- wait for the host: CTA 0 watches the mapped control block, the others two words in device memory
+        //      dctl[0] = (seq << 9) | (leave << 8) | action_bytes, dctl[1] = action pointer (written first)
         if (threadIdx.x == 0) {
-            int cmd = 0;
+            unsigned long long cmd, act;
             if (blockIdx.x == 0) {
                 const unsigned long long t0 = global_timer_ns();
                 for (;;) {
-                    if (ld_acquire_sys_u32(&ctl->go) == seq) { cmd = 1; break; }
-                    if (ld_acquire_sys_u32(&ctl->stop) != 0u || global_timer_ns() - t0 > idle_ns) { cmd = 2; break; }
+                    unsigned long long req;
+                    ld_ctl(ctl, req, act);
+                    if (req != kServeStop && (uint32_t)(req >> 8) == seq) { cmd = ((unsigned long long)seq << 9) | (req & 0xffull); break; }
+                    if (req == kServeStop || global_timer_ns() - t0 > idle_ns) { cmd = ((unsigned long long)seq << 9) | 0x100ull; break; }
                 }
-                st_release_gpu_u64(dctl, ((unsigned long long)seq << 2) | (unsigned long long)cmd);
+                // no system-scope fence: the action array is read with volatile (system-scope) loads that are issued only
+                // after this poll has RETURNED the new request (data dependency through dctl), and the host wrote the
+                // actions before the request word — a fence here costs a PCIe round trip per step
+                dctl[1] = act;
+                st_release_gpu_u64(dctl, cmd);
             } else {
                 for (;;) {
-                    const unsigned long long v = ld_acquire_gpu_u64(dctl);
-                    if ((uint32_t)(v >> 2) == seq) { cmd = (int)(v & 3ull); break; }
+                    cmd = ld_acquire_gpu_u64(dctl);
+                    if ((uint32_t)(cmd >> 9) == seq) break;
                 }
+                act = __ldcg(dctl + 1);
             }
-            s_cmd = cmd;
+            s_cmd[0] = cmd; s_cmd[1] = act;
         }
         __syncthreads();
-        if (s_cmd != 1) break;
+        if (s_cmd[0] & 0x100ull) break;
+        const int action_bytes = (int)(s_cmd[0] & 0xffull);
+        const void* actions = reinterpret_cast<const void*>(s_cmd[1]);
         // ---- one lockstep iteration
         MetricAcc acc;
         const uint64_t tick = __ldcg(S.tick);
         const int ring_slot = ring_slot_of(P, __ldcg(S.ring_clock) + 1ull);
         if (valid) {
-            const int64_t a = load_action_volatile(actions, K.action_bytes, i);       // over PCIe, beside the state loads
+            const int64_t a = load_action_volatile(actions, action_bytes, i);         // over PCIe, beside the state loads
             const EnvIn in = make_env_in(P, D, S, K, load_env_regs<true>(P, S, i), a);
             double p0, p1;
             load_prices(P, D, in, p0, p1);
@@ -519,7 +531,7 @@ struct HostIOStreams {
     ServeCtl* ctl = nullptr;
     unsigned long long* dctl = nullptr;
     bool serving = false;
-    GteParams sp; GteData sd; GteState ss; GteStepOut so; const void* sa = nullptr; float* sobs = nullptr; int sauto = 0;
+    GteParams sp; GteData sd; GteState ss; GteStepOut so; float* sobs = nullptr; int sauto = 0;
 };
 static HostIOStreams g_hio[16];
 
@@ -545,9 +557,9 @@ cudaError_t serve_quiesce() {
     if (cudaGetDevice(&dev) != cudaSuccess) return cudaSuccess;
     HostIOStreams& h = g_hio[dev & 15];
     if (!h.serving) return cudaSuccess;
-    h.ctl->stop = 1u;
+    h.ctl->req = kServeStop;
     const cudaError_t e = cudaStreamSynchronize(h.serve);
-    h.ctl->stop = 0u;
+    h.ctl->req = 0ull;
     h.serving = false;
     return e;
 }
@@ -610,9 +622,11 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
             memset(h->ctl, 0, sizeof(ServeCtl));
             if ((e = cudaMalloc(reinterpret_cast<void**>(&h->dctl), 64)) != cudaSuccess) return e;
         }
-        const bool same = h->serving && memcmp(&h->sp, &P, sizeof(P)) == 0 && memcmp(&h->sd, &D, sizeof(D)) == 0 &&
+        GteParams p0 = P;
+        p0.action_bytes = 0;                                 // travels with every request, not with the launch
+        const bool same = h->serving && memcmp(&h->sp, &p0, sizeof(p0)) == 0 && memcmp(&h->sd, &D, sizeof(D)) == 0 &&
                           memcmp(&h->ss, &S, sizeof(S)) == 0 && h->so.metrics_step == O.metrics_step &&
-                          h->so.reward == o.reward && h->sa == io.actions && h->sobs == obs && h->sauto == autoreset;
+                          h->so.reward == o.reward && h->sobs == obs && h->sauto == autoreset;
         if (h->serving && !same && (e = serve_quiesce()) != cudaSuccess) return e;
         auto launch = [&]() -> cudaError_t {
             cudaError_t le;
@@ -622,16 +636,17 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
             if ((le = cudaMemsetAsync(h->dctl, 0, 64, h->serve)) != cudaSuccess) return le;
             h->ctl->alive = 1u;
             const int grid = (int)((N + kStepThreads - 1) / kStepThreads);
-            serve_kernel<<<grid, kStepThreads, 0, h->serve>>>(P, D, S, io.actions, make_step_consts(P), o, autoreset, obs, h->ctl,
-                                                              h->dctl, seq, serve_idle_ns());
+            serve_kernel<<<grid, kStepThreads, 0, h->serve>>>(p0, D, S, make_step_consts(p0), o, autoreset, obs, h->ctl, h->dctl,
+                                                              seq, serve_idle_ns());
             if ((le = cudaGetLastError()) != cudaSuccess) return le;
             h->serving = true;
-            h->sp = P; h->sd = D; h->ss = S; h->so = O; h->so.reward = o.reward; h->sa = io.actions; h->sobs = obs; h->sauto = autoreset;
+            h->sp = p0; h->sd = D; h->ss = S; h->so = O; h->so.reward = o.reward; h->sobs = obs; h->sauto = autoreset;
             return cudaSuccess;
         };
         if ((!h->serving || h->ctl->alive == 0u) && (e = launch()) != cudaSuccess) return e;
-        __atomic_thread_fence(__ATOMIC_RELEASE);             // the caller's action writes before the request
-        h->ctl->go = seq;
+        h->ctl->actions = (unsigned long long)reinterpret_cast<uintptr_t>(io.actions);
+        __atomic_thread_fence(__ATOMIC_RELEASE);             // the caller's action writes (and the pointer) before the request
+        h->ctl->req = ((unsigned long long)seq << 8) | (unsigned long long)ab;
         for (uint32_t spins = 1; *seq_word != seq; ++spins) {
             _mm_pause();
             if (h->ctl->alive == 0u) {                       // it left (idle time-out) — possibly without seeing this request

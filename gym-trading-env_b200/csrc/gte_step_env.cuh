@@ -265,18 +265,20 @@ static __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O,
         s_part[warp][GTE_M_RESERVED] = 0.0;
     }
     __syncthreads();
-    // results written straight into mapped host memory: visible system-wide before this CTA takes its ticket
-    if (O.seq_out != nullptr) __threadfence_system();
     if (threadIdx.x < GTE_N_METRICS) {
         double t = 0.0;
 #pragma unroll
         for (int w = 0; w < NW; ++w) t = dadd(t, s_part[w][threadIdx.x]);
         rows[(int64_t)blockIdx.x * GTE_N_METRICS + threadIdx.x] = t;
-        __threadfence();
     }
     __syncthreads();
     const unsigned one = phase ? 0x10000u : 1u;
-    if (threadIdx.x == 0) s_last = (((atomicAdd(O.block_counter, one) >> (16 * phase)) & 0xffffu) == gridDim.x - 1);
+    if (threadIdx.x == 0) {
+        // ONE cumulative fence per CTA, by the thread that takes the ticket: the barrier above put every write of the
+        // CTA (results, partial row) before it.  System scope when the results went straight into mapped host memory.
+        if (O.seq_out != nullptr) __threadfence_system(); else __threadfence();
+        s_last = (((atomicAdd(O.block_counter, one) >> (16 * phase)) & 0xffffu) == gridDim.x - 1);
+    }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
@@ -305,12 +307,18 @@ static __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O,
         if (flags & kChunkLast) *S.tick = *S.tick + (uint64_t)n_iter;
         if (flags & kChunkFirst) *S.ring_clock = *S.ring_clock + (uint64_t)n_iter;
         // every CTA OR-ed its error bits before it took its ticket: the flag is complete here (may be mapped host memory)
-        if (O.error_out != nullptr) *O.error_out = __ldcg(S.error_flag);
+        const int err = (O.error_out != nullptr || O.seq_out != nullptr) ? __ldcg(S.error_flag) : 0;
         if (O.seq_out != nullptr) {
-            // LAST: a host thread polling this word may hand the next iteration to a kernel that is still resident, so
-            // everything above (and every CTA's results, fenced before its ticket) must be visible first
-            __threadfence_system();
-            *reinterpret_cast<volatile uint32_t*>(O.seq_out) = O.seq_value;
+            // LAST, and in ONE 8-byte store with the error flag that sits right in front of it in the result block
+            // (GTE_HOST_RESULT_ERROR_OFFSET / _SEQ_OFFSET): a host thread polling the sequence word may hand the next
+            // iteration to a kernel that is still resident.  Every CTA fenced its results system-wide BEFORE its
+            // ticket, and the tickets were all observed before this store is issued; the counters above only have to
+            // be visible on the device.
+            __threadfence();
+            *reinterpret_cast<volatile unsigned long long*>(O.seq_out - 1) =
+                ((unsigned long long)O.seq_value << 32) | (unsigned long long)(unsigned)err;
+        } else if (O.error_out != nullptr) {
+            *O.error_out = err;
         }
     }
 }

@@ -720,14 +720,15 @@ class TradingVectorEnv(_VectorEnvBase):
             if a is actions and len(self._pin_ident) < 64:
                 self._pin_ident[id(actions)] = (actions, ptr, nb)
             self._last_actions = a
-        hb, io, red = self._host, self._io, self._red_stream
+        hb, red = self._host, self._red_stream
         if hb is None:
             hb = self._host_buffers()
-            io = self._io
+        io = self._io
         if red is not None and self._red_snapshot is not None:
             torch.cuda.current_stream(self.device).wait_event(self._red_snapshot)   # metrics_step is about to be overwritten
         io.actions = ptr
-        io.step_done_event = self._step_done.cuda_event if red is not None else None
+        if red is not None:
+            io.step_done_event = self._step_done.cuda_event
         self._P.action_bytes = nb
         self._tick += 1
         f = self._fast_args

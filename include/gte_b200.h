@@ -196,7 +196,10 @@ typedef struct GteStepOut {
                                         May be mapped host memory: the flag then reaches the host with the results     */
     uint32_t* seq_out;               /* u32 [1]  or NULL: after every result of the launch is visible system-wide, the last
                                         CTA stores seq_value here — a host thread polling mapped memory sees the
-                                        iteration complete without a driver call                                       */
+                                        iteration complete without a driver call.  MUST be the upper half of an aligned
+                                        8-byte word whose lower half is the error flag's destination (the layout of the
+                                        host result block): the two are published with one 8-byte store, error_out itself
+                                        is then not written                                                            */
     uint32_t seq_value;
     uint32_t reserved1;
 } GteStepOut;

@@ -47,7 +47,7 @@ def main():
                   portfolio_initial_value=1000, max_episode_duration="max" if not args.windows else 720, num_envs=N,
                   seed=1, verbose=0)
         row = {"envs": N, "windows": args.windows}
-        for mode in ("mapped", "copy"):
+        for mode in ("mapped", "copy") + (("server",) if not args.windows and N <= 32768 else ()):
             env = gte.TradingVectorEnv(series, output="hybrid", host_io=mode, **kw)
             env.reset()
             pin = env.pinned_actions()
