@@ -347,12 +347,12 @@ int num_sms() {
     return g_num_sms;
 }
 
-// Consecutive 256-env tiles per CTA: the grid is capped at the CTAs that are resident at once (SMs x 4), so a large
+// Consecutive 256-env tiles per CTA: the grid is capped at the CTAs that are resident at once (SMs x 3), so a large
 // batch runs as ONE wave of CTAs that each walk through their tiles — the per-CTA set-up and the metric fold are paid
 // once per CTA instead of once per tile or two (C5 shard: 0.112 -> 0.089 ms; GTE_STEP_MAX_CTAS overrides the cap).
 static int step_tiles_per_cta(int n_envs) {
     static const int max_ctas = [] { const char* e = getenv("GTE_STEP_MAX_CTAS"); return e ? atoi(e) : 0; }();
-    int64_t cap = max_ctas > 0 ? max_ctas : (int64_t)num_sms() * 4;
+    int64_t cap = max_ctas > 0 ? max_ctas : (int64_t)num_sms() * 3;
     if (cap > kMaxPartialRows) cap = kMaxPartialRows;
     const int64_t tiles = ((int64_t)n_envs + kStepThreads - 1) / kStepThreads;
     return (int)((tiles + cap - 1) / cap);
@@ -368,7 +368,6 @@ cudaError_t launch_step_range(const GteParams& P, const GteData& D, const GteSta
                               const GteStepOut& O, int autoreset, int env_begin, int env_end, int chunk_flags,
                               cudaStream_t stream, float* obs_rows) {
     const StepConsts K = make_step_consts(P);
-    static const int min_ctas = [] { const char* e = getenv("GTE_STEP_MIN_CTAS"); return e ? atoi(e) : 4; }();
     const int n = env_end - env_begin;
     const int grid = step_grid(n), tpc = step_tiles_per_cta(n);
     // same shared-memory carve-out as the gather kernel, so CTAs of both can be resident on one SM
@@ -377,12 +376,12 @@ cudaError_t launch_step_range(const GteParams& P, const GteData& D, const GteSta
     cudaGetDevice(&dev);
     if (!carveout_set[dev & 15]) {
         cudaFuncSetAttribute(step_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(step_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         carveout_set[dev & 15] = true;
     }
-    // 4 CTAs/SM (64 registers, a few spills) pays once the grid runs in several waves; a grid that is resident at once
-    // is latency-bound and runs the spill-free 3-CTA build a little faster (C3: 47.3 -> 46.6 us per iteration)
-    auto kern = (min_ctas >= 4 && grid > num_sms() * 3) ? step_kernel<4> : step_kernel<3>;
+    // ONE build: 3 CTAs per SM at 80 registers with no local-memory spills.  The 4-CTAs/SM build (64 registers, 18 STL /
+    // 15 LDL) measures the same on the C5 shard (0.0925 vs 0.0930 ms): the kernel is bound by the issue rate of its
+    // dependent fp64 chains, not by resident warps, loads or stores (profiles/r02_tuning.md has the diagnostic runs)
+    auto kern = step_kernel<3>;
     return launch_pdl(kern, dim3(grid), dim3(kStepThreads), 0, stream, P, D, S, actions, K, O, autoreset, tpc,
                       env_begin, env_end, chunk_flags, obs_rows);
 }

@@ -1,13 +1,13 @@
-# step-kernel variants at the C5 shard size: software pipeline on/off x CTAs per SM
+# step-kernel variants at the C5 shard size: plain vs TMA-staged pipeline (4 and 3 CTAs per SM)
 mkdir -p gpurun_out
-GTE_STEP_PIPE=1 timeout 600 python -m pytest tests/test_cuda_fullsize_properties.py tests/test_cuda_edge_cases.py -m gpu -x -q 2>&1 | tail -3
-for v in "0 4" "1 4" "1 3" "1 2"; do
+timeout 900 python -m pytest tests/test_cuda_fullsize_properties.py tests/test_cuda_edge_cases.py tests/test_cuda_baseline_configs.py -m gpu -x -q -k "not server and not host_paths" 2>&1 | tail -3
+for v in "0 0" "1 0" "3 444"; do
   set -- $v
-  GTE_STEP_PIPE=$1 GTE_STEP_CTAS_PER_SM=$2 timeout 300 python bench.py --no-e2e --no-cpu --steps 100 > gpurun_out/r02_stepvar_$1_$2.json 2> gpurun_out/r02_stepvar.err || tail -3 gpurun_out/r02_stepvar.err
-  python - "$1" "$2" <<'PY'
+  GTE_STEP_TMA=$1 GTE_STEP_MAX_CTAS=$2 timeout 300 python bench.py --no-e2e --no-cpu --no-configs --steps 100 > gpurun_out/r02_stepvar_$1.json 2> gpurun_out/r02_stepvar.err || tail -3 gpurun_out/r02_stepvar.err
+  python - "$1" <<'PY'
 import json, sys
-d=json.loads(open(f"gpurun_out/r02_stepvar_{sys.argv[1]}_{sys.argv[2]}.json").read().strip().splitlines()[-1])
+d=json.loads(open(f"gpurun_out/r02_stepvar_{sys.argv[1]}.json").read().strip().splitlines()[-1])
 r=d["roofline"]
-print("pipe=%s ctas/sm=%s: step_ms=%.4f gather_ms=%.4f iter_ms=%.4f value=%.4e" % (sys.argv[1], sys.argv[2], r["step_kernel_ms"], r["kernel_ms"], d["ms_per_step"], d["value"]))
+print("tma=%s: step_ms=%.4f gather_ms=%.4f iter_ms=%.4f value=%.4e spread=%.3f" % (sys.argv[1], r["step_kernel_ms"], r["kernel_ms"], d["ms_per_step"], d["value"], d["spread"]["rel"]))
 PY
 done
