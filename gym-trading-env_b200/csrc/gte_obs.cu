@@ -467,18 +467,24 @@ static cudaError_t plan_tma(const ObsShape& sh, int n_envs, bool fused, TmaPlan*
     cudaGetDevice(&dev);
     // opt-in to > 48 KB dynamic smem once per kernel AND device (the attribute is per device), and how many CTAs of the
     // kernel an SM holds (registers, static + dynamic shared memory), asked of the runtime once
-    struct Slot { ObsKernelFn kern; size_t smem; int per_sm; };
+    struct Slot { ObsKernelFn kern; size_t smem_max, smem_asked; int per_sm; };
     static Slot slots[16][24] = {};
     auto configure = [&](ObsKernelFn k, int* per_sm) -> cudaError_t {
         Slot* sl = slots[dev & 15];
         int i = 0;
         while (i < 23 && sl[i].kern != nullptr && sl[i].kern != k) ++i;
-        if (sl[i].kern != k || smem > sl[i].smem) {
+        if (sl[i].kern != k) { sl[i].kern = k; sl[i].smem_max = 0; sl[i].smem_asked = (size_t)-1; }
+        if (smem > sl[i].smem_max) {                        // the opt-in only ever has to grow
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
+            sl[i].smem_max = smem;
+        }
+        if (smem != sl[i].smem_asked) {                     // occupancy belongs to THIS launch's shared-memory size
             int n = 0;
-            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, kCoopThreads, smem)) != cudaSuccess) return e;
-            sl[i].kern = k; sl[i].smem = smem; sl[i].per_sm = n < 1 ? 1 : n;
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, kCoopThreads, smem);
+            if (e != cudaSuccess) return e;
+            sl[i].smem_asked = smem;
+            sl[i].per_sm = n < 1 ? 1 : n;
         }
         *per_sm = sl[i].per_sm;
         return cudaSuccess;
