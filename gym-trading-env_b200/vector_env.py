@@ -1133,6 +1133,13 @@ class TradingVectorEnv(_VectorEnvBase):
         if self._red_stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self._red_stream)
 
+    @property
+    def error_flag(self):
+        """The sticky in-kernel error bits (include/gte_b200.h ``GteErrorBit``) as a 1-element int32 CUDA tensor that
+        every step refreshes — a device-resident loop can fold it into its own bookkeeping (or `.item()` it every k
+        steps) instead of calling :meth:`check_errors`; the host-output modes raise by themselves."""
+        return self._error_out
+
     def check_errors(self):
         """Synchronising check of the in-kernel error flags (device-resident actions are not validated on the host)."""
         self._raise_on_flag(int(self._error_flag.item()))

@@ -1,7 +1,9 @@
 """Shared test plumbing: golden fixtures, env factories, and the step-by-step comparison.
 
 The same `replay_golden` drives the CPU oracle (`-m "not gpu"`) and the CUDA path (`-m gpu`), so
-both are held to the outputs of the unmodified reference recorded in tests/golden/*.npz.
+both are held to the outputs of the reference's own code recorded in tests/golden/*.npz — run unmodified except for the one
+documented H3 normalisation (oracle/ref_harness.py zeroes each env's private dynamic-feature columns before every
+reset(), fixtures with normalize_dyn=True; `raw_stale_dynamic_rows` is the raw reference and pins the oracle's faithful mode).
 """
 from __future__ import annotations
 

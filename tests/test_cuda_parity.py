@@ -1,5 +1,6 @@
 """GPU: the CUDA path, called through the C-ABI (ctypes -> libgte_b200.so), against
-(a) the golden vectors recorded from the unmodified reference and (b) the CPU oracle on larger
+(a) the golden vectors recorded from the reference's own code (with the H3 normalisation of oracle/ref_harness.py:
+dynamic-feature columns zeroed before each reset) and (b) the CPU oracle on larger
 seeded inputs, with the same step-by-step comparison the oracle itself passes on the CPU.
 
 Bars (BASELINE.json north_star): position/step indices, flags and observations bit-exact;
@@ -156,7 +157,9 @@ def test_cabi_argument_errors_and_host_validation():
     with pytest.raises(ValueError):
         env.step(np.zeros(3, dtype=np.int64))
     import torch
+    assert int(env.error_flag) == 0
     env.step(torch.full((16,), 5, dtype=torch.int64, device=env.device))   # device actions: flagged in-kernel
+    assert int(env.error_flag) == 1                                        # refreshed by the step itself, no extra launch
     with pytest.raises(IndexError):
         env.check_errors()
     with pytest.raises(NotImplementedError):
