@@ -293,7 +293,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the short C2 / C3 / C4 legs of the default run")
-    ap.add_argument("--repeats", type=int, default=3, help="the timed region of K steps is repeated this many times; the median counts")
+    ap.add_argument("--repeats", type=int, default=3, help="the timed region of K steps is repeated at least this many times; the median counts")
+    ap.add_argument("--min-timed-seconds", type=float, default=0.3,
+                    help="keep repeating the K-step region (up to 25 times) until this much device time is covered")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = {"c3": 2000, "c2": 5000}.get(args.workload, 200) if args.impl == "b200" else 200
@@ -454,7 +456,9 @@ def measure(ctx, env, actions, wl, workload_name, steps, warmup, repeats=3, samp
     env._kernel_events_every = 1 if steps < 64 else (4 if N >= 2 ** 20 else 8)
     times = []
     t_host0 = time.time()
-    for _ in range(repeats):
+    rep = 0
+    while rep < repeats:
+        rep += 1
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         _barrier(ctx)
         e0.record()
@@ -467,6 +471,11 @@ def measure(ctx, env, actions, wl, workload_name, steps, warmup, repeats=3, samp
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         times.append(float(t.item()))
+        if rep == 1 and ctx.args.min_timed_seconds > 0:
+            # a short K (the driver passes --steps 20: 22 ms) would leave the clock sampler (20 ms period) with one or
+            # two samples and the median with three points: repeat the region until ~min_timed_seconds are covered
+            # (same count on every rank: the decision uses the max-over-ranks time)
+            repeats = max(repeats, min(25, int(ctx.args.min_timed_seconds * 1e3 / max(times[0], 1e-3)) + 1))
     clocks = sampler.stop(t_host0, time.time()) if (sampler is not None and ctx.rank == 0) else None
     env.check_errors()
     ms = statistics.median(times)
@@ -527,7 +536,7 @@ def measure(ctx, env, actions, wl, workload_name, steps, warmup, repeats=3, samp
                                    "achieved": whole * (a_step + a_obs + a_static) / (a_step + a_obs),
                                    "frac": whole * (a_step + a_obs + a_static) / (a_step + a_obs) / peak}}}
     return {"value": value, "ms_per_step": ms / steps, "spread": spread, "clocks": clocks, "roofline": roofline,
-            "repeats": {"n": repeats, "steps_each": steps, "statistic": "median"},
+            "repeats": {"n": len(times), "steps_each": steps, "statistic": "median"},
             "launches_per_step": launches_per_step, "obs_variant": env.obs_variant, "chunks": env.chunks,
             "l2_policy": "inputs larger than L2 (obs %.0f MB + state/ring %.0f MB per step vs 126 MB L2)"
                          % (env._obs.numel() * 4 / 1e6, (N * 44 + env._dyn_ring.numel()) / 1e6)}
@@ -604,7 +613,7 @@ def e2e_legs(ctx, env, actions, wl):
                 "action_dtype": str(acts_h.dtype)}
 
     out = {}
-    n_it = min(max(args.steps, 10), 200) if N >= 2 ** 20 else 2000
+    n_it = min(max(args.steps, 60), 200) if N >= 2 ** 20 else 2000
     # headline: the documented default wire format of a host policy — int8 actions (Discrete(P) fits, widened by the
     # step kernel: lossless), fp64 rewards + terminated + truncated + error flag back in ONE block
     out["e2e"] = time_e2e("hybrid", "auto", torch.int8, n_it)

@@ -359,6 +359,23 @@ def test_resident_server_kernel_matches_the_oracle_and_survives_interruptions():
     assert m[0] >= 3 * N
     env.close()
     assert env.closed
+    # two server-mode envs on one device take turns: each call finds the other env's kernel resident, stops it and
+    # launches its own — slow, but every step still matches the oracle
+    e1 = gte.TradingVectorEnv(series, num_envs=512, seed=5, verbose=0, output="hybrid", host_io="server", **kw)
+    e2 = gte.TradingVectorEnv(series, num_envs=300, seed=6, verbose=0, output="hybrid", host_io="server", **kw)
+    o1 = orc.OracleVecEnv(series.features, series.price, num_envs=512, seed=5, **kw)
+    o2 = orc.OracleVecEnv(series.features, series.price, num_envs=300, seed=6, **kw)
+    e1.reset(); e2.reset(); o1.reset(); o2.reset()
+    for k in range(30):
+        a1, a2 = rng.integers(0, len(pos), size=512), rng.integers(0, len(pos), size=300)
+        r1 = e1.step(a1.astype(np.int8))
+        r2 = e2.step(a2.astype(np.int16))
+        o1.step(a1); o2.step(a2)
+        H.assert_close64(r1[1], o1.reward, f"env1 step {k} reward")
+        H.assert_close64(r2[1], o2.reward, f"env2 step {k} reward")
+        H.assert_bits(r1[0].cpu().numpy(), o1.obs, f"env1 step {k} obs")
+        H.assert_bits(r2[0].cpu().numpy(), o2.obs, f"env2 step {k} obs")
+    e1.close(); e2.close()
     bad = gte.TradingVectorEnv(series, num_envs=64, seed=3, verbose=0, output="hybrid", host_io="server", **kw)
     bad.reset()
     with pytest.raises(IndexError):
