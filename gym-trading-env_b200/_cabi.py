@@ -81,7 +81,8 @@ class GteStepOut(C.Structure):
 class GteHostIO(C.Structure):
     _fields_ = [
         ("actions", C.c_void_p), ("results", C.c_void_p), ("dev_actions", C.c_void_p), ("dev_results", C.c_void_p),
-        ("step_done_event", C.c_void_p), ("mode", C.c_int32), ("reserved", C.c_int32),
+        ("step_done_event", C.c_void_p), ("obs_host", C.c_void_p), ("obs_bytes", C.c_int64),
+        ("mode", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -132,6 +132,7 @@ int gte_step_host(const GteParams* params, const GteData* data, const GteState* 
     GTE_REQUIRE("gte_step_host", io->mode >= GTE_IO_AUTO && io->mode <= GTE_IO_SERVER);
     GTE_REQUIRE("gte_step_host", (reinterpret_cast<uintptr_t>(io->results) & 7u) == 0);
     GTE_REQUIRE("gte_step_host", out->seq_out == nullptr);   // the call points it into the result block itself
+    GTE_REQUIRE("gte_step_host", io->obs_host == nullptr || io->obs_bytes > 0);
     if (gte::host_io_mode(*params, io->mode) == GTE_IO_COPY)
         GTE_REQUIRE("gte_step_host", io->dev_actions != nullptr && io->dev_results != nullptr &&
                                      (reinterpret_cast<uintptr_t>(io->dev_results) & 7u) == 0);

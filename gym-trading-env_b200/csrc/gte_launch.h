@@ -30,7 +30,7 @@ cudaError_t launch_step(const GteParams& P, const GteData& D, const GteState& S,
                         const GteStepOut& O, int autoreset, cudaStream_t stream);
 cudaError_t launch_step_range(const GteParams& P, const GteData& D, const GteState& S, const void* actions,
                               const GteStepOut& O, int autoreset, int env_begin, int env_end, int chunk_flags,
-                              cudaStream_t stream, float* obs_rows);
+                              cudaStream_t stream, float* obs_rows, bool obs_on_host = false);
 cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteState& S, const GteHostIO& io,
                              const GteStepOut& O, float* obs, int autoreset, int variant, int* mode_used,
                              cudaStream_t stream);

@@ -20,7 +20,7 @@ template <int MIN_CTAS>
 __global__ void __launch_bounds__(kStepThreads, MIN_CTAS)
 step_kernel(const GteParams P, const GteData D, const GteState S, const void* __restrict__ actions, const StepConsts K0,
             const GteStepOut O, int autoreset, int tiles_per_cta, int env_begin, int env_end, int chunk_flags,
-            float* __restrict__ obs_rows) {
+            float* __restrict__ obs_rows, int obs_on_host) {
     // the positions table in shared memory: a per-lane index into the kernel-parameter constant bank would be
     // replayed once per distinct address
     __shared__ double s_pos[GTE_MAX_POSITIONS];
@@ -38,18 +38,12 @@ step_kernel(const GteParams P, const GteData D, const GteState S, const void* __
     const int64_t base0 = (int64_t)env_begin + (int64_t)blockIdx.x * tiles_per_cta * kStepThreads;
     for (int t = 0; t < tiles_per_cta; ++t) {
         const int64_t i = base0 + (int64_t)t * kStepThreads + threadIdx.x;
-        if (i < env_end) {
-            const StepThreadOut r = step_env_now(P, D, S, actions, K, O, tick, ring_slot, autoreset, (int)i, acc, s_pos);
-            if (obs_rows != nullptr) {
-                // windows=None (environments.py:156-157): the observation is the single row idx, written by the
-                // env's own thread -> one launch per lockstep iteration at small N
-                const int F = P.n_static + P.n_dyn;
-                const float* __restrict__ f = D.features + ((int64_t)r.ds * P.t_stride + r.idx) * P.n_static;
-                float* __restrict__ o = obs_rows + i * F;
-                for (int c = 0; c < P.n_static; ++c) o[c] = __ldg(f + c);
-                if (P.n_dyn > 0) { o[P.n_static] = r.dyn_pos; o[P.n_static + 1] = r.dyn_rp; }
-            }
-        }
+        const bool valid = i < env_end;
+        StepThreadOut r = {};
+        if (valid) r = step_env_now(P, D, S, actions, K, O, tick, ring_slot, autoreset, (int)i, acc, s_pos);
+        // windows=None (environments.py:156-157): the observation is the single row idx, written by the step kernel
+        // itself -> one launch per lockstep iteration at small N
+        if (obs_rows != nullptr) write_obs_rows(P, D, obs_rows, i, valid, r, obs_on_host != 0);
     }
     reduce_metrics<kStepThreads>(acc, O, S, chunk_flags);
 }
@@ -98,12 +92,8 @@ rollout_kernel(const GteParams P, const GteData D, const GteState S, const void*
             if (o.pre_reset_portfolio) o.pre_reset_portfolio += (int64_t)k * 4 * N;
             const StepThreadOut r = step_env<false>(P, D, S, K, o, tick0 + (uint64_t)k, ring_slot_of(P, clock0 + 1ull + (uint64_t)k),
                                                     autoreset, (int)i, in, p0, p1, acc, s_pos, &e);
-            if (obs_rows != nullptr && (keep_obs || k == n_steps - 1)) {
-                const float* __restrict__ f = D.features + ((int64_t)r.ds * P.t_stride + r.idx) * P.n_static;
-                float* __restrict__ orow = obs_rows + (keep_obs ? (int64_t)k * N * F : 0) + i * F;
-                for (int c = 0; c < P.n_static; ++c) orow[c] = __ldg(f + c);
-                if (P.n_dyn > 0) { orow[P.n_static] = r.dyn_pos; orow[P.n_static + 1] = r.dyn_rp; }
-            }
+            if (obs_rows != nullptr && (keep_obs || k == n_steps - 1))
+                write_obs_rows(P, D, obs_rows + (keep_obs ? (int64_t)k * N * F : 0), i, true, r, false);
         }
     }
     if (valid) store_env(S, i, e);
@@ -159,7 +149,7 @@ __device__ __forceinline__ int64_t load_action_volatile(const void* actions, int
 
 __global__ void __launch_bounds__(kStepThreads, 2)
 serve_kernel(const GteParams P, const GteData D, const GteState S, const StepConsts K0, const GteStepOut O, int autoreset,
-             float* __restrict__ obs_rows, ServeCtl* ctl, unsigned long long* dctl, uint32_t first_seq,
+             float* __restrict__ obs_rows, int obs_on_host, ServeCtl* ctl, unsigned long long* dctl, uint32_t first_seq,
              unsigned long long idle_ns) {
     __shared__ double s_pos[GTE_MAX_POSITIONS];
     __shared__ int s_T0;
@@ -171,7 +161,6 @@ serve_kernel(const GteParams P, const GteData D, const GteState S, const StepCon
     K.T0 = s_T0;
     const int64_t i = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
     const bool valid = i < P.n_envs;
-    const int F = P.n_static + P.n_dyn;
     for (uint32_t seq = first_seq;; ++seq) {
         // ---- wait for the host: CTA 0 watches the mapped control block, the others two words in device memory
         //      dctl[0] = (seq << 9) | (leave << 8) | action_bytes, dctl[1] = action pointer (written first)
@@ -207,19 +196,15 @@ serve_kernel(const GteParams P, const GteData D, const GteState S, const StepCon
         MetricAcc acc;
         const uint64_t tick = __ldcg(S.tick);
         const int ring_slot = ring_slot_of(P, __ldcg(S.ring_clock) + 1ull);
+        StepThreadOut r = {};
         if (valid) {
             const int64_t a = load_action_volatile(actions, action_bytes, i);         // over PCIe, beside the state loads
             const EnvIn in = make_env_in(P, D, S, K, load_env_regs<true>(P, S, i), a);
             double p0, p1;
             load_prices(P, D, in, p0, p1);
-            const StepThreadOut r = step_env(P, D, S, K, O, tick, ring_slot, autoreset, (int)i, in, p0, p1, acc, s_pos);
-            if (obs_rows != nullptr) {
-                const float* __restrict__ f = D.features + ((int64_t)r.ds * P.t_stride + r.idx) * P.n_static;
-                float* __restrict__ o = obs_rows + i * F;
-                for (int c = 0; c < P.n_static; ++c) o[c] = __ldg(f + c);
-                if (P.n_dyn > 0) { o[P.n_static] = r.dyn_pos; o[P.n_static + 1] = r.dyn_rp; }
-            }
+            r = step_env(P, D, S, K, O, tick, ring_slot, autoreset, (int)i, in, p0, p1, acc, s_pos);
         }
+        if (obs_rows != nullptr) write_obs_rows(P, D, obs_rows, i, valid, r, obs_on_host != 0);
         GteStepOut o = O;
         o.seq_value = seq;                               // what the last CTA publishes to the host when all is visible
         reduce_metrics<kStepThreads>(acc, o, S, kChunkFirst | kChunkLast);
@@ -366,7 +351,7 @@ int step_grid(int n_envs) {
 
 cudaError_t launch_step_range(const GteParams& P, const GteData& D, const GteState& S, const void* actions,
                               const GteStepOut& O, int autoreset, int env_begin, int env_end, int chunk_flags,
-                              cudaStream_t stream, float* obs_rows) {
+                              cudaStream_t stream, float* obs_rows, bool obs_on_host) {
     const StepConsts K = make_step_consts(P);
     const int n = env_end - env_begin;
     const int grid = step_grid(n), tpc = step_tiles_per_cta(n);
@@ -383,7 +368,7 @@ cudaError_t launch_step_range(const GteParams& P, const GteData& D, const GteSta
     // dependent fp64 chains, not by resident warps, loads or stores (profiles/r02_tuning.md has the diagnostic runs)
     auto kern = step_kernel<3>;
     return launch_pdl(kern, dim3(grid), dim3(kStepThreads), 0, stream, P, D, S, actions, K, O, autoreset, tpc,
-                      env_begin, env_end, chunk_flags, obs_rows);
+                      env_begin, env_end, chunk_flags, obs_rows, obs_on_host ? 1 : 0);
 }
 
 cudaError_t launch_step(const GteParams& P, const GteData& D, const GteState& S, const void* actions,
@@ -623,6 +608,7 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
         }
         GteParams p0 = P;
         p0.action_bytes = 0;                                 // travels with every request, not with the launch
+        if (io.obs_host != nullptr) obs = static_cast<float*>(io.obs_host);   // windows == 0: rows written straight to the host
         const bool same = h->serving && memcmp(&h->sp, &p0, sizeof(p0)) == 0 && memcmp(&h->sd, &D, sizeof(D)) == 0 &&
                           memcmp(&h->ss, &S, sizeof(S)) == 0 && h->so.metrics_step == O.metrics_step &&
                           h->so.reward == o.reward && h->sobs == obs && h->sauto == autoreset;
@@ -635,8 +621,8 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
             if ((le = cudaMemsetAsync(h->dctl, 0, 64, h->serve)) != cudaSuccess) return le;
             h->ctl->alive = 1u;
             const int grid = (int)((N + kStepThreads - 1) / kStepThreads);
-            serve_kernel<<<grid, kStepThreads, 0, h->serve>>>(p0, D, S, make_step_consts(p0), o, autoreset, obs, h->ctl, h->dctl,
-                                                              seq, serve_idle_ns());
+            serve_kernel<<<grid, kStepThreads, 0, h->serve>>>(p0, D, S, make_step_consts(p0), o, autoreset, obs,
+                                                              io.obs_host != nullptr ? 1 : 0, h->ctl, h->dctl, seq, serve_idle_ns());
             if ((le = cudaGetLastError()) != cudaSuccess) return le;
             h->serving = true;
             h->sp = p0; h->sd = D; h->ss = S; h->so = O; h->so.reward = o.reward; h->sobs = obs; h->sauto = autoreset;
@@ -670,20 +656,32 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
         if ((e = cudaStreamWaitEvent(stream, h->ev_in, 0)) != cudaSuccess) return e;
         actions = io.dev_actions;
     }
-    float* obs_rows = P.windows == 0 ? obs : nullptr;        // windows=None: the step kernel writes the one-row observation
-    if ((e = launch_step_range(P, D, S, actions, o, autoreset, 0, P.n_envs, kChunkFirst | kChunkLast, stream, obs_rows)) != cudaSuccess) return e;
+    // windows=None: the step kernel writes the one-row observation itself — in the MAPPED mode straight into the host
+    // copy when the caller wants the observations there
+    const bool obs_mapped = P.windows == 0 && mode == GTE_IO_MAPPED && io.obs_host != nullptr;
+    float* obs_rows = P.windows == 0 ? (obs_mapped ? static_cast<float*>(io.obs_host) : obs) : nullptr;
+    if ((e = launch_step_range(P, D, S, actions, o, autoreset, 0, P.n_envs, kChunkFirst | kChunkLast, stream, obs_rows, obs_mapped)) != cudaSuccess) return e;
     if (io.step_done_event != nullptr &&
         (e = cudaEventRecord(static_cast<cudaEvent_t>(io.step_done_event), stream)) != cudaSuccess) return e;
+    const bool obs_copy = io.obs_host != nullptr && !obs_mapped;     // one more D2H behind the gather, on `stream` itself
     if (mode == GTE_IO_COPY) {
         if ((e = cudaEventRecord(h->ev_step, stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(h->out, h->ev_step, 0)) != cudaSuccess) return e;
         if ((e = cudaMemcpyAsync(io.results, io.dev_results, (size_t)GTE_HOST_RESULT_BYTES(N), cudaMemcpyDeviceToHost, h->out)) != cudaSuccess) return e;
         if (P.windows > 0 && (e = launch_obs_range(P, D, S, obs, variant, 0, P.n_envs, stream)) != cudaSuccess) return e;
+        if (obs_copy) {
+            if ((e = cudaMemcpyAsync(io.obs_host, obs, (size_t)io.obs_bytes, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+            if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+        }
         return cudaStreamSynchronize(h->out);               // reward / flags / error flag are on the host; the gather runs on
     }
     // MAPPED: the kernel itself wrote the host block and, last, the call's sequence number: poll that word instead
     // of going through the driver (the lowest-latency completion signal there is)
     if (P.windows > 0 && (e = launch_obs_range(P, D, S, obs, variant, 0, P.n_envs, stream)) != cudaSuccess) return e;
+    if (obs_copy) {
+        if ((e = cudaMemcpyAsync(io.obs_host, obs, (size_t)io.obs_bytes, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+        return cudaStreamSynchronize(stream);               // everything of this iteration, observations included
+    }
     for (uint32_t spins = 1; *seq_word != seq; ++spins) {
         _mm_pause();
         if ((spins & 0x3fffu) == 0) {                        // a faulted kernel never writes the word: ask the driver now and then

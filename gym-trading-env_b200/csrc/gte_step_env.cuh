@@ -217,6 +217,39 @@ __device__ __forceinline__ StepThreadOut step_env_now(const GteParams& P, const 
     return step_env(P, D, S, K, O, tick, ring_slot, autoreset, i, in, p0, p1, acc, pos_tab);
 }
 
+// The one-row observations (windows=None, environments.py:156-157) of the 32 consecutive envs of a warp; every lane of
+// the warp must call it (valid = this lane's env exists and r holds its step's result).
+//   coalesced = false: each lane writes its own row — 4-byte stores 4*F bytes apart; fine for device memory, where L2
+//                      merges the partial sectors;
+//   coalesced = true : the warp's rows are ONE contiguous block of 32*F floats: lane l writes elements l, l+32, ...,
+//                      fetching (row, dataset, dynamic features) of the owning env by shuffle -> full 128-byte stores.
+//                      For MAPPED HOST memory, where every partial-sector store is its own PCIe transaction
+//                      (4096 envs: 60 us -> 27 us per host step).
+__device__ __forceinline__ void write_obs_rows(const GteParams& P, const GteData& D, float* __restrict__ obs_rows, int64_t i,
+                                               bool valid, const StepThreadOut& r, bool coalesced) {
+    const int F = P.n_static + P.n_dyn;
+    if (!coalesced) {
+        if (valid) {
+            const float* __restrict__ f = D.features + ((int64_t)r.ds * P.t_stride + r.idx) * P.n_static;
+            float* __restrict__ o = obs_rows + i * F;
+            for (int c = 0; c < P.n_static; ++c) o[c] = __ldg(f + c);
+            if (P.n_dyn > 0) { o[P.n_static] = r.dyn_pos; o[P.n_static + 1] = r.dyn_rp; }
+        }
+        return;
+    }
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    float* __restrict__ o = obs_rows + (i - lane) * F;           // row of lane 0's env
+    for (int j = lane; j < 32 * F; j += 32) {                    // F trips for every lane
+        const int e = j / F, c = j - e * F;
+        const int idx = __shfl_sync(FULL, r.idx, e), ds = __shfl_sync(FULL, r.ds, e);
+        const float dp = __shfl_sync(FULL, r.dyn_pos, e), dr = __shfl_sync(FULL, r.dyn_rp, e);
+        const bool ok = __shfl_sync(FULL, (int)valid, e) != 0;
+        if (ok) o[j] = c < P.n_static ? __ldg(D.features + ((int64_t)ds * P.t_stride + idx) * P.n_static + c)
+                                      : (c == P.n_static ? dp : dr);
+    }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = dadd(v, __shfl_down_sync(0xffffffffu, v, o));

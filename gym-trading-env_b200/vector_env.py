@@ -595,6 +595,8 @@ class TradingVectorEnv(_VectorEnvBase):
             io = _cabi.GteHostIO()
             io.results, io.dev_results = blk.data_ptr(), self._result_block.data_ptr()
             io.dev_actions, io.mode = self._actions_raw.data_ptr(), _cabi.IO_MODES[self.host_io]
+            if self.output == "numpy":                       # the observation batch is delivered to the host as well
+                io.obs_host, io.obs_bytes = self._host["obs_t"].data_ptr(), self._obs.numel() * 4
             self._io, self._io_mode_used = io, C.c_int(0)
             self._io_ref, self._io_mode_ref = C.byref(io), C.byref(self._io_mode_used)
             # recorded by gte_step_host right behind the step kernel: lets the metric all-reduce run beside the gather
@@ -668,7 +670,7 @@ class TradingVectorEnv(_VectorEnvBase):
                 _cabi.check(rc, "gte_step_obs")
             return self._obs, self._reward, self._term_b, self._trunc_b, self.infos
         host_in = not (isinstance(actions, torch.Tensor) and actions.is_cuda)
-        if (host_in and self.output == "hybrid" and self._track_ids is None and not self.keep_final_obs
+        if (host_in and self.output != "torch" and self._track_ids is None and not self.keep_final_obs
                 and not self.cuda_graph and self._kernel_events is None and self.autoreset):
             return self._step_host(actions)
         with torch.cuda.device(self.device):
@@ -708,8 +710,9 @@ class TradingVectorEnv(_VectorEnvBase):
             return ret
 
     def _step_host(self, actions):
-        """output="hybrid": ONE blocking C call (gte_step_host) — host actions in, step kernel, reward / terminated /
-        truncated / error flag back in one pinned block, gather enqueued; returns as soon as the block has landed."""
+        """output="hybrid" / "numpy" with host actions: ONE blocking C call (gte_step_host) — host actions in, step
+        kernel, reward / terminated / truncated / error flag back in one pinned block, gather enqueued; returns as soon
+        as the block has landed ("numpy": and the observation batch, delivered into pinned host memory too)."""
         ent = self._pin_ident.get(id(actions))
         if ent is not None and ent[0] is actions:            # a pinned array seen before (kept alive by the cache)
             ptr, nb = ent[1], ent[2]
@@ -748,7 +751,7 @@ class TradingVectorEnv(_VectorEnvBase):
             self._issue_metric_allreduce(None, after=self._step_done)
         if hb["error"][0]:
             self._raise_on_flag(int(hb["error"][0]))
-        return self._obs, hb["reward"], hb["terminated"], hb["truncated"], self.infos
+        return (hb["obs"] if self.output == "numpy" else self._obs), hb["reward"], hb["terminated"], hb["truncated"], self.infos
 
     def _step_launch(self, act, main):
         if self._red_stream is not None and self._red_snapshot is not None:

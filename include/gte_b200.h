@@ -229,6 +229,12 @@ typedef struct GteHostIO {
     void* dev_results;               /* DEVICE block of GTE_HOST_RESULT_BYTES(N) bytes, same layout (COPY mode)        */
     void* step_done_event;           /* cudaEvent_t recorded on `stream` right behind the step kernel, or NULL: lets the
                                         caller hang more work (the metric all-reduce) beside the gather                */
+    void* obs_host;                  /* HOST, pinned, or NULL: the observation batch is ALSO delivered here (a host policy
+                                        that reads observations: gymnasium / stable-baselines3 numpy semantics) — with
+                                        windows == 0 in the MAPPED / SERVER modes the step kernel writes its one-row
+                                        observations straight into it (the device `obs` is then left untouched), else
+                                        one more device-to-host copy behind the gather; the call returns when it landed */
+    int64_t obs_bytes;               /* size of the observation batch in bytes (N * W * F * 4)                          */
     int32_t mode;                    /* enum GteHostIOMode                                                             */
     int32_t reserved;
 } GteHostIO;
@@ -286,7 +292,8 @@ int gte_step_obs(const GteParams* params, const GteData* data, const GteState* s
 /* One lockstep iteration for a policy that lives on the HOST — what a gymnasium VectorEnv.step(numpy actions) does
  * (environments.py:233-272 for N envs) — as ONE blocking call: host actions in -> step kernel -> reward / flags / error
  * flag out -> gather enqueued.  Returns once io->results holds this iteration's values; the observation gather may
- * still be running on `stream` (the observations stay device-resident for the next policy forward pass).
+ * still be running on `stream` (the observations stay device-resident for the next policy forward pass) — unless
+ * io->obs_host asks for the observations on the host too, in which case the call also waits for those.
  * out->reward / terminated / truncated / error_out are ignored: the call points them into the result block itself.
  * COPY mode: one H2D cudaMemcpyAsync (N * action_bytes) on a library-owned stream, the step kernel, ONE D2H
  * cudaMemcpyAsync (GTE_HOST_RESULT_BYTES(N)) on a second library-owned stream beside the gather.  MAPPED mode: no copy

@@ -382,3 +382,35 @@ def test_resident_server_kernel_matches_the_oracle_and_survives_interruptions():
         bad.step(np.full(64, 9, np.int8))
     bad.step(np.zeros(64, np.int8))
     bad.close()
+
+
+@pytest.mark.parametrize("host_io", ["auto", "copy", "server"])
+def test_numpy_mode_with_one_row_observations_matches_the_oracle(host_io):
+    """output="numpy", windows=None (the gymnasium / SB3 shape of the reference's default env): actions from the host,
+    observations + reward + flags back on the host in one C call.  "auto" (mapped at this size) and "server" have the
+    step kernel write the observation rows straight into pinned host memory; "copy" goes through the copy engines."""
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    from gym_trading_env_b200 import _cabi
+    N = 2048
+    series = gte.frame_to_arrays(gte.make_gbm_ohlcv(4000, seed=8))
+    pos = [-1, 0, 1]
+    kw = dict(positions=pos, windows=None, max_episode_duration=30, **FEES)
+    env = gte.TradingVectorEnv(series, num_envs=N, seed=4, verbose=0, output="numpy", host_io=host_io, **kw)
+    o = orc.OracleVecEnv(series.features, series.price, num_envs=N, seed=4, **kw)
+    obs, _ = env.reset()
+    assert isinstance(obs, np.ndarray)
+    H.assert_bits(obs, o.reset(), "reset obs")
+    rng = np.random.default_rng(2)
+    for k in range(90):
+        a = rng.integers(0, len(pos), size=N)
+        obs, rew, term, trunc, infos = env.step(a.astype(np.int8) if k % 2 else a)
+        o.step(a)
+        assert isinstance(obs, np.ndarray) and obs.shape == (N, 10) and obs.dtype == np.float32
+        H.assert_bits(obs, o.obs, f"step {k} obs")
+        H.assert_close64(rew, o.reward, f"step {k} reward")
+        H.assert_bits(term.view(np.uint8), o.terminated, f"step {k} terminated")
+        H.assert_bits(trunc.view(np.uint8), o.truncated, f"step {k} truncated")
+    want = {"auto": _cabi.IO_MAPPED, "copy": _cabi.IO_COPY, "server": _cabi.IO_SERVER}[host_io]
+    assert env._io_mode_used.value == want
+    env.close()
