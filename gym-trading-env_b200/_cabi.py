@@ -106,7 +106,7 @@ class GteInfo(C.Structure):
 
 
 EXPORTS = ["gte_version", "gte_last_error", "gte_build_id", "gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs",
-           "gte_step_host", "gte_serve_stop", "gte_rollout", "gte_info", "gte_obs_variant_for", "gte_default_chunks", "gte_struct_size",
+           "gte_step_host", "gte_step_host_begin", "gte_step_host_end", "gte_serve_stop", "gte_rollout", "gte_info", "gte_obs_variant_for", "gte_default_chunks", "gte_struct_size",
            "gte_step_obs_launches"]
 
 
@@ -190,11 +190,16 @@ def load():
     lib.gte_obs_variant_for.argtypes = [P(GteParams), P(GteData)]
     lib.gte_step_obs_launches.argtypes = [P(GteParams), P(GteData), C.c_int, C.c_int]
     lib.gte_step_obs_launches.restype = C.c_int
+    lib.gte_step_host_begin.argtypes = [P(GteParams), P(GteData), P(GteState), P(GteHostIO), P(GteStepOut), C.c_void_p,
+                                        C.c_int, C.c_int, C.c_void_p]
+    lib.gte_step_host_begin.restype = C.c_int
+    lib.gte_step_host_end.argtypes = [P(GteHostIO)]
+    lib.gte_step_host_end.restype = C.c_int
     lib.gte_serve_stop.argtypes = []
     lib.gte_serve_stop.restype = C.c_int
     lib.gte_default_chunks.argtypes = [C.c_int]
     lib.gte_default_chunks.restype = C.c_int
-    for name in ("gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs", "gte_step_host", "gte_serve_stop", "gte_rollout", "gte_info",
+    for name in ("gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs", "gte_step_host", "gte_step_host_begin", "gte_step_host_end", "gte_serve_stop", "gte_rollout", "gte_info",
                  "gte_obs_variant_for"):
         getattr(lib, name).restype = C.c_int
     lib.gte_struct_size.argtypes = [C.c_int]

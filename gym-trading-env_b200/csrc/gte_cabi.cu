@@ -142,6 +142,25 @@ int gte_step_host(const GteParams* params, const GteData* data, const GteState* 
                                                              mode_used, static_cast<cudaStream_t>(stream)));
 }
 
+int gte_step_host_begin(const GteParams* params, const GteData* data, const GteState* state, const GteHostIO* io,
+                        const GteStepOut* out, float* obs, int autoreset, int variant, void* stream) {
+    if (int rc = check_common("gte_step_host_begin", params, data, state)) return rc;
+    GTE_REQUIRE("gte_step_host_begin", io != nullptr && io->actions != nullptr && io->results != nullptr);
+    if (int rc = check_step_out("gte_step_host_begin", io->actions, out, true)) return rc;
+    GTE_REQUIRE("gte_step_host_begin", io->dev_actions != nullptr && io->dev_results != nullptr);
+    GTE_REQUIRE("gte_step_host_begin", ((reinterpret_cast<uintptr_t>(io->results) | reinterpret_cast<uintptr_t>(io->dev_results)) & 7u) == 0);
+    GTE_REQUIRE("gte_step_host_begin", io->obs_host == nullptr && out->seq_out == nullptr);
+    if (int rc = check_variant("gte_step_host_begin", params, data, variant)) return rc;
+    if (int rc = check_obs_ptr("gte_step_host_begin", params, data, obs, variant)) return rc;
+    return check_cuda("gte_step_host_begin", gte::launch_step_host_begin(*params, *data, *state, *io, *out, obs, autoreset,
+                                                                         variant, static_cast<cudaStream_t>(stream)));
+}
+
+int gte_step_host_end(const GteHostIO* io) {
+    if (io == nullptr || io->results == nullptr) return fail_arg("gte_step_host_end", "io / io->results");
+    return check_cuda("gte_step_host_end", gte::launch_step_host_end(*io));
+}
+
 int gte_serve_stop(void) { return check_cuda("gte_serve_stop", gte::serve_quiesce()); }
 
 int gte_rollout(const GteParams* params, const GteData* data, const GteState* state, const void* actions,

@@ -50,6 +50,9 @@ cudaError_t launch_fused_step_obs(const GteParams& P, const GteData& D, const Gt
                                   const StepConsts& K, const GteStepOut& O, float* obs, int autoreset, int variant,
                                   cudaStream_t stream, bool* done);
 bool step_obs_is_fused(const GteParams& P, const GteData& D, int variant);
+cudaError_t launch_step_host_begin(const GteParams& P, const GteData& D, const GteState& S, const GteHostIO& io,
+                                   const GteStepOut& O, float* obs, int autoreset, int variant, cudaStream_t stream);
+cudaError_t launch_step_host_end(const GteHostIO& io);
 int default_chunks(int n_envs);
 int host_io_mode(const GteParams& P, int mode);
 cudaError_t serve_quiesce();

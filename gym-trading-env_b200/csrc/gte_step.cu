@@ -516,6 +516,8 @@ struct HostIOStreams {
     unsigned long long* dctl = nullptr;
     bool serving = false;
     GteParams sp; GteData sd; GteState ss; GteStepOut so; float* sobs = nullptr; int sauto = 0;
+    // gte_step_host_begin / _end: completion events of the result copies in flight, keyed by the host result block
+    struct Pending { const void* results = nullptr; cudaEvent_t ev = nullptr; cudaEvent_t ev_in = nullptr; cudaEvent_t ev_step = nullptr; } pending[4];
 };
 static HostIOStreams g_hio[16];
 
@@ -690,6 +692,60 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
         }
     }
     return cudaSuccess;
+}
+
+// ---- the same iteration split in two: begin() enqueues everything and returns, end() waits for the result block -----
+// A caller that alternates TWO GteHostIO sets (host + device result block and action staging each) can call
+// begin(k+1) before end(k): the device-to-host copy of iteration k then runs under the action copy, transition and
+// gather of iteration k+1 (copy engines only; the blocks of a set are free again once its end() has returned).
+cudaError_t launch_step_host_begin(const GteParams& P, const GteData& D, const GteState& S, const GteHostIO& io,
+                                   const GteStepOut& O, float* obs, int autoreset, int variant, cudaStream_t stream) {
+    const int64_t N = P.n_envs;
+    const int ab = P.action_bytes == 0 ? 8 : P.action_bytes;
+    HostIOStreams* h = nullptr;
+    cudaError_t e;
+    if ((e = hio_for_current_device(&h)) != cudaSuccess) return e;
+    if ((e = serve_quiesce()) != cudaSuccess) return e;
+    HostIOStreams::Pending* slot = nullptr;
+    for (auto& p : h->pending) if (p.results == io.results) slot = &p;
+    if (slot == nullptr) for (auto& p : h->pending) if (p.results == nullptr) { slot = &p; break; }
+    if (slot == nullptr) return cudaErrorInvalidValue;       // more than 4 result blocks in flight
+    if (slot->ev == nullptr) {
+        if ((e = cudaEventCreateWithFlags(&slot->ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&slot->ev_in, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&slot->ev_step, cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    slot->results = io.results;
+    char* blk = static_cast<char*>(io.dev_results);
+    GteStepOut o = O;
+    o.reward = reinterpret_cast<double*>(blk);
+    o.terminated = reinterpret_cast<uint8_t*>(blk + GTE_HOST_RESULT_TERM_OFFSET(N));
+    o.truncated = reinterpret_cast<uint8_t*>(blk + GTE_HOST_RESULT_TRUNC_OFFSET(N));
+    o.error_out = reinterpret_cast<int32_t*>(blk + GTE_HOST_RESULT_ERROR_OFFSET(N));
+    o.seq_out = nullptr;
+    // this set's staging buffer is free: its previous iteration's end() has returned (the caller's contract)
+    if ((e = cudaMemcpyAsync(io.dev_actions, io.actions, (size_t)(N * ab), cudaMemcpyHostToDevice, h->in)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(slot->ev_in, h->in)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(stream, slot->ev_in, 0)) != cudaSuccess) return e;
+    float* obs_rows = P.windows == 0 ? obs : nullptr;
+    if ((e = launch_step_range(P, D, S, io.dev_actions, o, autoreset, 0, P.n_envs, kChunkFirst | kChunkLast, stream, obs_rows)) != cudaSuccess) return e;
+    if (io.step_done_event != nullptr &&
+        (e = cudaEventRecord(static_cast<cudaEvent_t>(io.step_done_event), stream)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(slot->ev_step, stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(h->out, slot->ev_step, 0)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(io.results, io.dev_results, (size_t)GTE_HOST_RESULT_BYTES(N), cudaMemcpyDeviceToHost, h->out)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(slot->ev, h->out)) != cudaSuccess) return e;
+    if (P.windows > 0 && (e = launch_obs_range(P, D, S, obs, variant, 0, P.n_envs, stream)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+cudaError_t launch_step_host_end(const GteHostIO& io) {
+    HostIOStreams* h = nullptr;
+    cudaError_t e;
+    if ((e = hio_for_current_device(&h)) != cudaSuccess) return e;
+    for (auto& p : h->pending)
+        if (p.results == io.results && p.ev != nullptr) return cudaEventSynchronize(p.ev);
+    return cudaErrorInvalidValue;                            // no begin() for this result block
 }
 
 cudaError_t launch_info(const GteParams& P, const GteData& D, const GteState& S, const GteInfo& I,

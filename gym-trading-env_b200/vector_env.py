@@ -171,7 +171,7 @@ class LazyInfos(Mapping):
     def __getitem__(self, key):
         e = self._env
         if key == "reward":               # host-output modes: the step's rewards are in the pinned result block
-            return e._host["reward"] if (e.output != "torch" and e._host is not None) else e._reward
+            return e._last_reward_host if (e.output != "torch" and e._last_reward_host is not None) else e._reward
         if key == "episode_metrics":
             return e.get_metrics()
         if key not in self.KEYS:
@@ -337,6 +337,8 @@ class TradingVectorEnv(_VectorEnvBase):
         self._copy_in = None
         self._pin_ident = {}                 # id(array) -> (array, pointer, itemsize) of pinned action arrays seen by step()
         self._last_actions = None            # the actions of the last step (infos["position_index"]); None after a reset
+        self._last_reward_host = None        # host-output modes: the reward array the last step returned
+        self._async = None                   # step_async / step_wait: two wire sets + the queue of iterations in flight
         self._track_ids = None
         self._limit_price = None
         self._red_stream = None              # enable_metric_allreduce(): side stream of the per-iteration all-reduce
@@ -749,9 +751,109 @@ class TradingVectorEnv(_VectorEnvBase):
             _cabi.check(rc, "gte_step_host")
         if red is not None:
             self._issue_metric_allreduce(None, after=self._step_done)
+        self._last_reward_host = hb["reward"]
         if hb["error"][0]:
             self._raise_on_flag(int(hb["error"][0]))
         return (hb["obs"] if self.output == "numpy" else self._obs), hb["reward"], hb["terminated"], hb["truncated"], self.infos
+
+    # ------------------------------------------------------------------ step_async / step_wait (host policy, pipelined)
+    def _async_sets(self):
+        """Two independent wire sets (pinned result block, device result block, device + pinned action staging, one
+        GteHostIO each) for step_async / step_wait."""
+        if self._async is None:
+            N, dev = self.num_envs, self.device
+            toff, uoff, eoff, nbytes = _cabi.host_result_layout(N)
+            sets = []
+            for _ in range(2):
+                host = torch.zeros(nbytes, dtype=torch.uint8, pin_memory=True)
+                devb = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+                dact = torch.zeros(N * 8, dtype=torch.uint8, device=dev)
+                r = host.numpy()
+                io = _cabi.GteHostIO()
+                io.results, io.dev_results, io.dev_actions = host.data_ptr(), devb.data_ptr(), dact.data_ptr()
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                sets.append({"io": io, "io_ref": C.byref(io), "host": host, "dev": devb, "dact": dact, "event": ev,
+                             "stage": {}, "reward": r[:8 * N].view(np.float64),
+                             "terminated": r[toff:toff + N].view(np.bool_), "truncated": r[uoff:uoff + N].view(np.bool_),
+                             "error": r[eoff:eoff + 4].view(np.int32)})
+            self._async = {"sets": sets, "pending": [], "n": 0}
+        return self._async
+
+    def step_async(self, actions):
+        """Enqueue one lockstep iteration for host actions and return at once (`output="hybrid"`): the action copy, the
+        transition, the copy of the result block and the gather are all in flight when this returns; :meth:`step_wait`
+        hands out the results.  Up to TWO iterations may be in flight — ``step_async(a[k+1])`` before ``step_wait()`` of
+        iteration k — so that the device-to-host copy of iteration k runs under iteration k+1 (what a caller that does
+        not need iteration k's rewards to choose iteration k+1's actions wants: scripted or replayed actions, a policy
+        that reads the device-resident observations).  A pinned ``actions`` array is read in place: do not overwrite it
+        before the matching ``step_wait()``."""
+        if self.output != "hybrid" or self._track_ids is not None or self.keep_final_obs or self.cuda_graph or not self.autoreset:
+            raise ValueError("step_async() needs output='hybrid' with autoreset, without tracking / final_obs / CUDA graphs")
+        st = self._async_sets()
+        if len(st["pending"]) >= 2:
+            raise RuntimeError("two iterations are already in flight: call step_wait() first")
+        k = st["n"] & 1
+        ws = st["sets"][k]
+        self._host_buffers()
+        a = np.asarray(actions)
+        if a.shape != (self.num_envs,):
+            raise ValueError(f"actions must have shape ({self.num_envs},), got {a.shape}")
+        pinned = False
+        if a.dtype in _WIRE_ACTION_DTYPES and a.flags.c_contiguous:
+            known = self._host["pinned"].get(a.ctypes.data)
+            if known is None and a.flags.writeable and len(self._host["pinned"]) < 64:
+                known = self._host["pinned"][a.ctypes.data] = bool(torch.from_numpy(a).is_pinned())
+            pinned = bool(known)
+        if not pinned:                                   # this set's own staging buffer: free since its last step_wait()
+            dt = a.dtype if a.dtype in _WIRE_ACTION_DTYPES else np.dtype(np.int64)
+            buf = ws["stage"].get(dt)
+            if buf is None:
+                t = torch.empty(self.num_envs, dtype=torch.from_numpy(np.empty(0, dt)).dtype, pin_memory=True)
+                buf = ws["stage"][dt] = t.numpy()
+                ws["stage"][("t", dt)] = t
+            buf[...] = a
+            a = buf
+        io = ws["io"]
+        io.actions = a.ctypes.data
+        red = self._red_stream
+        if red is not None:
+            if self._red_snapshot is not None:
+                torch.cuda.current_stream(self.device).wait_event(self._red_snapshot)
+            io.step_done_event = ws["event"].cuda_event
+        self._P.action_bytes = a.dtype.itemsize
+        self._tick += 1
+        self._last_actions = a
+        f = self._fast_args
+        try:
+            with torch.cuda.device(self.device):
+                rc = self._lib.gte_step_host_begin(f[0], f[1], f[2], ws["io_ref"], f[3], f[4], 1, self._obs_variant,
+                                                   torch.cuda.current_stream(self.device).cuda_stream)
+        finally:
+            self._P.action_bytes = 0
+        if rc:
+            _cabi.check(rc, "gte_step_host_begin")
+        if red is not None:
+            self._issue_metric_allreduce(None, after=ws["event"])
+        st["pending"].append(k)
+        st["n"] += 1
+
+    def step_wait(self):
+        """Results of the OLDEST iteration enqueued by :meth:`step_async`: ``(obs, reward, terminated, truncated,
+        infos)`` — numpy views of that iteration's pinned result block (valid until the second ``step_async`` from
+        now); ``obs`` is the device-resident observation tensor, which the newest enqueued iteration writes."""
+        st = self._async
+        if st is None or not st["pending"]:
+            raise RuntimeError("step_wait() without a pending step_async()")
+        ws = st["sets"][st["pending"].pop(0)]
+        with torch.cuda.device(self.device):
+            rc = self._lib.gte_step_host_end(ws["io_ref"])
+        if rc:
+            _cabi.check(rc, "gte_step_host_end")
+        self._last_reward_host = ws["reward"]
+        if ws["error"][0]:
+            self._raise_on_flag(int(ws["error"][0]))
+        return self._obs, ws["reward"], ws["terminated"], ws["truncated"], self.infos
 
     def _step_launch(self, act, main):
         if self._red_stream is not None and self._red_snapshot is not None:
@@ -818,6 +920,7 @@ class TradingVectorEnv(_VectorEnvBase):
             if self.output == "numpy":
                 hb["obs_t"].copy_(self._obs, non_blocking=True)
             main.synchronize()
+        self._last_reward_host = hb["reward"]
         if hb["error"][0]:
             self._raise_on_flag(int(hb["error"][0]))
         obs = hb["obs"] if self.output == "numpy" else self._obs
@@ -836,6 +939,10 @@ class TradingVectorEnv(_VectorEnvBase):
         self.closed = True
 
     def close_extras(self, **kwargs):
+        if getattr(self, "_async", None) is not None:
+            while self._async["pending"]:                 # let the iterations in flight land before the buffers go
+                self._lib.gte_step_host_end(self._async["sets"][self._async["pending"].pop(0)]["io_ref"])
+            self._async = None
         if getattr(self, "host_io", None) == "server" and getattr(self, "_lib", None) is not None:
             self._lib.gte_serve_stop()           # the resident server kernel, if it is still waiting for requests
         self._host = None

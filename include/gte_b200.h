@@ -301,6 +301,17 @@ int gte_step_obs(const GteParams* params, const GteData* data, const GteState* s
 int gte_step_host(const GteParams* params, const GteData* data, const GteState* state, const GteHostIO* io,
                   const GteStepOut* out, float* obs, int autoreset, int variant, int* mode_used, void* stream);
 
+/* gte_step_host split in two (copy engines only; io->mode and io->obs_host are ignored / must be NULL): _begin enqueues
+ * the action copy, the transition, the copy of the result block and the gather, and returns at once; _end waits until
+ * io->results holds that iteration's values.  A caller that alternates TWO GteHostIO sets (results, dev_results and
+ * dev_actions each their own; out->reward / terminated / truncated are again ignored) may call _begin for iteration
+ * k+1 before _end for iteration k — what gymnasium 0.x / stable-baselines3 vector envs call step_async / step_wait:
+ * the device-to-host copy of iteration k then runs under the action copy, transition and gather of iteration k+1.
+ * A set's buffers are free for the next _begin once its _end has returned; at most 4 result blocks per device. */
+int gte_step_host_begin(const GteParams* params, const GteData* data, const GteState* state, const GteHostIO* io,
+                        const GteStepOut* out, float* obs, int autoreset, int variant, void* stream);
+int gte_step_host_end(const GteHostIO* io);
+
 /* Stop the resident server kernel of the current device (GTE_IO_SERVER), if one is running, and wait for it.  Every
  * other entry point does this implicitly before it enqueues anything. */
 int gte_serve_stop(void);

@@ -414,3 +414,46 @@ def test_numpy_mode_with_one_row_observations_matches_the_oracle(host_io):
     want = {"auto": _cabi.IO_MAPPED, "copy": _cabi.IO_COPY, "server": _cabi.IO_SERVER}[host_io]
     assert env._io_mode_used.value == want
     env.close()
+
+
+def test_step_async_wait_pipelined_equals_synchronous_steps():
+    """step_async / step_wait with TWO iterations in flight (the copy of iteration k's results runs under iteration
+    k+1): same results, in order, as synchronous hybrid steps and as the oracle; pinned and pageable action arrays."""
+    import gym_trading_env_b200 as gte
+    import oracle as orc
+    N, K = 40_000, 50
+    series = gte.frame_to_arrays(gte.make_gbm_ohlcv(20_000, seed=2))
+    pos = [-1, 0, 0.5, 1]
+    kw = dict(positions=pos, windows=64, max_episode_duration=15, **FEES)
+    env = gte.TradingVectorEnv(series, num_envs=N, seed=3, verbose=0, output="hybrid", **kw)
+    o = orc.OracleVecEnv(series.features, series.price, num_envs=N, seed=3, threads=8, **kw)
+    obs, _ = env.reset()
+    H.assert_bits(obs.cpu().numpy(), o.reset(), "reset obs")
+    rng = np.random.default_rng(5)
+    acts = rng.integers(0, len(pos), size=(K, N))
+    pins = [env.pinned_actions(), env.pinned_actions()]
+    with pytest.raises(RuntimeError):
+        env.step_wait()
+    pins[0][...] = acts[0]
+    env.step_async(pins[0])
+    for k in range(K):
+        if k + 1 < K:                                                    # iteration k+1 goes out before k is read
+            if k % 5 == 4:
+                env.step_async(acts[k + 1].astype(np.int16))             # pageable: staged per wire set
+            else:
+                pins[(k + 1) & 1][...] = acts[k + 1]
+                env.step_async(pins[(k + 1) & 1])
+        _, rew, term, trunc, _ = env.step_wait()
+        o.step(acts[k])
+        H.assert_close64(rew, o.reward, f"step {k} reward")
+        H.assert_bits(term.view(np.uint8), o.terminated, f"step {k} terminated")
+        H.assert_bits(trunc.view(np.uint8), o.truncated, f"step {k} truncated")
+    H.assert_bits(env._obs.cpu().numpy(), o.obs, "last obs")
+    H.assert_bits(env._asset.cpu().numpy(), o.asset, "last asset")
+    env.step_async(acts[0]); env.step_async(acts[1])
+    with pytest.raises(RuntimeError):
+        env.step_async(acts[2])                                          # two already in flight
+    env.step_wait(); env.step_wait()
+    r = env.step(acts[2].astype(np.int8))                                # the synchronous call still works afterwards
+    assert r[1].shape == (N,)
+    env.close()

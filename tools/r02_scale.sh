@@ -7,7 +7,7 @@ import json, sys
 n, tag = sys.argv[1], sys.argv[2]
 d=json.loads(open(f"gpurun_out/{tag}_bench_c5_n{n}.json").read().strip().splitlines()[-1])
 print("n_gpus", d["n_gpus"], "value=%.4e ms=%.5f spread=%.4f" % (d["value"], d["ms_per_step"], d["spread"]["rel"]))
-for k in ("e2e","e2e_gymnasium_dtypes"):
+for k in ("e2e","e2e_gymnasium_dtypes","e2e_pipelined"):
     e=d.get(k)
     if e: print("   ",k,"%.4e"%e["value"], e["host_io"], e["action_dtype"], "us/step=%.2f"%e["us_per_step"])
 print(d["clocks"])
