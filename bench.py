@@ -581,7 +581,13 @@ def e2e_legs(ctx, env, actions, wl):
     around the step() calls.  "hybrid" (headline): observations stay device-resident for the policy's forward pass;
     "numpy": the full observation windows also cross PCIe (2.5 KB per env-step: PCIe-bound)."""
     torch, dist, world, dev, args = ctx.torch, ctx.dist, ctx.world, ctx.dev, ctx.args
-    from gym_trading_env_b200._cabi import host_result_layout
+    from gym_trading_env_b200._cabi import host_result_layout, host_result_sparse_bytes
+
+    def d2h_bytes(mode):
+        """bytes of the result block that cross PCIe per step (the sparse prefix when the env's flag wire is sparse)"""
+        hb = env._host or {}
+        sparse = mode == "hybrid" and hb.get("sparse") is not None and env._io_mode_used.value == 1
+        return host_result_sparse_bytes(N) if sparse else host_result_layout(N)[3]
     N, n_sets = wl["envs"], actions.shape[0]
     wire = {}
     for dt in (torch.int8, torch.int64):                 # action sets staged in pinned host memory, both wire widths
@@ -607,7 +613,8 @@ def e2e_legs(ctx, env, actions, wl):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ab = acts_h.dtype.itemsize
         return {"value": world * N * n_it / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": N * ab,
-                "d2h_bytes_per_step": host_result_layout(N)[3] + (env._obs.numel() * 4 if mode == "numpy" else 0),
+                "d2h_bytes_per_step": d2h_bytes(mode) + (env._obs.numel() * 4 if mode == "numpy" else 0),
+                "flag_wire": "sparse (list of ended envs)" if d2h_bytes(mode) != host_result_layout(N)[3] else "dense bytes",
                 "steps": n_it, "us_per_step": 1e6 * float(tt.item()) / n_it,
                 "timing": "host wall clock around the step() calls, max over ranks", "mode": mode,
                 "host_io": {1: "copy", 2: "mapped", 3: "server"}.get(env._io_mode_used.value, "?"),
@@ -644,7 +651,8 @@ def e2e_legs(ctx, env, actions, wl):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         out["e2e_pipelined"] = {"value": world * N * n_it / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": N,
-                                "d2h_bytes_per_step": host_result_layout(N)[3], "steps": n_it,
+                                "d2h_bytes_per_step": host_result_sparse_bytes(N) if env.sparse_flags else host_result_layout(N)[3],
+                                "steps": n_it,
                                 "us_per_step": 1e6 * float(tt.item()) / n_it, "mode": "hybrid", "host_io": "copy",
                                 "action_dtype": "int8", "timing": "host wall clock around the calls, max over ranks",
                                 "note": "step_async(a[k+1]) before step_wait() of iteration k: two iterations in flight, every "

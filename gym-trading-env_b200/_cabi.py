@@ -18,7 +18,7 @@ INCLUDE_DIR = os.path.join(os.path.dirname(_PKG), "include")
 SOURCES = ["gte_step.cu", "gte_obs.cu", "gte_cabi.cu"]
 HEADERS = ["gte_device.cuh", "gte_step_env.cuh", "gte_tma.cuh", "gte_launch.h", os.path.join(INCLUDE_DIR, "gte_b200.h")]
 
-GTE_VERSION = 200                 # include/gte_b200.h GTE_VERSION this binding was written against
+GTE_VERSION = 201                 # include/gte_b200.h GTE_VERSION this binding was written against
 GTE_MAX_POSITIONS = 64
 GTE_MAX_DATASETS = 64
 GTE_N_METRICS = 8
@@ -74,7 +74,8 @@ class GteStepOut(C.Structure):
         ("info_step", C.c_void_p), ("pre_reset_portfolio", C.c_void_p),
         ("metric_partials", C.c_void_p), ("metrics_step", C.c_void_p),
         ("metrics_total", C.c_void_p), ("block_counter", C.c_void_p), ("error_out", C.c_void_p),
-        ("seq_out", C.c_void_p), ("seq_value", C.c_uint32), ("reserved1", C.c_uint32),
+        ("seq_out", C.c_void_p), ("seq_value", C.c_uint32), ("ended_cap", C.c_uint32),
+        ("ended_list", C.c_void_p), ("ended_counter", C.c_void_p), ("ended_n_out", C.c_void_p),
     ]
 
 
@@ -82,7 +83,7 @@ class GteHostIO(C.Structure):
     _fields_ = [
         ("actions", C.c_void_p), ("results", C.c_void_p), ("dev_actions", C.c_void_p), ("dev_results", C.c_void_p),
         ("step_done_event", C.c_void_p), ("obs_host", C.c_void_p), ("obs_bytes", C.c_int64),
-        ("mode", C.c_int32), ("reserved", C.c_int32),
+        ("mode", C.c_int32), ("sparse_flags", C.c_int32),
     ]
 
 
@@ -92,9 +93,22 @@ E_ACTION_RANGE, E_PAST_END, E_PLAN_RANGE, E_PLAN_EXHAUSTED, E_NEGATIVE_ACTION = 
 
 
 def host_result_layout(n: int):
-    """(term offset, trunc offset, error offset, total bytes) of gte_step_host's result block (GTE_HOST_RESULT_*)."""
-    err = (n * 10 + 7) // 8 * 8
-    return n * 8, n * 9, err, err + 8
+    """(term offset, trunc offset, error offset, total bytes) of gte_step_host's result block (GTE_HOST_RESULT_*):
+    reward f64[N] | header 32 B (error i32, sequence u32, n_ended u32, cap u32, counter u32, pad) | ended u32[cap] |
+    terminated u8[N] | truncated u8[N]."""
+    cap = host_result_ended_cap(n)
+    err = n * 8
+    term = err + 32 + 4 * cap
+    return term, term + n, err, (term + 2 * n + 7) // 8 * 8
+
+
+def host_result_ended_cap(n: int) -> int:
+    return (max(n // 32, 1024) + 3) // 4 * 4
+
+
+def host_result_sparse_bytes(n: int) -> int:
+    """Bytes of the sparse prefix (reward | header | ended list)."""
+    return n * 8 + 32 + 4 * host_result_ended_cap(n)
 
 
 class GteInfo(C.Structure):

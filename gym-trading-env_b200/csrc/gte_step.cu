@@ -517,7 +517,8 @@ struct HostIOStreams {
     bool serving = false;
     GteParams sp; GteData sd; GteState ss; GteStepOut so; float* sobs = nullptr; int sauto = 0;
     // gte_step_host_begin / _end: completion events of the result copies in flight, keyed by the host result block
-    struct Pending { const void* results = nullptr; cudaEvent_t ev = nullptr; cudaEvent_t ev_in = nullptr; cudaEvent_t ev_step = nullptr; } pending[4];
+    struct Pending { const void* results = nullptr; cudaEvent_t ev = nullptr; cudaEvent_t ev_in = nullptr; cudaEvent_t ev_step = nullptr;
+                     int64_t n = 0; bool sparse = false; } pending[4];
 };
 static HostIOStreams g_hio[16];
 
@@ -562,6 +563,31 @@ bool serve_supported(const GteParams& P) {
     return P.windows == 0 && grid <= (int64_t)num_sms() && grid <= kMaxPartialRows;
 }
 
+// out->reward / flags / error / (device block only) the sparse episode-end list -> a result block (include/gte_b200.h)
+static void point_results(GteStepOut& o, char* blk, int64_t N, bool device_block) {
+    o.reward = reinterpret_cast<double*>(blk);
+    o.terminated = reinterpret_cast<uint8_t*>(blk + GTE_HOST_RESULT_TERM_OFFSET(N));
+    o.truncated = reinterpret_cast<uint8_t*>(blk + GTE_HOST_RESULT_TRUNC_OFFSET(N));
+    o.error_out = reinterpret_cast<int32_t*>(blk + GTE_HOST_RESULT_ERROR_OFFSET(N));
+    o.ended_list = nullptr; o.ended_counter = nullptr; o.ended_n_out = nullptr; o.ended_cap = 0;
+    if (device_block) {          // the append counter needs device atomics: mapped host blocks carry dense flags only
+        o.ended_list = reinterpret_cast<uint32_t*>(blk + GTE_HOST_RESULT_ENDED_OFFSET(N));
+        o.ended_counter = reinterpret_cast<uint32_t*>(blk + GTE_HOST_RESULT_COUNTER_OFFSET(N));
+        o.ended_n_out = reinterpret_cast<uint32_t*>(blk + GTE_HOST_RESULT_NENDED_OFFSET(N));
+        o.ended_cap = (uint32_t)GTE_HOST_RESULT_ENDED_CAP(N);
+    }
+}
+
+// After the sparse prefix has landed: more episodes ended than the list holds -> fetch the dense flag bytes as well.
+static cudaError_t fetch_dense_flags_if_needed(const GteHostIO& io, int64_t N, cudaStream_t copy_stream) {
+    const uint32_t n_ended = *reinterpret_cast<volatile uint32_t*>(static_cast<char*>(io.results) + GTE_HOST_RESULT_NENDED_OFFSET(N));
+    if (n_ended <= (uint32_t)GTE_HOST_RESULT_ENDED_CAP(N)) return cudaSuccess;
+    const int64_t off = GTE_HOST_RESULT_TERM_OFFSET(N);
+    cudaError_t e = cudaMemcpyAsync(static_cast<char*>(io.results) + off, static_cast<char*>(io.dev_results) + off, (size_t)(2 * N),
+                                    cudaMemcpyDeviceToHost, copy_stream);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(copy_stream);
+}
+
 int host_io_mode(const GteParams& P, int mode) {
     if (mode == GTE_IO_SERVER) return serve_supported(P) ? GTE_IO_SERVER : GTE_IO_MAPPED;
     // measured on B200 (tools/host_path_probe.py, profiles/r02_tuning.md): with a gather behind the step kernel the
@@ -586,10 +612,9 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
     // the results of this iteration: one block, on the device (COPY) or straight in the mapped host memory (MAPPED)
     char* blk = static_cast<char*>(mode != GTE_IO_COPY ? io.results : io.dev_results);
     GteStepOut o = O;
-    o.reward = reinterpret_cast<double*>(blk);
-    o.terminated = reinterpret_cast<uint8_t*>(blk + GTE_HOST_RESULT_TERM_OFFSET(N));
-    o.truncated = reinterpret_cast<uint8_t*>(blk + GTE_HOST_RESULT_TRUNC_OFFSET(N));
-    o.error_out = reinterpret_cast<int32_t*>(blk + GTE_HOST_RESULT_ERROR_OFFSET(N));
+    point_results(o, blk, N, mode == GTE_IO_COPY);
+    const bool sparse = mode == GTE_IO_COPY && io.sparse_flags != 0;
+    const size_t d2h_bytes = sparse ? (size_t)GTE_HOST_RESULT_SPARSE_BYTES(N) : (size_t)GTE_HOST_RESULT_BYTES(N);
     volatile uint32_t* seq_word = reinterpret_cast<volatile uint32_t*>(static_cast<char*>(io.results) + GTE_HOST_RESULT_SEQ_OFFSET(N));
     uint32_t seq = 0;
     if (mode == GTE_IO_MAPPED || mode == GTE_IO_SERVER) {
@@ -669,13 +694,14 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
     if (mode == GTE_IO_COPY) {
         if ((e = cudaEventRecord(h->ev_step, stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(h->out, h->ev_step, 0)) != cudaSuccess) return e;
-        if ((e = cudaMemcpyAsync(io.results, io.dev_results, (size_t)GTE_HOST_RESULT_BYTES(N), cudaMemcpyDeviceToHost, h->out)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(io.results, io.dev_results, d2h_bytes, cudaMemcpyDeviceToHost, h->out)) != cudaSuccess) return e;
         if (P.windows > 0 && (e = launch_obs_range(P, D, S, obs, variant, 0, P.n_envs, stream)) != cudaSuccess) return e;
         if (obs_copy) {
             if ((e = cudaMemcpyAsync(io.obs_host, obs, (size_t)io.obs_bytes, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
             if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
         }
-        return cudaStreamSynchronize(h->out);               // reward / flags / error flag are on the host; the gather runs on
+        if ((e = cudaStreamSynchronize(h->out)) != cudaSuccess) return e;   // reward / flags / error flag are on the host; the gather runs on
+        return sparse ? fetch_dense_flags_if_needed(io, N, h->out) : cudaSuccess;
     }
     // MAPPED: the kernel itself wrote the host block and, last, the call's sequence number: poll that word instead
     // of going through the driver (the lowest-latency completion signal there is)
@@ -716,12 +742,10 @@ cudaError_t launch_step_host_begin(const GteParams& P, const GteData& D, const G
         if ((e = cudaEventCreateWithFlags(&slot->ev_step, cudaEventDisableTiming)) != cudaSuccess) return e;
     }
     slot->results = io.results;
-    char* blk = static_cast<char*>(io.dev_results);
+    slot->n = N;
+    slot->sparse = io.sparse_flags != 0;
     GteStepOut o = O;
-    o.reward = reinterpret_cast<double*>(blk);
-    o.terminated = reinterpret_cast<uint8_t*>(blk + GTE_HOST_RESULT_TERM_OFFSET(N));
-    o.truncated = reinterpret_cast<uint8_t*>(blk + GTE_HOST_RESULT_TRUNC_OFFSET(N));
-    o.error_out = reinterpret_cast<int32_t*>(blk + GTE_HOST_RESULT_ERROR_OFFSET(N));
+    point_results(o, static_cast<char*>(io.dev_results), N, true);
     o.seq_out = nullptr;
     // this set's staging buffer is free: its previous iteration's end() has returned (the caller's contract)
     if ((e = cudaMemcpyAsync(io.dev_actions, io.actions, (size_t)(N * ab), cudaMemcpyHostToDevice, h->in)) != cudaSuccess) return e;
@@ -733,7 +757,9 @@ cudaError_t launch_step_host_begin(const GteParams& P, const GteData& D, const G
         (e = cudaEventRecord(static_cast<cudaEvent_t>(io.step_done_event), stream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(slot->ev_step, stream)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(h->out, slot->ev_step, 0)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyAsync(io.results, io.dev_results, (size_t)GTE_HOST_RESULT_BYTES(N), cudaMemcpyDeviceToHost, h->out)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(io.results, io.dev_results,
+                             slot->sparse ? (size_t)GTE_HOST_RESULT_SPARSE_BYTES(N) : (size_t)GTE_HOST_RESULT_BYTES(N),
+                             cudaMemcpyDeviceToHost, h->out)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(slot->ev, h->out)) != cudaSuccess) return e;
     if (P.windows > 0 && (e = launch_obs_range(P, D, S, obs, variant, 0, P.n_envs, stream)) != cudaSuccess) return e;
     return cudaSuccess;
@@ -744,7 +770,11 @@ cudaError_t launch_step_host_end(const GteHostIO& io) {
     cudaError_t e;
     if ((e = hio_for_current_device(&h)) != cudaSuccess) return e;
     for (auto& p : h->pending)
-        if (p.results == io.results && p.ev != nullptr) return cudaEventSynchronize(p.ev);
+        if (p.results == io.results && p.ev != nullptr) {
+            if ((e = cudaEventSynchronize(p.ev)) != cudaSuccess) return e;
+            // (a later iteration's copy may be queued behind on the same stream: the rare dense fetch waits for it too)
+            return p.sparse ? fetch_dense_flags_if_needed(io, p.n, h->out) : cudaSuccess;
+        }
     return cudaErrorInvalidValue;                            // no begin() for this result block
 }
 

@@ -169,6 +169,10 @@ __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteD
     O.reward[i] = rew;
     O.terminated[i] = (uint8_t)done;
     O.truncated[i] = (uint8_t)trunc;
+    if ((done || trunc) && O.ended_list != nullptr) {                        // the sparse form of the two flag arrays
+        const unsigned slot = atomicAdd(O.ended_counter, 1u);
+        if (slot < O.ended_cap) O.ended_list[slot] = (unsigned)i | (done ? 0x80000000u : 0u) | (trunc ? 0x40000000u : 0u);
+    }
     if (O.valuation) O.valuation[i] = val;
     if (O.real_position) O.real_position[i] = rp;
     if (O.info_idx) O.info_idx[i] = idx;
@@ -337,6 +341,10 @@ static __device__ void reduce_metrics(const MetricAcc& acc, const GteStepOut& O,
         // every CTA of this launch has read the tick / ring clock by now.  The Philox event counter advances with
         // the LAST env range of an iteration; the ring clock with the FIRST one, so that the later ranges and
         // every gather of the iteration (all stream-ordered behind this launch) read the new value
+        if (O.ended_list != nullptr) {                   // every CTA's appends came before its ticket
+            *O.ended_n_out = __ldcg(O.ended_counter);
+            *O.ended_counter = 0u;
+        }
         if (flags & kChunkLast) *S.tick = *S.tick + (uint64_t)n_iter;
         if (flags & kChunkFirst) *S.ring_clock = *S.ring_clock + (uint64_t)n_iter;
         // every CTA OR-ed its error bits before it took its ticket: the flag is complete here (may be mapped host memory)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GTE_VERSION 200            /* 0.2.0 */
+#define GTE_VERSION 201            /* 0.2.1 */
 #define GTE_MAX_POSITIONS 64
 #define GTE_MAX_DATASETS 64        /* least-used rotation keeps a 64-bit "used this round" mask per env */
 #define GTE_N_METRICS 8
@@ -43,13 +43,26 @@ extern "C" {
 #define GTE_RING_POS_OFFSET(W, s, e) ((W) * 128 + (s) * 32 + (e))
 #define GTE_STEP_THREADS 256       /* envs per tile of the step kernel */
 #define GTE_MAX_PARTIAL_ROWS 4096  /* rows of GteStepOut.metric_partials (one per CTA; every grid is capped at this) */
-/* host result block of gte_step_host: reward f64[N] | terminated u8[N] | truncated u8[N] | pad to 8 | error_flag i32 |
- * sequence u32 (MAPPED mode: the number of the call whose results the block holds) */
-#define GTE_HOST_RESULT_TERM_OFFSET(N) ((int64_t)(N) * 8)
-#define GTE_HOST_RESULT_TRUNC_OFFSET(N) ((int64_t)(N) * 9)
-#define GTE_HOST_RESULT_ERROR_OFFSET(N) ((((int64_t)(N) * 10) + 7) / 8 * 8)
+/* Result block of gte_step_host — everything a host policy needs back from one iteration, in ONE piece of memory
+ * (device copy and pinned host copy have the same layout):
+ *   reward f64[N] | header (32 B) | ended u32[cap] | terminated u8[N] | truncated u8[N] | pad to 8
+ *   header: error_flag i32 | sequence u32 | n_ended u32 | cap u32 | append counter u32 (device side) | 12 B pad
+ *   ended[j] (j < min(n_ended, cap)): one entry per env whose episode ended in this iteration, in no particular order:
+ *            bit 31 terminated, bit 30 truncated, bits 0..29 the env index.  Episode ends are rare (1 env in
+ *            max_episode_duration per iteration), so `reward | header | ended` — the SPARSE prefix — carries the flags of
+ *            a large batch in 8.1 instead of 10 bytes per env; the dense byte arrays are only needed when more than `cap`
+ *            episodes ended at once.
+ * The device copy must be zero-initialised before its first use (the append counter lives in it). */
+#define GTE_HOST_RESULT_ENDED_CAP(N) ((((int64_t)(N) / 32 > 1024 ? (int64_t)(N) / 32 : 1024) + 3) / 4 * 4)
+#define GTE_HOST_RESULT_ERROR_OFFSET(N) ((int64_t)(N) * 8)
 #define GTE_HOST_RESULT_SEQ_OFFSET(N) (GTE_HOST_RESULT_ERROR_OFFSET(N) + 4)
-#define GTE_HOST_RESULT_BYTES(N) (GTE_HOST_RESULT_ERROR_OFFSET(N) + 8)
+#define GTE_HOST_RESULT_NENDED_OFFSET(N) (GTE_HOST_RESULT_ERROR_OFFSET(N) + 8)
+#define GTE_HOST_RESULT_COUNTER_OFFSET(N) (GTE_HOST_RESULT_ERROR_OFFSET(N) + 16)
+#define GTE_HOST_RESULT_ENDED_OFFSET(N) (GTE_HOST_RESULT_ERROR_OFFSET(N) + 32)
+#define GTE_HOST_RESULT_SPARSE_BYTES(N) (GTE_HOST_RESULT_ENDED_OFFSET(N) + 4 * GTE_HOST_RESULT_ENDED_CAP(N))
+#define GTE_HOST_RESULT_TERM_OFFSET(N) GTE_HOST_RESULT_SPARSE_BYTES(N)
+#define GTE_HOST_RESULT_TRUNC_OFFSET(N) (GTE_HOST_RESULT_TERM_OFFSET(N) + (int64_t)(N))
+#define GTE_HOST_RESULT_BYTES(N) ((GTE_HOST_RESULT_TRUNC_OFFSET(N) + (int64_t)(N) + 7) / 8 * 8)
 
 #define GTE_OK 0
 #define GTE_ERR_ARG (-1)
@@ -201,7 +214,13 @@ typedef struct GteStepOut {
                                         host result block): the two are published with one 8-byte store, error_out itself
                                         is then not written                                                            */
     uint32_t seq_value;
-    uint32_t reserved1;
+    uint32_t ended_cap;              /* entries ended_list can hold                                                     */
+    uint32_t* ended_list;            /* u32 [ended_cap] or NULL: every env whose episode ends in this launch appends
+                                        (terminated << 31) | (truncated << 30) | env index (any order)                  */
+    uint32_t* ended_counter;         /* u32 [1], device memory, zero before the first launch: the append cursor; the last
+                                        CTA of the launch moves its value to ended_n_out and resets it                  */
+    uint32_t* ended_n_out;           /* u32 [1]: how many episodes ended in this launch (may exceed ended_cap: the list
+                                        then holds only the first ended_cap of them and the dense flags must be read)   */
 } GteStepOut;
 
 /* Host side of one lockstep iteration for a HOST policy (gte_step_host): actions come from pinned host memory,
@@ -236,7 +255,10 @@ typedef struct GteHostIO {
                                         one more device-to-host copy behind the gather; the call returns when it landed */
     int64_t obs_bytes;               /* size of the observation batch in bytes (N * W * F * 4)                          */
     int32_t mode;                    /* enum GteHostIOMode                                                             */
-    int32_t reserved;
+    int32_t sparse_flags;            /* copy engines only: bring back just the sparse prefix of the result block
+                                        (GTE_HOST_RESULT_SPARSE_BYTES: reward | header | ended list) — the dense
+                                        terminated / truncated bytes follow, inside the same call, only when more than
+                                        `cap` episodes ended at once (header: n_ended > cap)                            */
 } GteHostIO;
 
 /* Lazily computed info columns (History's last row, environments.py:253-264 / utils/history.py). */

@@ -457,3 +457,39 @@ def test_step_async_wait_pipelined_equals_synchronous_steps():
     r = env.step(acts[2].astype(np.int8))                                # the synchronous call still works afterwards
     assert r[1].shape == (N,)
     env.close()
+
+
+def test_sparse_flag_wire_reconstructs_the_dense_flags_including_bursts():
+    """The sparse flag wire (copy engines): terminated / truncated rebuilt on the host from the list of ended envs are
+    identical to the dense bytes — in ordinary iterations, and in the iteration where EVERY env's episode ends at once
+    (more entries than the list holds: the dense bytes are fetched inside the same call), synchronously and through
+    step_async / step_wait."""
+    import gym_trading_env_b200 as gte
+    N = 50_000
+    series = gte.frame_to_arrays(gte.make_gbm_ohlcv(20_000, seed=2))
+    pos = [-1, 0, 0.5, 1]
+    kw = dict(positions=pos, windows=8, max_episode_duration=12, num_envs=N, seed=3, verbose=0, output="hybrid",
+              host_io="copy", **FEES)
+    sparse = gte.TradingVectorEnv(series, sparse_flags=True, **kw)
+    dense = gte.TradingVectorEnv(series, sparse_flags=False, **kw)
+    apipe = gte.TradingVectorEnv(series, sparse_flags=True, **kw)
+    assert sparse.sparse_flags and not dense.sparse_flags
+    sparse.reset(); dense.reset(); apipe.reset()
+    rng = np.random.default_rng(5)
+    acts = rng.integers(0, len(pos), size=(40, N)).astype(np.int8)
+    bursts = 0
+    apipe.step_async(acts[0])
+    for k in range(40):
+        if k + 1 < 40:
+            apipe.step_async(acts[k + 1])
+        ra = apipe.step_wait()
+        rs, rd = sparse.step(acts[k]), dense.step(acts[k])
+        for r in (rs, ra):
+            assert np.array_equal(r[1], rd[1]), k
+            assert np.array_equal(r[2], rd[2]) and np.array_equal(r[3], rd[3]), k
+            assert r[2].dtype == np.bool_ and r[3].dtype == np.bool_
+        n_end = int((rd[2] | rd[3]).sum())
+        assert int(sparse._host["sparse"].n_ended[0]) == n_end
+        bursts += n_end > sparse._host["sparse"].entries.size
+    assert bursts >= 2            # all envs start together: every 11th iteration all 50 000 episodes end at once
+    assert int((rd[2] | rd[3]).sum()) < N
