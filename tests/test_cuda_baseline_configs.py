@@ -493,3 +493,35 @@ def test_sparse_flag_wire_reconstructs_the_dense_flags_including_bursts():
         bursts += n_end > sparse._host["sparse"].entries.size
     assert bursts >= 2            # all envs start together: every 11th iteration all 50 000 episodes end at once
     assert int((rd[2] | rd[3]).sum()) < N
+
+
+@pytest.mark.parametrize("windows", [None, 8])
+def test_persistent_rollout_with_dataset_rotation_and_narrow_actions_equals_stepping(windows):
+    """gte_rollout as ONE persistent launch (state in registers for all K iterations) on a multi-dataset env: dataset
+    switches, Philox resets and ring slots derived inside the kernel give the same bits as K separate step() calls."""
+    import gym_trading_env_b200 as gte
+    frames = [gte.make_gbm_ohlcv(T, seed=50 + k) for k, T in enumerate([700, 900, 800])]
+    kw = dict(positions=[-1, 0, 1, 2], windows=windows, max_episode_duration=17, num_envs=3000, seed=13, verbose=0,
+              episodes_between_dataset_switch=2, **FEES)
+    a, b = gte.MultiDatasetTradingVectorEnv(datasets=frames, **kw), gte.MultiDatasetTradingVectorEnv(datasets=frames, **kw)
+    a.reset(); b.reset()
+    acts = _acts(3000, 70, 4, a.device, seed=8)
+    acts[::3, ::5] = -1
+    out = a.rollout(acts[:40], keep_obs=windows is None)
+    out2 = a.rollout(acts[40:])
+    for k in range(70):
+        obs, rew, term, trunc, _ = b.step(acts[k])
+        o = out if k < 40 else out2
+        kk = k if k < 40 else k - 40
+        assert torch.equal(o["reward"][kk], rew) and torch.equal(o["terminated"][kk], term) and torch.equal(o["truncated"][kk], trunc), k
+        assert torch.equal(o["valuation"][kk], b._valuation), k
+        if windows is None and k < 40:
+            assert torch.equal(o["obs"][kk].view(torch.int32), obs.view(torch.int32)), k
+    for nm in ("obs", "asset", "fiat", "interest_asset", "interest_fiat", "pos_idx", "step", "ep_start", "dataset_idx", "dyn_ring",
+               "ds_used", "ds_episodes"):
+        x, y = getattr(a, "_" + nm), getattr(b, "_" + nm)
+        assert torch.equal(x.view(torch.int32) if x.dtype == torch.float32 else x, y.view(torch.int32) if y.dtype == torch.float32 else y), nm
+    assert int(a._ring_clock) == int(b._ring_clock) == 70 and int(a._tick_dev) == int(b._tick_dev)
+    assert torch.equal(a._metrics_total[:3], b._metrics_total[:3])
+    torch.testing.assert_close(a._metrics_total, b._metrics_total, rtol=1e-12, atol=1e-12)
+    assert set(a._dataset_idx.cpu().tolist()) == {0, 1, 2}
