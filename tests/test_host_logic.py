@@ -135,3 +135,54 @@ def test_dataset_files_are_loaded_and_reconciled_by_column_name(tmp_path):
         gte.reconcile_series([sa, c], ["a.pkl", "c.pkl"])
     with pytest.raises(ValueError, match="unsupported dataset file type"):
         gte.load_frame(str(tmp_path / "x.xlsx"))
+
+
+def test_sparse_flag_mirror_patches_and_falls_back_to_dense_bytes():
+    """Host side of the sparse flag wire (pure numpy): entries (terminated << 31 | truncated << 30 | env) are patched into
+    persistent arrays, the previous iteration's entries are cleared, and a burst larger than the list takes the dense bytes."""
+    from gym_trading_env_b200 import _cabi
+    from gym_trading_env_b200.vector_env import _SparseFlags
+    n = 5000
+    toff, uoff, eoff, nbytes = _cabi.host_result_layout(n)
+    cap = _cabi.host_result_ended_cap(n)
+    assert cap == 1024 and _cabi.host_result_sparse_bytes(n) == 8 * n + 32 + 4 * cap == toff and nbytes % 8 == 0
+    assert _cabi.host_result_ended_cap(1 << 21) == 65536 and eoff == 8 * n and uoff == toff + n
+    block = np.zeros(nbytes, np.uint8)
+    m = _SparseFlags(n, block)
+    hdr = block[eoff:eoff + 32].view(np.uint32)
+    entries = block[eoff + 32:eoff + 32 + 4 * cap].view(np.uint32)
+
+    def publish(term_ids, trunc_ids, both_ids=()):
+        e = [i | 0x80000000 for i in term_ids] + [i | 0x40000000 for i in trunc_ids] + [i | 0xC0000000 for i in both_ids]
+        entries[:len(e)] = np.array(e, np.uint32)
+        hdr[2] = len(e)
+
+    publish([3, 4999], [10, 11], [77])
+    t, u = m.update()
+    assert np.flatnonzero(t).tolist() == [3, 77, 4999] and np.flatnonzero(u).tolist() == [10, 11, 77]
+    publish([], [5])
+    t2, u2 = m.update()
+    assert t2 is t and u2 is u and not t.any() and np.flatnonzero(u).tolist() == [5]      # same arrays, old entries cleared
+    # burst: more ends than the list holds -> the dense bytes (fetched by gte_step_host in the same call) are taken
+    dense_t, dense_u = block[toff:toff + n].view(np.bool_), block[uoff:uoff + n].view(np.bool_)
+    dense_u[:] = True
+    dense_t[::2] = True
+    hdr[2] = n
+    t, u = m.update()
+    assert u.all() and t[::2].all() and not t[1::2].any()
+    publish([1], [])
+    t, u = m.update()                                                                     # after a burst everything is cleared first
+    assert np.flatnonzero(t).tolist() == [1] and not u.any()
+
+
+def test_hostbind_helpers_parse_cpu_lists_and_device_order(monkeypatch):
+    from gym_trading_env_b200 import hostbind
+    assert hostbind._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11} and hostbind._parse_cpulist("") == set()
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "4,6")
+    assert hostbind._physical_index(1) == 6 and hostbind._physical_index(5) == 5
+    monkeypatch.delenv("CUDA_VISIBLE_DEVICES")
+    assert hostbind._physical_index(3) == 3
+    info = hostbind.bind_host_to_gpu(0, enable=False)
+    assert info == {"gpu": 0, "bound": False, "how": "disabled"}
+    info = hostbind.bind_host_to_gpu(0)                         # no GPU / no NUMA information here: a no-op that says so
+    assert info["gpu"] == 0 and "how" in info
