@@ -498,7 +498,9 @@ static cudaError_t plan_tma(const ObsShape& sh, int n_envs, bool fused, TmaPlan*
     const int64_t cap = (int64_t)num_sms() * per_sm;
     int unit = 32;
     int64_t best = -1;
+    static const int forced_unit = [] { const char* e = getenv("GTE_TMA_UNIT"); return e ? atoi(e) : 0; }();   // tuning runs
     for (int u = 32; u >= 8 && u >= cfg.group; u /= 2) {
+        if (forced_unit > 0 && tma_kernel(cfg, forced_unit, fused) != nullptr) { unit = forced_unit; break; }
         if (tma_kernel(cfg, u, fused) == nullptr) continue;
         const int64_t units = ((int64_t)n_envs + u - 1) / u;
         const int64_t per_cta = (units + cap - 1) / cap;
