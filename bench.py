@@ -118,10 +118,10 @@ class ClockSampler:
                 "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
-CPU_SAMPLE_ENVS = 2048
-CPU_SAMPLE_NOTE = ("the %d-env sample's state and observation batch are cache-resident on the host (5 MB of observations against "
+CPU_SAMPLE_ENVS = 4096
+CPU_SAMPLE_NOTE = ("the %d-env sample's state and observation batch are cache-resident on the host (10 MB of observations against "
                    "2 MB of L2 per core), which flatters the CPU; each env keeps its own private dynamic-feature columns like the "
-                   "reference (1.6 GB, pre-faulted)" % CPU_SAMPLE_ENVS)
+                   "reference (3.2 GB, pre-faulted)" % CPU_SAMPLE_ENVS)
 
 
 def make_cpu_port(wl, n_sample, threads, seed=0):
