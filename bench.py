@@ -251,6 +251,7 @@ def run_reference_arm(args, wl, rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["label"], "sample": sample}, "spread": spread,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "single_core_value": cpu_port_rate(wl, 256, 2.0, 1, repeats=3, burn_in=0)["value"],
                          "python_reference": python_reference_rate(wl, args.workload)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -290,7 +291,6 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=None)
     ap.add_argument("--obs-variant", default="auto")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--cuda-graph", action="store_true", help="replay one captured lockstep iteration (small N)")
     ap.add_argument("--pyref-worker", type=float, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--pyref-seed", type=int, default=0, help=argparse.SUPPRESS)
@@ -372,16 +372,7 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only): scalar C port of the reference on the host cores ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = len(os.sched_getaffinity(0))
-        n_sample = CPU_SAMPLE_ENVS
-        r_all = cpu_port_rate(wl, n_sample, args.cpu_seconds, cores)
-        r_one = cpu_port_rate(wl, 256, 3.0, 1, repeats=3, burn_in=0)
-        cpu = {"value": r_all["value"], "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n_sample} envs x {r_all['iters_per_repeat']} lockstep iterations, median of {r_all['repeats']} "
-                         f"repeats, same dataset/config, oracle/gte_oracle.c on {cores} pinned threads (pthreads inside C); "
-                         + CPU_SAMPLE_NOTE,
-               "spread": {k: r_all[k] for k in ("min", "max", "spread")}, "single_core_value": r_one["value"],
-               "python_reference": python_reference_rate(wl, args.workload)}
+        cpu = cpu_baseline_leg(args.workload)
 
     if rank == 0:
         out = {
@@ -406,6 +397,24 @@ def main():
         _emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_baseline_leg(workload_name):
+    """The `cpu_baseline` object of the GPU arm: the SAME measurement as `--impl reference`, run the same way — in a
+    fresh process (a process that holds a CUDA context, torch's thread pools and gigabytes of pinned memory times the
+    very same C code ~20 % slower), 12 bench steps of 1000 lockstep iterations after the burn-in."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload_name,
+           "--steps", "12", "--warmup", "3"]
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        d = json.loads(p.stdout.strip().splitlines()[-1])
+        cb = d["cpu_baseline"]
+        cb["spread"] = d.get("spread")
+        cb["how"] = "subprocess: " + " ".join(cmd[1:])
+        return cb
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                "sample": "failed: " + repr(e)[:200]}
 
 
 class Ctx:
