@@ -651,6 +651,20 @@ class TradingVectorEnv(_VectorEnvBase):
             self._step_done.record(torch.cuda.current_stream(self.device))
         return self._host
 
+    @staticmethod
+    def _is_pinned(hb, a):
+        """Whether a numpy array lives in pinned (page-locked) memory — asked of the driver once per buffer.  A positive
+        answer is cached TOGETHER WITH a reference to the array, so the buffer cannot be freed (and its address handed
+        to pageable memory) while the cache says "pinned"; a negative answer is never cached."""
+        ent = hb["pinned"].get(a.ctypes.data)
+        if ent is not None:
+            return True
+        if a.flags.writeable and torch.from_numpy(a).is_pinned():
+            if len(hb["pinned"]) < 64:
+                hb["pinned"][a.ctypes.data] = a
+            return True
+        return False
+
     def _stage_host_actions(self, actions):
         """numpy / list actions -> (array in PINNED memory, its dtype one of int8/16/32/64).  Arrays handed out by
         :meth:`pinned_actions` (or any other pinned array) are used in place; everything else goes through one
@@ -660,10 +674,7 @@ class TradingVectorEnv(_VectorEnvBase):
         if a.shape != (self.num_envs,):
             raise ValueError(f"actions must have shape ({self.num_envs},), got {a.shape}")
         if a.dtype in _WIRE_ACTION_DTYPES and a.flags.c_contiguous:
-            known = hb["pinned"].get(a.ctypes.data)
-            if known is None and a.flags.writeable and len(hb["pinned"]) < 64:
-                known = hb["pinned"][a.ctypes.data] = bool(torch.from_numpy(a).is_pinned())
-            if known:
+            if self._is_pinned(hb, a):
                 return a
         dt = a.dtype if a.dtype in _WIRE_ACTION_DTYPES else np.dtype(np.int64)
         buf = hb["actions"].get(dt)
@@ -851,10 +862,7 @@ class TradingVectorEnv(_VectorEnvBase):
             raise ValueError(f"actions must have shape ({self.num_envs},), got {a.shape}")
         pinned = False
         if a.dtype in _WIRE_ACTION_DTYPES and a.flags.c_contiguous:
-            known = self._host["pinned"].get(a.ctypes.data)
-            if known is None and a.flags.writeable and len(self._host["pinned"]) < 64:
-                known = self._host["pinned"][a.ctypes.data] = bool(torch.from_numpy(a).is_pinned())
-            pinned = bool(known)
+            pinned = self._is_pinned(self._host, a)
         if not pinned:                                   # this set's own staging buffer: free since its last step_wait()
             dt = a.dtype if a.dtype in _WIRE_ACTION_DTYPES else np.dtype(np.int64)
             buf = ws["stage"].get(dt)
@@ -1315,7 +1323,7 @@ class TradingVectorEnv(_VectorEnvBase):
         t = torch.empty(self.num_envs, dtype=torch.from_numpy(np.empty(0, dt)).dtype, pin_memory=True)
         a = t.numpy()
         hb = self._host_buffers()
-        hb["pinned"][a.ctypes.data] = True
+        hb["pinned"][a.ctypes.data] = a
         hb["actions"][("handed", a.ctypes.data)] = t          # keeps the allocation alive as long as the env
         return a
 
