@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <immintrin.h>
 
 #include "gte_step_env.cuh"
@@ -588,6 +589,18 @@ static cudaError_t fetch_dense_flags_if_needed(const GteHostIO& io, int64_t N, c
     return e != cudaSuccess ? e : cudaStreamSynchronize(copy_stream);
 }
 
+// The host polls mapped memory for a kernel's answer; whatever goes wrong on the device, it gives up after
+// GTE_HOST_SPIN_TIMEOUT_S (default 20 s) instead of spinning for ever.
+static double host_now_s() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+static bool spin_deadline_passed(double t_start) {
+    static const double limit = [] { const char* e = getenv("GTE_HOST_SPIN_TIMEOUT_S"); return e ? atof(e) : 20.0; }();
+    return host_now_s() - t_start > limit;
+}
+
 int host_io_mode(const GteParams& P, int mode) {
     if (mode == GTE_IO_SERVER) return serve_supported(P) ? GTE_IO_SERVER : GTE_IO_MAPPED;
     // measured on B200 (tools/host_path_probe.py, profiles/r02_tuning.md): with a gather behind the step kernel the
@@ -656,6 +669,7 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
             return cudaSuccess;
         };
         if ((!h->serving || h->ctl->alive == 0u) && (e = launch()) != cudaSuccess) return e;
+        const double t_start = host_now_s();
         h->ctl->actions = (unsigned long long)reinterpret_cast<uintptr_t>(io.actions);
         __atomic_thread_fence(__ATOMIC_RELEASE);             // the caller's action writes (and the pointer) before the request
         h->ctl->req = ((unsigned long long)seq << 8) | (unsigned long long)ab;
@@ -666,8 +680,9 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
                 if (*seq_word == seq) break;
                 if ((e = cudaStreamSynchronize(h->serve)) != cudaSuccess) return e;
                 if ((e = launch()) != cudaSuccess) return e;
-            } else if ((spins & 0x3fffu) == 0 && (e = cudaStreamQuery(h->serve)) != cudaErrorNotReady && e != cudaSuccess) {
-                return e;                                    // a faulted kernel never answers
+            } else if ((spins & 0x3fffu) == 0) {
+                if ((e = cudaStreamQuery(h->serve)) != cudaErrorNotReady && e != cudaSuccess) return e;   // a faulted kernel never answers
+                if (spin_deadline_passed(t_start)) return cudaErrorLaunchTimeout;
             }
         }
         __atomic_thread_fence(__ATOMIC_ACQUIRE);
@@ -710,11 +725,13 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
         if ((e = cudaMemcpyAsync(io.obs_host, obs, (size_t)io.obs_bytes, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
         return cudaStreamSynchronize(stream);               // everything of this iteration, observations included
     }
+    const double t_start = host_now_s();
     for (uint32_t spins = 1; *seq_word != seq; ++spins) {
         _mm_pause();
         if ((spins & 0x3fffu) == 0) {                        // a faulted kernel never writes the word: ask the driver now and then
             e = cudaStreamQuery(stream);
             if (e != cudaErrorNotReady) return (e == cudaSuccess && *seq_word != seq) ? cudaErrorUnknown : e;
+            if (spin_deadline_passed(t_start)) return cudaErrorLaunchTimeout;
         }
     }
     return cudaSuccess;
