@@ -385,7 +385,7 @@ def main():
                        "host_bind": host_bind},
             "repeats": m["repeats"], "spread": m["spread"],
             "clocks": m["clocks"], "e2e": e2e.get("e2e"), "e2e_gymnasium_dtypes": e2e.get("e2e_gymnasium_dtypes"),
-            "e2e_pipelined": e2e.get("e2e_pipelined"),
+            "e2e_pipelined": e2e.get("e2e_pipelined"), "e2e_f32_reward": e2e.get("e2e_f32_reward"),
             "e2e_other_host_io": e2e.get("e2e_other_host_io"), "e2e_server": e2e.get("e2e_server"),
             "e2e_full_obs_to_host": e2e.get("e2e_full_obs_to_host"),
             "gpu_launches": m["launches_per_step"] * args.steps * m["repeats"]["n"], "roofline": m["roofline"], "cpu_baseline": cpu,
@@ -600,7 +600,10 @@ def e2e_legs(ctx, env, actions, wl):
         """bytes of the result block that cross PCIe per step (the sparse prefix when the env's flag wire is sparse)"""
         hb = env._host or {}
         sparse = mode == "hybrid" and hb.get("sparse") is not None and env._io_mode_used.value == 1
-        return host_result_sparse_bytes(N) if sparse else host_result_layout(N)[3]
+        b = host_result_sparse_bytes(N) if sparse else host_result_layout(N)[3]
+        if mode == "hybrid" and env.reward_wire == "f32" and env._io_mode_used.value == 1:
+            b -= 4 * N                                       # float32 instead of fp64 rewards on the wire
+        return b
     N, n_sets = wl["envs"], actions.shape[0]
     wire = {}
     for dt in (torch.int8, torch.int64):                 # action sets staged in pinned host memory, both wire widths
@@ -627,7 +630,8 @@ def e2e_legs(ctx, env, actions, wl):
         ab = acts_h.dtype.itemsize
         return {"value": world * N * n_it / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": N * ab,
                 "d2h_bytes_per_step": d2h_bytes(mode) + (env._obs.numel() * 4 if mode == "numpy" else 0),
-                "flag_wire": "sparse (list of ended envs)" if d2h_bytes(mode) != host_result_layout(N)[3] else "dense bytes",
+                "flag_wire": "sparse (list of ended envs)" if (env._host or {}).get("sparse") is not None and env._io_mode_used.value == 1 else "dense bytes",
+                "reward_wire": env.reward_wire,
                 "steps": n_it, "us_per_step": 1e6 * float(tt.item()) / n_it,
                 "timing": "host wall clock around the step() calls, max over ranks", "mode": mode,
                 "host_io": {1: "copy", 2: "mapped", 3: "server"}.get(env._io_mode_used.value, "?"),
@@ -671,6 +675,12 @@ def e2e_legs(ctx, env, actions, wl):
                                 "note": "step_async(a[k+1]) before step_wait() of iteration k: two iterations in flight, every "
                                         "step's actions still come from pinned host memory and every step's reward / flags still "
                                         "land on the host inside the timed region"}
+    if N >= 2 ** 20:
+        env.reward_wire = "f32"
+        out["e2e_f32_reward"] = time_e2e("hybrid", "auto", torch.int8, n_it)
+        out["e2e_f32_reward"]["note"] = ("OPT-IN, LOSSY: reward_wire='f32' — the rewards cross PCIe as numpy's float32 cast of the fp64 "
+                                         "rewards (what stable-baselines3 keeps anyway); flags exact; the fp64 rewards stay on the device")
+        env.reward_wire = "f64"
     if world == 1:
         other = "mapped" if out["e2e"]["host_io"] == "copy" else "copy"
         out["e2e_other_host_io"] = time_e2e("hybrid", other, torch.int8, min(n_it, 50) if N >= 2 ** 20 else n_it)

@@ -18,7 +18,7 @@ INCLUDE_DIR = os.path.join(os.path.dirname(_PKG), "include")
 SOURCES = ["gte_step.cu", "gte_obs.cu", "gte_cabi.cu"]
 HEADERS = ["gte_device.cuh", "gte_step_env.cuh", "gte_tma.cuh", "gte_launch.h", os.path.join(INCLUDE_DIR, "gte_b200.h")]
 
-GTE_VERSION = 201                 # include/gte_b200.h GTE_VERSION this binding was written against
+GTE_VERSION = 202                 # include/gte_b200.h GTE_VERSION this binding was written against
 GTE_MAX_POSITIONS = 64
 GTE_MAX_DATASETS = 64
 GTE_N_METRICS = 8
@@ -76,6 +76,7 @@ class GteStepOut(C.Structure):
         ("metrics_total", C.c_void_p), ("block_counter", C.c_void_p), ("error_out", C.c_void_p),
         ("seq_out", C.c_void_p), ("seq_value", C.c_uint32), ("ended_cap", C.c_uint32),
         ("ended_list", C.c_void_p), ("ended_counter", C.c_void_p), ("ended_n_out", C.c_void_p),
+        ("reward_f32", C.c_void_p),
     ]
 
 
@@ -83,6 +84,7 @@ class GteHostIO(C.Structure):
     _fields_ = [
         ("actions", C.c_void_p), ("results", C.c_void_p), ("dev_actions", C.c_void_p), ("dev_results", C.c_void_p),
         ("step_done_event", C.c_void_p), ("obs_host", C.c_void_p), ("obs_bytes", C.c_int64),
+        ("reward_f32_host", C.c_void_p), ("dev_reward_f32", C.c_void_p),
         ("mode", C.c_int32), ("sparse_flags", C.c_int32),
     ]
 

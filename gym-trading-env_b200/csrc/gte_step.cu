@@ -627,7 +627,12 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
     GteStepOut o = O;
     point_results(o, blk, N, mode == GTE_IO_COPY);
     const bool sparse = mode == GTE_IO_COPY && io.sparse_flags != 0;
-    const size_t d2h_bytes = sparse ? (size_t)GTE_HOST_RESULT_SPARSE_BYTES(N) : (size_t)GTE_HOST_RESULT_BYTES(N);
+    // float32 reward wire (copy engines, opt-in, lossy): the f64 rewards stay in the device block, the block copy starts
+    // behind them, and the rounded rewards come back with a copy of their own
+    const bool f32 = mode == GTE_IO_COPY && io.reward_f32_host != nullptr && io.dev_reward_f32 != nullptr;
+    o.reward_f32 = f32 ? static_cast<float*>(io.dev_reward_f32) : nullptr;
+    const size_t d2h_skip = f32 ? (size_t)GTE_HOST_RESULT_ERROR_OFFSET(N) : 0;
+    const size_t d2h_bytes = (sparse ? (size_t)GTE_HOST_RESULT_SPARSE_BYTES(N) : (size_t)GTE_HOST_RESULT_BYTES(N)) - d2h_skip;
     volatile uint32_t* seq_word = reinterpret_cast<volatile uint32_t*>(static_cast<char*>(io.results) + GTE_HOST_RESULT_SEQ_OFFSET(N));
     uint32_t seq = 0;
     if (mode == GTE_IO_MAPPED || mode == GTE_IO_SERVER) {
@@ -709,7 +714,9 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
     if (mode == GTE_IO_COPY) {
         if ((e = cudaEventRecord(h->ev_step, stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(h->out, h->ev_step, 0)) != cudaSuccess) return e;
-        if ((e = cudaMemcpyAsync(io.results, io.dev_results, d2h_bytes, cudaMemcpyDeviceToHost, h->out)) != cudaSuccess) return e;
+        if (f32 && (e = cudaMemcpyAsync(io.reward_f32_host, io.dev_reward_f32, (size_t)N * 4, cudaMemcpyDeviceToHost, h->out)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(static_cast<char*>(io.results) + d2h_skip, static_cast<char*>(io.dev_results) + d2h_skip, d2h_bytes,
+                                 cudaMemcpyDeviceToHost, h->out)) != cudaSuccess) return e;
         if (P.windows > 0 && (e = launch_obs_range(P, D, S, obs, variant, 0, P.n_envs, stream)) != cudaSuccess) return e;
         if (obs_copy) {
             if ((e = cudaMemcpyAsync(io.obs_host, obs, (size_t)io.obs_bytes, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
@@ -764,6 +771,7 @@ cudaError_t launch_step_host_begin(const GteParams& P, const GteData& D, const G
     GteStepOut o = O;
     point_results(o, static_cast<char*>(io.dev_results), N, true);
     o.seq_out = nullptr;
+    o.reward_f32 = (io.reward_f32_host != nullptr && io.dev_reward_f32 != nullptr) ? static_cast<float*>(io.dev_reward_f32) : nullptr;
     // this set's staging buffer is free: its previous iteration's end() has returned (the caller's contract)
     if ((e = cudaMemcpyAsync(io.dev_actions, io.actions, (size_t)(N * ab), cudaMemcpyHostToDevice, h->in)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(slot->ev_in, h->in)) != cudaSuccess) return e;
@@ -774,8 +782,11 @@ cudaError_t launch_step_host_begin(const GteParams& P, const GteData& D, const G
         (e = cudaEventRecord(static_cast<cudaEvent_t>(io.step_done_event), stream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(slot->ev_step, stream)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(h->out, slot->ev_step, 0)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyAsync(io.results, io.dev_results,
-                             slot->sparse ? (size_t)GTE_HOST_RESULT_SPARSE_BYTES(N) : (size_t)GTE_HOST_RESULT_BYTES(N),
+    const bool f32 = io.reward_f32_host != nullptr && io.dev_reward_f32 != nullptr;
+    const size_t skip = f32 ? (size_t)GTE_HOST_RESULT_ERROR_OFFSET(N) : 0;
+    if (f32 && (e = cudaMemcpyAsync(io.reward_f32_host, io.dev_reward_f32, (size_t)N * 4, cudaMemcpyDeviceToHost, h->out)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(static_cast<char*>(io.results) + skip, static_cast<char*>(io.dev_results) + skip,
+                             (slot->sparse ? (size_t)GTE_HOST_RESULT_SPARSE_BYTES(N) : (size_t)GTE_HOST_RESULT_BYTES(N)) - skip,
                              cudaMemcpyDeviceToHost, h->out)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(slot->ev, h->out)) != cudaSuccess) return e;
     if (P.windows > 0 && (e = launch_obs_range(P, D, S, obs, variant, 0, P.n_envs, stream)) != cudaSuccess) return e;

@@ -167,6 +167,7 @@ __device__ __forceinline__ StepThreadOut step_env(const GteParams& P, const GteD
     }
 
     O.reward[i] = rew;
+    if (O.reward_f32 != nullptr) O.reward_f32[i] = (float)rew;              // round-to-nearest-even, as numpy casts
     O.terminated[i] = (uint8_t)done;
     O.truncated[i] = (uint8_t)trunc;
     if ((done || trunc) && O.ended_list != nullptr) {                        // the sparse form of the two flag arrays

@@ -282,6 +282,12 @@ class TradingVectorEnv(_VectorEnvBase):
     persistent bool arrays on the host — 8.1 instead of 10 bytes per env-step, lossless; a burst of more than N/32
     simultaneous episode ends falls back to the dense bytes inside the same call.
 
+    ``reward_wire`` ("f64" = default, lossless; "f32" = opt-in, LOSSY): in the "hybrid" mode with the copy engines the
+    rewards cross PCIe rounded to float32 (numpy's cast of the fp64 reward, round-to-nearest-even) — what a trainer that
+    keeps float32 rewards anyway (stable-baselines3's buffers) would do on the host; with the sparse flags 5.1 instead of
+    9.1 bytes per env-step come back.  ``step()`` then returns a float32 reward array; the fp64 rewards stay on the
+    device (``env.reward_device``).
+
     Host actions (``output`` "numpy" / "hybrid") may be int8 / int16 / int32 / int64: they cross PCIe in that width
     (``Discrete(P)`` fits int8 for every supported P, which is what :meth:`pinned_actions` hands out by default) and
     are widened by the step kernel's own load — lossless, 8x fewer host-to-device bytes than gymnasium's int64.
@@ -303,7 +309,8 @@ class TradingVectorEnv(_VectorEnvBase):
                  num_envs=1, device=None, seed=0, env_id_offset=0, done_valuation_ratio=0.7,
                  reset_plan=None, obs_variant="auto", output="torch", autoreset=True,
                  debug_outputs=False, cuda_graph=False, n_chunks=0, final_obs=False, strict_actions=False,
-                 host_io="auto", sparse_flags=None, _multi_dataset=False, _episodes_between_dataset_switch=1):
+                 host_io="auto", sparse_flags=None, reward_wire="f64", _multi_dataset=False,
+                 _episodes_between_dataset_switch=1):
         self._lib = _cabi.load()                      # fails loudly when the CUDA library is missing
         if not torch.cuda.is_available():
             raise RuntimeError("gym_trading_env_b200 needs a CUDA device (no CPU fallback)")
@@ -368,6 +375,11 @@ class TradingVectorEnv(_VectorEnvBase):
         self.strict_actions = bool(strict_actions)
         # host-output wire of the flags: None = sparse (the list of ended envs) for batches of 2^18 envs and more
         self.sparse_flags = (int(num_envs) >= (1 << 18)) if sparse_flags is None else bool(sparse_flags)
+        if reward_wire not in ("f64", "f32"):
+            raise ValueError("reward_wire must be 'f64' (lossless, default) or 'f32' (lossy, opt-in)")
+        if reward_wire == "f32" and output != "hybrid":
+            raise ValueError("reward_wire='f32' is a wire format of output='hybrid'")
+        self.reward_wire = reward_wire
         self.autoreset = bool(autoreset)
         self.debug_outputs = bool(debug_outputs)
         self.cuda_graph = bool(cuda_graph)
@@ -642,6 +654,12 @@ class TradingVectorEnv(_VectorEnvBase):
             # 10 bytes per env over PCIe, and are patched into persistent bool arrays on the host
             self._host["sparse"] = _SparseFlags(N, r) if (self.sparse_flags and self.output == "hybrid") else None
             io.sparse_flags = int(self._host["sparse"] is not None)
+            if self.reward_wire == "f32":                    # opt-in lossy wire: float32 rewards, 4 bytes per env
+                self._host["reward_f32_t"] = torch.zeros(N, dtype=torch.float32, pin_memory=True)
+                self._host["reward_f32"] = self._host["reward_f32_t"].numpy()
+                self._host["reward_f32_dev"] = torch.zeros(N, dtype=torch.float32, device=self.device)
+                io.reward_f32_host = self._host["reward_f32_t"].data_ptr()
+                io.dev_reward_f32 = self._host["reward_f32_dev"].data_ptr()
             if self.output == "numpy":                       # the observation batch is delivered to the host as well
                 io.obs_host, io.obs_bytes = self._host["obs_t"].data_ptr(), self._obs.numel() * 4
             self._io, self._io_mode_used = io, C.c_int(0)
@@ -807,13 +825,18 @@ class TradingVectorEnv(_VectorEnvBase):
             _cabi.check(rc, "gte_step_host")
         if red is not None:
             self._issue_metric_allreduce(None, after=self._step_done)
-        self._last_reward_host = hb["reward"]
+        reward = hb["reward"]
+        if self.reward_wire == "f32":
+            reward = hb["reward_f32"]
+            if self._io_mode_used.value != _cabi.IO_COPY:    # small batches answer through mapped memory in fp64: same dtype out
+                np.copyto(reward, hb["reward"], casting="same_kind")
+        self._last_reward_host = reward
         if hb["error"][0]:
             self._raise_on_flag(int(hb["error"][0]))
         term, trunc = hb["terminated"], hb["truncated"]
         if hb["sparse"] is not None and self._io_mode_used.value == _cabi.IO_COPY:
             term, trunc = hb["sparse"].update()
-        return (hb["obs"] if self.output == "numpy" else self._obs), hb["reward"], term, trunc, self.infos
+        return (hb["obs"] if self.output == "numpy" else self._obs), reward, term, trunc, self.infos
 
     # ------------------------------------------------------------------ step_async / step_wait (host policy, pipelined)
     def _async_sets(self):
@@ -833,9 +856,14 @@ class TradingVectorEnv(_VectorEnvBase):
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream(dev))
                 io.sparse_flags = int(self.sparse_flags)
-                sets.append({"io": io, "io_ref": C.byref(io), "host": host, "dev": devb, "dact": dact, "event": ev,
+                r32 = r32d = None
+                if self.reward_wire == "f32":
+                    r32 = torch.zeros(N, dtype=torch.float32, pin_memory=True)
+                    r32d = torch.zeros(N, dtype=torch.float32, device=dev)
+                    io.reward_f32_host, io.dev_reward_f32 = r32.data_ptr(), r32d.data_ptr()
+                sets.append({"io": io, "r32": (r32, r32d), "io_ref": C.byref(io), "host": host, "dev": devb, "dact": dact, "event": ev,
                              "sparse": _SparseFlags(N, r) if self.sparse_flags else None,
-                             "stage": {}, "reward": r[:8 * N].view(np.float64),
+                             "stage": {}, "reward": r[:8 * N].view(np.float64) if r32 is None else r32.numpy(),
                              "terminated": r[toff:toff + N].view(np.bool_), "truncated": r[uoff:uoff + N].view(np.bool_),
                              "error": r[eoff:eoff + 4].view(np.int32)})
             self._async = {"sets": sets, "pending": [], "n": 0}
@@ -1353,6 +1381,11 @@ class TradingVectorEnv(_VectorEnvBase):
             getattr(self, "_" + n).copy_(v)
         self._tick += 1                    # invalidates the lazily computed infos
         self._needs_first = False
+
+    @property
+    def reward_device(self):
+        """The fp64 rewards of the last `step()` as a device tensor (kept exact whatever `reward_wire` says)."""
+        return self._reward
 
     @property
     def idx(self):

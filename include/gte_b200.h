@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GTE_VERSION 201            /* 0.2.1 */
+#define GTE_VERSION 202            /* 0.2.2 */
 #define GTE_MAX_POSITIONS 64
 #define GTE_MAX_DATASETS 64        /* least-used rotation keeps a 64-bit "used this round" mask per env */
 #define GTE_N_METRICS 8
@@ -221,6 +221,8 @@ typedef struct GteStepOut {
                                         CTA of the launch moves its value to ended_n_out and resets it                  */
     uint32_t* ended_n_out;           /* u32 [1]: how many episodes ended in this launch (may exceed ended_cap: the list
                                         then holds only the first ended_cap of them and the dense flags must be read)   */
+    float* reward_f32;               /* f32 [N] or NULL: the reward ALSO rounded to float32 (numpy's cast) — the opt-in,
+                                        LOSSY wire of a trainer that keeps float32 rewards anyway (stable-baselines3)   */
 } GteStepOut;
 
 /* Host side of one lockstep iteration for a HOST policy (gte_step_host): actions come from pinned host memory,
@@ -254,6 +256,11 @@ typedef struct GteHostIO {
                                         observations straight into it (the device `obs` is then left untouched), else
                                         one more device-to-host copy behind the gather; the call returns when it landed */
     int64_t obs_bytes;               /* size of the observation batch in bytes (N * W * F * 4)                          */
+    void* reward_f32_host;           /* HOST, pinned, f32 [N], or NULL.  With dev_reward_f32 (copy engines only): the rewards
+                                        cross PCIe rounded to float32 (4 instead of 8 bytes per env: LOSSY, opt-in) and the
+                                        fp64 rewards stay on the device; the result block then only brings back its
+                                        header + ended list (sparse_flags) or header + list + dense flags              */
+    void* dev_reward_f32;            /* DEVICE, f32 [N], or NULL                                                          */
     int32_t mode;                    /* enum GteHostIOMode                                                             */
     int32_t sparse_flags;            /* copy engines only: bring back just the sparse prefix of the result block
                                         (GTE_HOST_RESULT_SPARSE_BYTES: reward | header | ended list) — the dense

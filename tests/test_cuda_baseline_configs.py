@@ -495,6 +495,47 @@ def test_sparse_flag_wire_reconstructs_the_dense_flags_including_bursts():
     assert int((rd[2] | rd[3]).sum()) < N
 
 
+def test_float32_reward_wire_is_the_numpy_cast_of_the_fp64_reward():
+    """reward_wire="f32" (opt-in, lossy): the rewards that cross PCIe are exactly numpy's float32 cast of the fp64 rewards
+    of the lossless wire, flags and error word are unchanged (sparse and dense flag wires, bursts included), the fp64
+    rewards stay on the device, and a small batch answered through mapped memory hands out the same dtype."""
+    import gym_trading_env_b200 as gte
+    N = 50_000
+    series = gte.frame_to_arrays(gte.make_gbm_ohlcv(20_000, seed=2))
+    pos = [-1, 0, 0.5, 1]
+    kw = dict(positions=pos, windows=8, max_episode_duration=12, num_envs=N, seed=3, verbose=0, output="hybrid",
+              host_io="copy", **FEES)
+    ref = gte.TradingVectorEnv(series, sparse_flags=False, **kw)
+    envs = [gte.TradingVectorEnv(series, sparse_flags=sp, reward_wire="f32", **kw) for sp in (True, False)]
+    apipe = gte.TradingVectorEnv(series, sparse_flags=True, reward_wire="f32", **kw)
+    for e in envs + [ref, apipe]:
+        e.reset()
+    rng = np.random.default_rng(5)
+    acts = rng.integers(0, len(pos), size=(26, N)).astype(np.int8)
+    apipe.step_async(acts[0])
+    for k in range(26):
+        if k + 1 < 26:
+            apipe.step_async(acts[k + 1])
+        rd = ref.step(acts[k])
+        want = rd[1].astype(np.float32)
+        for r in [e.step(acts[k]) for e in envs] + [apipe.step_wait()]:
+            assert r[1].dtype == np.float32
+            H.assert_bits(r[1], want, f"step {k} f32 reward")
+            assert np.array_equal(r[2], rd[2]) and np.array_equal(r[3], rd[3]), k
+        for e in envs:
+            H.assert_bits(e.reward_device.cpu().numpy(), rd[1], f"step {k} device fp64 reward")
+    assert np.count_nonzero(want) > N // 2
+    with pytest.raises(ValueError):
+        gte.TradingVectorEnv(series, reward_wire="f32", **dict(kw, output="torch"))
+    small = dict(kw, num_envs=512, host_io="auto")
+    a, b = gte.TradingVectorEnv(series, reward_wire="f32", **small), gte.TradingVectorEnv(series, **small)
+    a.reset(); b.reset()
+    for k in range(5):
+        ra, rb = a.step(acts[k, :512]), b.step(acts[k, :512])
+        assert ra[1].dtype == np.float32
+        H.assert_bits(ra[1], rb[1].astype(np.float32), "mapped batch, f32 out")
+
+
 @pytest.mark.parametrize("windows", [None, 8])
 def test_persistent_rollout_with_dataset_rotation_and_narrow_actions_equals_stepping(windows):
     """gte_rollout as ONE persistent launch (state in registers for all K iterations) on a multi-dataset env: dataset
