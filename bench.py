@@ -295,6 +295,7 @@ def main():
     ap.add_argument("--pyref-worker", type=float, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--pyref-seed", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-relay", action="store_true", help="multi-GPU e2e legs without enable_result_relay()")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the short C2 / C3 / C4 legs of the default run")
     ap.add_argument("--repeats", type=int, default=3, help="the timed region of K steps is repeated at least this many times; the median counts")
@@ -385,7 +386,8 @@ def main():
                        "host_bind": host_bind},
             "repeats": m["repeats"], "spread": m["spread"],
             "clocks": m["clocks"], "e2e": e2e.get("e2e"), "e2e_gymnasium_dtypes": e2e.get("e2e_gymnasium_dtypes"),
-            "e2e_pipelined": e2e.get("e2e_pipelined"), "e2e_f32_reward": e2e.get("e2e_f32_reward"),
+            "e2e_pipelined": e2e.get("e2e_pipelined"), "e2e_no_relay": e2e.get("e2e_no_relay"),
+            "e2e_f32_reward": e2e.get("e2e_f32_reward"),
             "e2e_other_host_io": e2e.get("e2e_other_host_io"), "e2e_server": e2e.get("e2e_server"),
             "e2e_full_obs_to_host": e2e.get("e2e_full_obs_to_host"),
             "gpu_launches": m["launches_per_step"] * args.steps * m["repeats"]["n"], "roofline": m["roofline"], "cpu_baseline": cpu,
@@ -596,12 +598,20 @@ def e2e_legs(ctx, env, actions, wl):
     torch, dist, world, dev, args = ctx.torch, ctx.dist, ctx.world, ctx.dev, ctx.args
     from gym_trading_env_b200._cabi import host_result_layout, host_result_sparse_bytes
 
+    def io_mode_used():
+        """1 = copy engines, 2 = mapped, 3 = server; a relayed env always steps through the copy engines (begin / end)"""
+        return 1 if env._relay is not None else env._io_mode_used.value
+
+    def sparse_wire():
+        if env._relay is not None:
+            return bool(env.sparse_flags)
+        return (env._host or {}).get("sparse") is not None and env._io_mode_used.value == 1
+
     def d2h_bytes(mode):
         """bytes of the result block that cross PCIe per step (the sparse prefix when the env's flag wire is sparse)"""
-        hb = env._host or {}
-        sparse = mode == "hybrid" and hb.get("sparse") is not None and env._io_mode_used.value == 1
+        sparse = mode == "hybrid" and sparse_wire()
         b = host_result_sparse_bytes(N) if sparse else host_result_layout(N)[3]
-        if mode == "hybrid" and env.reward_wire == "f32" and env._io_mode_used.value == 1:
+        if mode == "hybrid" and env.reward_wire == "f32" and io_mode_used() == 1:
             b -= 4 * N                                       # float32 instead of fp64 rewards on the wire
         return b
     N, n_sets = wl["envs"], actions.shape[0]
@@ -630,21 +640,33 @@ def e2e_legs(ctx, env, actions, wl):
         ab = acts_h.dtype.itemsize
         return {"value": world * N * n_it / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": N * ab,
                 "d2h_bytes_per_step": d2h_bytes(mode) + (env._obs.numel() * 4 if mode == "numpy" else 0),
-                "flag_wire": "sparse (list of ended envs)" if (env._host or {}).get("sparse") is not None and env._io_mode_used.value == 1 else "dense bytes",
+                "flag_wire": "sparse (list of ended envs)" if sparse_wire() else "dense bytes",
                 "reward_wire": env.reward_wire,
                 "steps": n_it, "us_per_step": 1e6 * float(tt.item()) / n_it,
                 "timing": "host wall clock around the step() calls, max over ranks", "mode": mode,
-                "host_io": {1: "copy", 2: "mapped", 3: "server"}.get(env._io_mode_used.value, "?"),
+                "host_io": {1: "copy", 2: "mapped", 3: "server"}.get(io_mode_used(), "?"),
                 "action_dtype": str(acts_h.dtype)}
 
     out = {}
     n_it = min(max(args.steps, 60), 200) if N >= 2 ** 20 else 2000
+    relay = None
+    if world > 1 and N >= 2 ** 20 and not args.no_relay:
+        # multi-GPU: first the plain wire for comparison (every rank's result block over its own PCIe link), then the
+        # result relay — part of the slow links' reward bytes reach the host through a peer GPU (lossless, collective)
+        out["e2e_no_relay"] = time_e2e("hybrid", "auto", torch.int8, n_it)
+        out["e2e_no_relay"]["note"] = "the headline wire WITHOUT enable_result_relay(): every rank's results over its own PCIe link"
+        env.output, env._host = "hybrid", None
+        relay = env.enable_result_relay()
     # headline: the documented default wire format of a host policy — int8 actions (Discrete(P) fits, widened by the
     # step kernel: lossless), fp64 rewards + terminated + truncated + error flag back in ONE block
     out["e2e"] = time_e2e("hybrid", "auto", torch.int8, n_it)
     out["e2e"]["note"] = ("VectorEnv(output='hybrid').step(pinned int8 numpy actions) -> numpy f64 reward / bool terminated / bool "
                           "truncated every step through ONE gte_step_host call (one copy per direction, or mapped host memory at "
                           "small N); the observation tensor stays in HBM for the policy's forward pass")
+    if relay is not None:
+        out["e2e"]["relay"] = relay
+        out["e2e"]["note"] += ("; env.enable_result_relay() called once: reward bytes balanced over the GPUs' PCIe links through peer "
+                               "GPUs (NVLink + the peer's copy engine), see `relay`")
     out["e2e_gymnasium_dtypes"] = time_e2e("hybrid", "auto", torch.int64, n_it)
     out["e2e_gymnasium_dtypes"]["note"] = "same call with gymnasium's own dtypes on the wire (int64 actions in, f64 reward + bool flags out)"
     if N >= 2 ** 20:
@@ -675,6 +697,8 @@ def e2e_legs(ctx, env, actions, wl):
                                 "note": "step_async(a[k+1]) before step_wait() of iteration k: two iterations in flight, every "
                                         "step's actions still come from pinned host memory and every step's reward / flags still "
                                         "land on the host inside the timed region"}
+    if relay is not None:
+        env.close_extras()                                   # collective: leaves the relay, frees the wire sets
     if N >= 2 ** 20:
         env.reward_wire = "f32"
         out["e2e_f32_reward"] = time_e2e("hybrid", "auto", torch.int8, n_it)

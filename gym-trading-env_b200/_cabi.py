@@ -15,10 +15,10 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_CSRC, "libgte_b200.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_PKG), "include")
-SOURCES = ["gte_step.cu", "gte_obs.cu", "gte_cabi.cu"]
+SOURCES = ["gte_step.cu", "gte_obs.cu", "gte_relay.cu", "gte_cabi.cu"]
 HEADERS = ["gte_device.cuh", "gte_step_env.cuh", "gte_tma.cuh", "gte_launch.h", os.path.join(INCLUDE_DIR, "gte_b200.h")]
 
-GTE_VERSION = 202                 # include/gte_b200.h GTE_VERSION this binding was written against
+GTE_VERSION = 203                 # include/gte_b200.h GTE_VERSION this binding was written against
 GTE_MAX_POSITIONS = 64
 GTE_MAX_DATASETS = 64
 GTE_N_METRICS = 8
@@ -84,7 +84,7 @@ class GteHostIO(C.Structure):
     _fields_ = [
         ("actions", C.c_void_p), ("results", C.c_void_p), ("dev_actions", C.c_void_p), ("dev_results", C.c_void_p),
         ("step_done_event", C.c_void_p), ("obs_host", C.c_void_p), ("obs_bytes", C.c_int64),
-        ("reward_f32_host", C.c_void_p), ("dev_reward_f32", C.c_void_p),
+        ("reward_f32_host", C.c_void_p), ("dev_reward_f32", C.c_void_p), ("reward_host_count", C.c_int64),
         ("mode", C.c_int32), ("sparse_flags", C.c_int32),
     ]
 
@@ -122,7 +122,8 @@ class GteInfo(C.Structure):
 
 
 EXPORTS = ["gte_version", "gte_last_error", "gte_build_id", "gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs",
-           "gte_step_host", "gte_step_host_begin", "gte_step_host_end", "gte_serve_stop", "gte_rollout", "gte_info", "gte_obs_variant_for", "gte_default_chunks", "gte_struct_size",
+           "gte_step_host", "gte_step_host_begin", "gte_step_host_end", "gte_serve_stop", "gte_relay_supported", "gte_relay_alloc", "gte_relay_open",
+           "gte_relay_release", "gte_relay_push", "gte_relay_serve", "gte_host_register", "gte_host_unregister", "gte_rollout", "gte_info", "gte_obs_variant_for", "gte_default_chunks", "gte_struct_size",
            "gte_step_obs_launches"]
 
 
@@ -213,9 +214,21 @@ def load():
     lib.gte_step_host_end.restype = C.c_int
     lib.gte_serve_stop.argtypes = []
     lib.gte_serve_stop.restype = C.c_int
+    lib.gte_relay_supported.argtypes = []
+    lib.gte_relay_alloc.argtypes = [C.c_int64, P(C.c_void_p), C.c_void_p]
+    lib.gte_relay_open.argtypes = [C.c_void_p, P(C.c_void_p)]
+    lib.gte_relay_release.argtypes = [C.c_void_p, C.c_int]
+    lib.gte_relay_push.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.gte_relay_serve.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.gte_host_register.argtypes = [C.c_void_p, C.c_int64]
+    lib.gte_host_unregister.argtypes = [C.c_void_p]
+    for name in ("gte_relay_supported", "gte_relay_alloc", "gte_relay_open", "gte_relay_release", "gte_relay_push",
+                 "gte_relay_serve", "gte_host_register", "gte_host_unregister"):
+        getattr(lib, name).restype = C.c_int
     lib.gte_default_chunks.argtypes = [C.c_int]
     lib.gte_default_chunks.restype = C.c_int
-    for name in ("gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs", "gte_step_host", "gte_step_host_begin", "gte_step_host_end", "gte_serve_stop", "gte_rollout", "gte_info",
+    for name in ("gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs", "gte_step_host", "gte_step_host_begin", "gte_step_host_end", "gte_serve_stop", "gte_relay_supported", "gte_relay_alloc", "gte_relay_open",
+           "gte_relay_release", "gte_relay_push", "gte_relay_serve", "gte_host_register", "gte_host_unregister", "gte_rollout", "gte_info",
                  "gte_obs_variant_for"):
         getattr(lib, name).restype = C.c_int
     lib.gte_struct_size.argtypes = [C.c_int]

@@ -163,6 +163,45 @@ int gte_step_host_end(const GteHostIO* io) {
 
 int gte_serve_stop(void) { return check_cuda("gte_serve_stop", gte::serve_quiesce()); }
 
+int gte_relay_supported(void) { return gte::relay_supported() ? 1 : 0; }
+
+int gte_relay_alloc(int64_t bytes, void** dev_base, void* ipc_handle) {
+    GTE_REQUIRE("gte_relay_alloc", bytes > 0 && dev_base != nullptr && ipc_handle != nullptr);
+    return check_cuda("gte_relay_alloc", gte::relay_alloc(bytes, dev_base, ipc_handle));
+}
+
+int gte_relay_open(const void* ipc_handle, void** dev_base) {
+    GTE_REQUIRE("gte_relay_open", ipc_handle != nullptr && dev_base != nullptr);
+    return check_cuda("gte_relay_open", gte::relay_open(ipc_handle, dev_base));
+}
+
+int gte_relay_release(void* dev_base, int opened) {
+    GTE_REQUIRE("gte_relay_release", dev_base != nullptr);
+    return check_cuda("gte_relay_release", gte::relay_release(dev_base, opened != 0));
+}
+
+int gte_relay_push(void* peer_base, const void* src_dev, int64_t bytes, uint32_t seq, void* after_event, void* done_event) {
+    GTE_REQUIRE("gte_relay_push", peer_base != nullptr && src_dev != nullptr && bytes > 0);
+    return check_cuda("gte_relay_push", gte::relay_push(peer_base, src_dev, bytes, seq, static_cast<cudaEvent_t>(after_event),
+                                                        static_cast<cudaEvent_t>(done_event)));
+}
+
+int gte_relay_serve(int lane, void* own_base, int64_t bytes, uint32_t seq, void* host_dst, void* host_seq) {
+    GTE_REQUIRE("gte_relay_serve", lane >= 0 && lane < 8 && own_base != nullptr && bytes > 0 && host_dst != nullptr && host_seq != nullptr);
+    GTE_REQUIRE("gte_relay_serve", gte::relay_supported());
+    return check_cuda("gte_relay_serve", gte::relay_serve(lane, own_base, bytes, seq, host_dst, host_seq));
+}
+
+int gte_host_register(void* ptr, int64_t bytes) {
+    GTE_REQUIRE("gte_host_register", ptr != nullptr && bytes > 0);
+    return check_cuda("gte_host_register", cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+}
+
+int gte_host_unregister(void* ptr) {
+    GTE_REQUIRE("gte_host_unregister", ptr != nullptr);
+    return check_cuda("gte_host_unregister", cudaHostUnregister(ptr));
+}
+
 int gte_rollout(const GteParams* params, const GteData* data, const GteState* state, const void* actions,
                 int n_steps, const GteStepOut* out, float* obs, int keep_obs, int autoreset, int variant, void* stream) {
     if (int rc = check_common("gte_rollout", params, data, state)) return rc;

@@ -53,6 +53,13 @@ bool step_obs_is_fused(const GteParams& P, const GteData& D, int variant);
 cudaError_t launch_step_host_begin(const GteParams& P, const GteData& D, const GteState& S, const GteHostIO& io,
                                    const GteStepOut& O, float* obs, int autoreset, int variant, cudaStream_t stream);
 cudaError_t launch_step_host_end(const GteHostIO& io);
+// result relay (gte_relay.cu)
+bool relay_supported();
+cudaError_t relay_alloc(int64_t bytes, void** dev_base, void* ipc_handle);
+cudaError_t relay_open(const void* ipc_handle, void** dev_base);
+cudaError_t relay_release(void* dev_base, bool opened);
+cudaError_t relay_push(void* peer_base, const void* src_dev, int64_t bytes, uint32_t seq, cudaEvent_t after, cudaEvent_t done);
+cudaError_t relay_serve(int lane, void* own_base, int64_t bytes, uint32_t seq, void* host_dst, void* host_seq);
 int default_chunks(int n_envs);
 int host_io_mode(const GteParams& P, int mode);
 cudaError_t serve_quiesce();

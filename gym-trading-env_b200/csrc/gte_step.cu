@@ -579,6 +579,27 @@ static void point_results(GteStepOut& o, char* blk, int64_t N, bool device_block
     }
 }
 
+// The device-to-host copies of one result block (copy engines).  Default: ONE copy of the block (its sparse prefix when
+// the flags travel as a list).  float32 reward wire (opt-in, lossy): the fp64 rewards stay in the device block, the block
+// copy starts behind them and the rounded rewards come back with a copy of their own.  reward_host_count (result relay,
+// gte_relay_*): only that many leading rewards take this GPU's own link — the caller routes the rest through a peer.
+static bool f32_wire(const GteHostIO& io) { return io.reward_f32_host != nullptr && io.dev_reward_f32 != nullptr; }
+static cudaError_t copy_results_to_host(const GteHostIO& io, int64_t N, bool sparse, cudaStream_t s) {
+    const size_t end = sparse ? (size_t)GTE_HOST_RESULT_SPARSE_BYTES(N) : (size_t)GTE_HOST_RESULT_BYTES(N);
+    const size_t hdr = (size_t)GTE_HOST_RESULT_ERROR_OFFSET(N);
+    const int64_t own = (io.reward_host_count > 0 && io.reward_host_count < N) ? io.reward_host_count : N;
+    char* dst = static_cast<char*>(io.results);
+    const char* src = static_cast<const char*>(io.dev_results);
+    cudaError_t e;
+    if (f32_wire(io)) {
+        if ((e = cudaMemcpyAsync(io.reward_f32_host, io.dev_reward_f32, (size_t)own * 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+        return cudaMemcpyAsync(dst + hdr, src + hdr, end - hdr, cudaMemcpyDeviceToHost, s);
+    }
+    if (own == N) return cudaMemcpyAsync(dst, src, end, cudaMemcpyDeviceToHost, s);
+    if ((e = cudaMemcpyAsync(dst, src, (size_t)own * 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    return cudaMemcpyAsync(dst + hdr, src + hdr, end - hdr, cudaMemcpyDeviceToHost, s);
+}
+
 // After the sparse prefix has landed: more episodes ended than the list holds -> fetch the dense flag bytes as well.
 static cudaError_t fetch_dense_flags_if_needed(const GteHostIO& io, int64_t N, cudaStream_t copy_stream) {
     const uint32_t n_ended = *reinterpret_cast<volatile uint32_t*>(static_cast<char*>(io.results) + GTE_HOST_RESULT_NENDED_OFFSET(N));
@@ -627,12 +648,7 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
     GteStepOut o = O;
     point_results(o, blk, N, mode == GTE_IO_COPY);
     const bool sparse = mode == GTE_IO_COPY && io.sparse_flags != 0;
-    // float32 reward wire (copy engines, opt-in, lossy): the f64 rewards stay in the device block, the block copy starts
-    // behind them, and the rounded rewards come back with a copy of their own
-    const bool f32 = mode == GTE_IO_COPY && io.reward_f32_host != nullptr && io.dev_reward_f32 != nullptr;
-    o.reward_f32 = f32 ? static_cast<float*>(io.dev_reward_f32) : nullptr;
-    const size_t d2h_skip = f32 ? (size_t)GTE_HOST_RESULT_ERROR_OFFSET(N) : 0;
-    const size_t d2h_bytes = (sparse ? (size_t)GTE_HOST_RESULT_SPARSE_BYTES(N) : (size_t)GTE_HOST_RESULT_BYTES(N)) - d2h_skip;
+    o.reward_f32 = (mode == GTE_IO_COPY && f32_wire(io)) ? static_cast<float*>(io.dev_reward_f32) : nullptr;
     volatile uint32_t* seq_word = reinterpret_cast<volatile uint32_t*>(static_cast<char*>(io.results) + GTE_HOST_RESULT_SEQ_OFFSET(N));
     uint32_t seq = 0;
     if (mode == GTE_IO_MAPPED || mode == GTE_IO_SERVER) {
@@ -714,9 +730,7 @@ cudaError_t launch_step_host(const GteParams& P, const GteData& D, const GteStat
     if (mode == GTE_IO_COPY) {
         if ((e = cudaEventRecord(h->ev_step, stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(h->out, h->ev_step, 0)) != cudaSuccess) return e;
-        if (f32 && (e = cudaMemcpyAsync(io.reward_f32_host, io.dev_reward_f32, (size_t)N * 4, cudaMemcpyDeviceToHost, h->out)) != cudaSuccess) return e;
-        if ((e = cudaMemcpyAsync(static_cast<char*>(io.results) + d2h_skip, static_cast<char*>(io.dev_results) + d2h_skip, d2h_bytes,
-                                 cudaMemcpyDeviceToHost, h->out)) != cudaSuccess) return e;
+        if ((e = copy_results_to_host(io, N, sparse, h->out)) != cudaSuccess) return e;
         if (P.windows > 0 && (e = launch_obs_range(P, D, S, obs, variant, 0, P.n_envs, stream)) != cudaSuccess) return e;
         if (obs_copy) {
             if ((e = cudaMemcpyAsync(io.obs_host, obs, (size_t)io.obs_bytes, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
@@ -771,7 +785,7 @@ cudaError_t launch_step_host_begin(const GteParams& P, const GteData& D, const G
     GteStepOut o = O;
     point_results(o, static_cast<char*>(io.dev_results), N, true);
     o.seq_out = nullptr;
-    o.reward_f32 = (io.reward_f32_host != nullptr && io.dev_reward_f32 != nullptr) ? static_cast<float*>(io.dev_reward_f32) : nullptr;
+    o.reward_f32 = f32_wire(io) ? static_cast<float*>(io.dev_reward_f32) : nullptr;
     // this set's staging buffer is free: its previous iteration's end() has returned (the caller's contract)
     if ((e = cudaMemcpyAsync(io.dev_actions, io.actions, (size_t)(N * ab), cudaMemcpyHostToDevice, h->in)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(slot->ev_in, h->in)) != cudaSuccess) return e;
@@ -782,12 +796,7 @@ cudaError_t launch_step_host_begin(const GteParams& P, const GteData& D, const G
         (e = cudaEventRecord(static_cast<cudaEvent_t>(io.step_done_event), stream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(slot->ev_step, stream)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(h->out, slot->ev_step, 0)) != cudaSuccess) return e;
-    const bool f32 = io.reward_f32_host != nullptr && io.dev_reward_f32 != nullptr;
-    const size_t skip = f32 ? (size_t)GTE_HOST_RESULT_ERROR_OFFSET(N) : 0;
-    if (f32 && (e = cudaMemcpyAsync(io.reward_f32_host, io.dev_reward_f32, (size_t)N * 4, cudaMemcpyDeviceToHost, h->out)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyAsync(static_cast<char*>(io.results) + skip, static_cast<char*>(io.dev_results) + skip,
-                             (slot->sparse ? (size_t)GTE_HOST_RESULT_SPARSE_BYTES(N) : (size_t)GTE_HOST_RESULT_BYTES(N)) - skip,
-                             cudaMemcpyDeviceToHost, h->out)) != cudaSuccess) return e;
+    if ((e = copy_results_to_host(io, N, slot->sparse, h->out)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(slot->ev, h->out)) != cudaSuccess) return e;
     if (P.windows > 0 && (e = launch_obs_range(P, D, S, obs, variant, 0, P.n_envs, stream)) != cudaSuccess) return e;
     return cudaSuccess;

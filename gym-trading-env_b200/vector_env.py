@@ -392,6 +392,7 @@ class TradingVectorEnv(_VectorEnvBase):
         self._last_actions = None            # the actions of the last step (infos["position_index"]); None after a reset
         self._last_reward_host = None        # host-output modes: the reward array the last step returned
         self._async = None                   # step_async / step_wait: two wire sets + the queue of iterations in flight
+        self._relay = None                   # enable_result_relay(): multi-GPU routing of result bytes through peer GPUs
         self._track_ids = None
         self._limit_price = None
         self._red_stream = None              # enable_metric_allreduce(): side stream of the per-iteration all-reduce
@@ -748,6 +749,11 @@ class TradingVectorEnv(_VectorEnvBase):
         host_in = not (isinstance(actions, torch.Tensor) and actions.is_cuda)
         if (host_in and self.output != "torch" and self._track_ids is None and not self.keep_final_obs
                 and not self.cuda_graph and self._kernel_events is None and self.autoreset):
+            if self._relay is not None:
+                if self._async is not None and self._async["pending"]:
+                    raise RuntimeError("step() while step_async() iterations are in flight: call step_wait() first")
+                self.step_async(actions)
+                return self.step_wait()
             return self._step_host(actions)
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
@@ -846,8 +852,10 @@ class TradingVectorEnv(_VectorEnvBase):
             N, dev = self.num_envs, self.device
             toff, uoff, eoff, nbytes = _cabi.host_result_layout(N)
             sets = []
-            for _ in range(2):
-                host = torch.zeros(nbytes, dtype=torch.uint8, pin_memory=True)
+            for k_set in range(2):
+                host = self._relay.host_block(k_set) if self._relay is not None else None
+                if host is None:
+                    host = torch.zeros(nbytes, dtype=torch.uint8, pin_memory=True)
                 devb = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
                 dact = torch.zeros(N * 8, dtype=torch.uint8, device=dev)
                 r = host.numpy()
@@ -856,6 +864,8 @@ class TradingVectorEnv(_VectorEnvBase):
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream(dev))
                 io.sparse_flags = int(self.sparse_flags)
+                if self._relay is not None:
+                    io.reward_host_count = self._relay.own_count
                 r32 = r32d = None
                 if self.reward_wire == "f32":
                     r32 = torch.zeros(N, dtype=torch.float32, pin_memory=True)
@@ -868,6 +878,27 @@ class TradingVectorEnv(_VectorEnvBase):
                              "error": r[eoff:eoff + 4].view(np.int32)})
             self._async = {"sets": sets, "pending": [], "n": 0}
         return self._async
+
+    def enable_result_relay(self, group=None, plan=None, verbose=False):
+        """COLLECTIVE (every rank of the ``torch.distributed`` job, or of ``group``): balance the device-to-host result
+        bytes of a multi-GPU host-policy job over the GPUs' PCIe links in proportion to the bandwidth each link gets while
+        all ranks copy (measured here in four short rounds: the even load, then the planned split, refined).  A rank on a slow link then ships
+        the tail of its fp64 rewards over NVLink to a peer GPU whose copy engine writes them into this rank's (shared,
+        pinned) result block — lossless, no kernel, no NCCL call per step (``relay.py``, ``gte_relay_*``).  Afterwards
+        every ``step()`` / ``step_async()`` is a collective too: all ranks must make the same calls in the same order.
+        ``plan`` = {sender rank: (peer rank, envs)} overrides the measurement (also: ``GTE_RELAY_FORCE``).  Returns the
+        plan and the measured bandwidths; an empty plan (links within 20 % of each other) changes nothing."""
+        from .relay import ResultRelay
+        if self.output != "hybrid" or self.reward_wire != "f64" or not self.autoreset:
+            raise ValueError("the result relay serves output='hybrid' with the lossless fp64 reward wire and autoreset")
+        if self._async is not None and self._async["pending"]:
+            raise RuntimeError("step_async() iterations are in flight: call step_wait() first")
+        if self._relay is not None:
+            self._relay.close()
+        self._async = None                                 # wire sets are rebuilt (a sender's result blocks move to shared memory)
+        with torch.cuda.device(self.device):
+            self._relay = ResultRelay(self, group=group, plan=plan, verbose=verbose)
+        return self._relay.describe()
 
     def step_async(self, actions):
         """Enqueue one lockstep iteration for host actions and return at once (`output="hybrid"`): the action copy, the
@@ -884,6 +915,8 @@ class TradingVectorEnv(_VectorEnvBase):
             raise RuntimeError("two iterations are already in flight: call step_wait() first")
         k = st["n"] & 1
         ws = st["sets"][k]
+        if self._relay is not None and (self._relay.count & 1) != k:
+            raise RuntimeError("result relay: wire sets out of step with the relay's iteration count")
         self._host_buffers()
         a = np.asarray(actions)
         if a.shape != (self.num_envs,):
@@ -902,10 +935,13 @@ class TradingVectorEnv(_VectorEnvBase):
             a = buf
         io = ws["io"]
         io.actions = a.ctypes.data
-        red = self._red_stream
+        red, relay = self._red_stream, self._relay
+        if relay is not None:
+            relay.before_begin()                          # this rank's share of its senders' iteration, enqueued first
         if red is not None:
             if self._red_snapshot is not None:
                 torch.cuda.current_stream(self.device).wait_event(self._red_snapshot)
+        if red is not None or relay is not None:
             io.step_done_event = ws["event"].cuda_event
         self._P.action_bytes = a.dtype.itemsize
         self._tick += 1
@@ -919,6 +955,8 @@ class TradingVectorEnv(_VectorEnvBase):
             self._P.action_bytes = 0
         if rc:
             _cabi.check(rc, "gte_step_host_begin")
+        if relay is not None:
+            relay.after_begin(k, ws["dev"].data_ptr(), ws["event"].cuda_event)
         if red is not None:
             self._issue_metric_allreduce(None, after=ws["event"])
         st["pending"].append(k)
@@ -931,11 +969,14 @@ class TradingVectorEnv(_VectorEnvBase):
         st = self._async
         if st is None or not st["pending"]:
             raise RuntimeError("step_wait() without a pending step_async()")
-        ws = st["sets"][st["pending"].pop(0)]
+        k = st["pending"].pop(0)
+        ws = st["sets"][k]
         with torch.cuda.device(self.device):
             rc = self._lib.gte_step_host_end(ws["io_ref"])
         if rc:
             _cabi.check(rc, "gte_step_host_end")
+        if self._relay is not None:
+            self._relay.wait(k)                           # the tail of the rewards comes through a peer GPU's link
         self._last_reward_host = ws["reward"]
         if ws["error"][0]:
             self._raise_on_flag(int(ws["error"][0]))
@@ -1030,6 +1071,9 @@ class TradingVectorEnv(_VectorEnvBase):
             while self._async["pending"]:                 # let the iterations in flight land before the buffers go
                 self._lib.gte_step_host_end(self._async["sets"][self._async["pending"].pop(0)]["io_ref"])
             self._async = None
+        if getattr(self, "_relay", None) is not None:    # collective, like enable_result_relay()
+            self._relay.close()
+            self._relay = None
         if getattr(self, "host_io", None) == "server" and getattr(self, "_lib", None) is not None:
             self._lib.gte_serve_stop()           # the resident server kernel, if it is still waiting for requests
         self._host = None

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GTE_VERSION 202            /* 0.2.2 */
+#define GTE_VERSION 203            /* 0.2.3 */
 #define GTE_MAX_POSITIONS 64
 #define GTE_MAX_DATASETS 64        /* least-used rotation keeps a 64-bit "used this round" mask per env */
 #define GTE_N_METRICS 8
@@ -261,6 +261,10 @@ typedef struct GteHostIO {
                                         fp64 rewards stay on the device; the result block then only brings back its
                                         header + ended list (sparse_flags) or header + list + dense flags              */
     void* dev_reward_f32;            /* DEVICE, f32 [N], or NULL                                                          */
+    int64_t reward_host_count;       /* copy engines only; 0 or N = all.  0 < count < N: this call's own device-to-host copy
+                                        delivers only the FIRST count rewards (and the header / ended list / flags); rewards
+                                        [count, N) stay in the device block for the caller to route to the host through a
+                                        peer GPU's PCIe link (gte_relay_push) — the multi-GPU result relay              */
     int32_t mode;                    /* enum GteHostIOMode                                                             */
     int32_t sparse_flags;            /* copy engines only: bring back just the sparse prefix of the result block
                                         (GTE_HOST_RESULT_SPARSE_BYTES: reward | header | ended list) — the dense
@@ -340,6 +344,41 @@ int gte_step_host(const GteParams* params, const GteData* data, const GteState* 
 int gte_step_host_begin(const GteParams* params, const GteData* data, const GteState* state, const GteHostIO* io,
                         const GteStepOut* out, float* obs, int autoreset, int variant, void* stream);
 int gte_step_host_end(const GteHostIO* io);
+
+/* ---- result relay (multi-GPU host IO) --------------------------------------------------------------------------
+ * On a box where the GPUs' device-to-host paths are unequal under load (measured on an 8 x B200 node: 12.9 GB/s for each
+ * of four GPUs against 22.6 GB/s for each of the other four when all eight copy at once), a rank on a slow path ships the
+ * tail of its result block over NVLink into a buffer on a peer GPU with a fast path; the PEER's copy engine then writes
+ * it into the slow rank's result block, which lives in host memory both processes map (POSIX shared memory, registered
+ * with gte_host_register in both).  No kernel and no host thread is involved in the data path: the sender's copy engine
+ * writes data then a sequence word into the peer buffer (CUDA IPC mapping), the peer's stream waits for that word with a
+ * stream memory operation (cuStreamWaitValue32), copies the data to the host and, behind it, the sequence word — which
+ * the slow rank's host polls.  A rank may push to one peer and serve any number of peers.  Nothing in the reference
+ * corresponds to this (it has no device): it exists to keep gte_step_host's bytes-per-second up at 8 GPUs.
+ *
+ * gte_relay_supported: 1 when the current device can wait on memory from a stream (needed by gte_relay_serve).
+ * gte_relay_alloc:  cudaMalloc a relay buffer of `bytes` payload (+ a 256-byte header holding the sequence word), zeroed;
+ *                   *dev_base receives the buffer, ipc_handle (64 bytes) what another process passes to gte_relay_open.
+ * gte_relay_open:   map a peer process's relay buffer into this process (peer access enabled lazily).
+ * gte_relay_release: undo gte_relay_alloc (opened == 0) or gte_relay_open (opened != 0).
+ * gte_relay_push:   (sender) on a library-owned stream: wait for after_event (a cudaEvent_t recorded behind the step
+ *                   kernel: GteHostIO.step_done_event), copy `bytes` from src_dev into the peer buffer's payload, then
+ *                   publish `seq` in the peer buffer's header; done_event (a cudaEvent_t or NULL) is recorded behind both
+ *                   — the caller orders the next writer of src_dev behind it.
+ * gte_relay_serve:  (peer) on a library-owned stream per `lane` (0..7, one per rank served): wait until the header of
+ *                   own_base holds a sequence number >= seq, copy `bytes` of payload to host_dst, then the 4-byte
+ *                   sequence word to host_seq.  Both host addresses must be pinned for this process (gte_host_register).
+ *                   Returns at once; the sender's host learns of completion by polling *host_seq == seq.
+ * gte_host_register / gte_host_unregister: page-lock a host range (e.g. a shared-memory mapping) for DMA. */
+#define GTE_RELAY_HEADER_BYTES 256
+int gte_relay_supported(void);
+int gte_relay_alloc(int64_t bytes, void** dev_base, void* ipc_handle);
+int gte_relay_open(const void* ipc_handle, void** dev_base);
+int gte_relay_release(void* dev_base, int opened);
+int gte_relay_push(void* peer_base, const void* src_dev, int64_t bytes, uint32_t seq, void* after_event, void* done_event);
+int gte_relay_serve(int lane, void* own_base, int64_t bytes, uint32_t seq, void* host_dst, void* host_seq);
+int gte_host_register(void* ptr, int64_t bytes);
+int gte_host_unregister(void* ptr);
 
 /* Stop the resident server kernel of the current device (GTE_IO_SERVER), if one is running, and wait for it.  Every
  * other entry point does this implicitly before it enqueues anything. */

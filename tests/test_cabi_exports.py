@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/gte_b200.h but not exported"
     assert set(_cabi.EXPORTS) == set(_declared_functions())
     lib.gte_version.restype = ctypes.c_int
-    assert lib.gte_version() == _cabi.GTE_VERSION == 202
+    assert lib.gte_version() == _cabi.GTE_VERSION == 203
     lib.gte_build_id.restype = ctypes.c_char_p
     assert lib.gte_build_id().decode() == _cabi.source_hash() == _cabi.built_id()
 

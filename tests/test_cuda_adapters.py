@@ -151,3 +151,21 @@ def test_narrow_integer_host_actions_are_widened_on_the_device(output):
     assert env.pinned_actions().dtype == np.int8                     # the default wire type holds Discrete(P)
     with pytest.raises(ValueError):
         env.pinned_actions(np.uint8)
+
+
+def test_result_relay_between_two_processes_is_bit_exact():
+    """The multi-GPU result relay (relay.py, gte_relay_*): two processes — on this box's one GPU, so the NVLink hop is a
+    local copy, everything else (CUDA IPC mapping, stream wait on the sequence word, the peer's copy engine writing into
+    the sender's shared pinned result block) is the real thing — each step a relayed and a plain env and compare reward /
+    flags bit for bit, synchronously and with two iterations in flight, in both directions at once."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GTE_HOST_SPIN_TIMEOUT_S="20")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29671", os.path.join(root, "tools", "relay_check.py"), "--same-gpu", "--envs", "65536",
+           "--plan", "0>1:0.3,1>0:0.2"]
+    r = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert '"relay_check": "ok"' in r.stdout

@@ -186,3 +186,45 @@ def test_hostbind_helpers_parse_cpu_lists_and_device_order(monkeypatch):
     assert info == {"gpu": 0, "bound": False, "how": "disabled"}
     info = hostbind.bind_host_to_gpu(0)                         # no GPU / no NUMA information here: a no-op that says so
     assert info["gpu"] == 0 and "how" in info
+
+
+# ---- result relay (relay.py): the planner and the shared block, without a device -----------------------------------
+def test_relay_plan_pairs_slow_links_with_fast_ones_and_leaves_even_links_alone():
+    from gym_trading_env_b200.relay import QUANTUM, parse_forced_plan, plan_relay
+    N = 1 << 21
+    bw = [12.9, 12.9, 12.9, 12.9, 22.5, 22.7, 23.0, 22.1]          # profiles/r02_host_io_probe_n8.json
+    plan = plan_relay(bw, N)
+    assert sorted(plan) == [0, 1, 2, 3] and sorted(f for f, _ in plan.values()) == [4, 5, 6, 7]
+    for s, (f, x) in plan.items():
+        assert x % QUANTUM == 0 and 0 < x < N // 2
+        t_s, t_f = (N - x) / bw[s], (N + x) / bw[f]                  # both links finish together
+        assert abs(t_s - t_f) / t_f < 0.01
+    assert plan_relay([50.0, 51.0, 49.5, 50.2], N) == {}              # within 20 %: nothing to balance
+    assert plan_relay([10.0], N) == {} and plan_relay([], N) == {}
+    assert plan_relay([10.0, 100.0], N)[0] == (1, N // 2 // QUANTUM * QUANTUM)      # never more than half
+    assert plan_relay([0.0, 10.0], N) == {}
+    assert plan_relay(bw, N) == plan_relay(list(bw), N)               # pure: the same plan on every rank
+    assert parse_forced_plan("0>1:0.3, 2>3:0.25", 1 << 18) == {0: (1, 77824), 2: (3, 65536)}
+    assert parse_forced_plan("", 1 << 18) == {} and parse_forced_plan("0>1:0.0001", 1 << 18) == {}
+
+
+def test_relay_shared_block_is_one_memory_seen_through_two_mappings():
+    from gym_trading_env_b200.relay import SharedPinnedBlock
+
+    class NoDevice:                                                    # page-locking needs a GPU; the mapping does not
+        def __init__(self): self.calls = []
+        def gte_host_register(self, p, n): self.calls.append(("reg", n)); return 0
+        def gte_host_unregister(self, p): self.calls.append(("unreg",)); return 0
+
+    lib = NoDevice()
+    own = SharedPinnedBlock(lib, 1 << 16)
+    peer = SharedPinnedBlock(lib, 1 << 16, path=own.path)
+    assert own.array.flags.writeable and not own.array.any()
+    own.array[5] = 7
+    peer.array[1000:1004].view(np.uint32)[0] = 0xdeadbeef
+    assert peer.array[5] == 7 and own.array[1000:1004].view(np.uint32)[0] == 0xdeadbeef
+    own.drop_fd()                                                      # the mappings outlive the descriptor
+    peer.array[9] = 4
+    assert own.array[9] == 4
+    own.close(); peer.close(); own.close()
+    assert lib.calls == [("reg", 1 << 16), ("reg", 1 << 16), ("unreg",), ("unreg",)]
