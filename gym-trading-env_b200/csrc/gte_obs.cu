@@ -160,13 +160,21 @@ struct FusedStep {
     StepConsts K;
     GteStepOut O;
     int autoreset;
+    unsigned int* sched;       // DYN only: {next tile to hand out (beyond the first gridDim.x), CTAs finished}, both 0 at launch
 };
 
-template <int WS, int RT, int G, int UNIT = kTileEnvs, bool FUSED = false>
+// DYN (large batches): tiles are CLAIMED, not assigned — tile 0 of a CTA is its block index, every further one comes from
+// a global counter (one atomicAdd per tile, issued by the producer a whole tile before its answer is needed).  Measured
+// (tools/store_path_probe.cu): a persistent grid that splits a 5.4 GB store stream EVENLY over the SMs writes 6.2 TB/s, the
+// same stream handed out on demand 7.4-7.6 TB/s — the SMs do not all reach memory equally fast, and with a static split
+// the launch lasts as long as the slowest of them.  The producer publishes each tile id through shared memory (ring of 4
+// ids, riding on the release of the stage's full barrier); a tile id past the end stops consumers and store warp.
+template <int WS, int RT, int G, int UNIT = kTileEnvs, bool FUSED = false, bool DYN = false>
 __global__ void __launch_bounds__(kCoopThreads, FUSED ? 4 : 1)
 obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float* __restrict__ obs,
                     const ObsShape sh, const int env_begin, const int env_end, const FusedStep FS) {
     static_assert(RT >= 2, "a ring tile is requested while the previous one is being consumed");
+    static_assert(!DYN || (RT == 2 && !FUSED), "claimed tiles: the producer looks exactly one ring tile ahead; a fused CTA owns its envs");
     static_assert(UNIT % G == 0 && kTileEnvs % UNIT == 0, "a work unit is a whole number of groups inside one ring block");
     // work unit ("tile") = UNIT consecutive envs inside one 32-env ring block: 32 normally, 16 or 8 when the batch
     // is so small that whole blocks would leave CTAs idle or unevenly loaded (the block is then fetched once per unit)
@@ -184,6 +192,7 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
     __shared__ int f_live[FUSED ? kFusedMaxEnvs : 1];                 //        env this CTA owns, written by its step phase
     __shared__ double f_pos[FUSED ? GTE_MAX_POSITIONS : 1];
     __shared__ int f_T0;
+    __shared__ int tile_id_s[4];                                 // DYN: id of tile k of this CTA at [k & 3]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool ring = sh.nd > 0;
     const uint32_t win_bytes = (uint32_t)sh.win_bytes;
@@ -207,6 +216,7 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
 
     // tile k of this CTA = unit_envs consecutive envs, tiles strided over the grid; group gi of it = G envs
     auto tile_env0 = [&](int k) -> int64_t { return env_begin + ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * unit_envs; };
+    auto env0_of = [&](int t) -> int64_t { return env_begin + (int64_t)t * unit_envs; };        // DYN: first env of tile id t
     // ring slot of window row 0 AFTER this iteration's transition.  Two launches: the step kernel has advanced the clock.
     // FUSED: the clock is advanced by the last CTA of THIS launch, after every CTA has read it here.
     int s0 = 0;
@@ -233,10 +243,11 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
         s0 = (int)((*S.ring_clock + 1ull) % (uint64_t)sh.W);
     }
     auto group_env0 = [&](int k, int gi) -> int64_t { return tile_env0(k) + gi * G; };
-    auto group_valid = [&](int k, int gi) -> int {               // envs of the group inside [env_begin, env_end)
-        const int64_t left = (int64_t)env_end - group_env0(k, gi);
+    auto valid_from = [&](int64_t e0) -> int {                   // envs of the group starting at env e0 inside [.., env_end)
+        const int64_t left = (int64_t)env_end - e0;
         return left >= G ? G : (left > 0 ? (int)left : 0);
     };
+    auto group_valid = [&](int k, int gi) -> int { return valid_from(group_env0(k, gi)); };
 
     if (warp == kCoopConsumerWarps) {
         // ------------------------------------------------------------------ producer warp
@@ -265,6 +276,74 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
                 bulk_g2s(rbase + (size_t)stage * rstride, ring_tile(S, sh.W, tile_env0(k)), rstride, &full_r[stage]);
             }
         };
+        if (DYN) {
+            auto load_tile_id = [&](int t) {
+                TilePre p;
+                p.src = 0ull; p.first_live = 0;
+                const int64_t env = env0_of(t) + lane;
+                if (lane < unit_envs && env < env_end) {
+                    const int ep = __ldcg(S.ep_start + env), st = __ldcg(S.step + env), ds = __ldcg(S.dataset_idx + env);
+                    p.first_live = sh.W - 1 - st;
+                    p.src = (unsigned long long)window_src(D, sh, ds, ep + st + 1 - sh.W);
+                }
+                return p;
+            };
+            auto issue_ring_id = [&](int k, int t) {             // lane 0
+                if (ring && env0_of(t) < env_end) {
+                    const int stage = k % RT, use = k / RT;
+                    if (use > 0) mbar_wait(&empty_r[stage], (uint32_t)(use - 1) & 1u);
+                    mbar_expect_tx(&full_r[stage], rstride);
+                    bulk_g2s(rbase + (size_t)stage * rstride, ring_tile(S, sh.W, env0_of(t)), rstride, &full_r[stage]);
+                }
+            };
+            // lane 0 claims; the answer of a claim is only looked at one whole tile later (claim_use), so the round trip of
+            // the atomic never stalls the pipeline
+            auto claim = [&]() -> int { return lane == 0 ? (int)(gridDim.x + atomicAdd(FS.sched, 1u)) : 0; };
+            auto claim_use = [&](int raw) -> int {
+                asm volatile("" : "+r"(raw));                    // the value is waited for HERE, not where it was asked for
+                return __shfl_sync(FULL, raw, 0);
+            };
+            int ta = (int)blockIdx.x;                            // T(0)
+            int tb = claim_use(claim());                         // T(1): the one exposed round trip, once per CTA
+            int tc_raw = claim();                                // T(2), in flight
+            TilePre pc = load_tile_id(ta), pn = load_tile_id(tb);
+            if (lane == 0) issue_ring_id(0, ta);
+            int q = 0;
+            for (int k = 0;; ++k) {
+                const bool last = env0_of(ta) >= env_end;        // a tile id past the end: tell the others and stop
+                for (int gi = 0; gi < GROUPS; ++gi, ++q) {
+                    const int n_valid = last ? 0 : valid_from(env0_of(ta) + gi * G);
+                    if (n_valid == 0 && !(last && gi == 0)) break;
+                    if (!last && lane == 0 && gi == RING_AT) issue_ring_id(k + 1, tb);
+                    __syncwarp();
+                    const int stage = q % WS, use = q / WS;
+                    if (use > 0) mbar_wait(&empty_w[stage], (uint32_t)(use - 1) & 1u);
+                    if (gi == 0) {
+                        first_live[k & 1][lane] = pc.first_live;
+                        if (lane == 0) tile_id_s[k & 3] = last ? -1 : ta;
+                        __syncwarp();
+                    }
+                    if (last) {                                  // completes the stage's phase without data (release: the -1)
+                        if (lane == 0) mbar_arrive(&full_w[stage]);
+                        break;
+                    }
+                    unsigned char* sbuf = wbase + (size_t)stage * wstage_bytes;
+                    if (lane == 0) mbar_expect_tx(&full_w[stage], (uint32_t)n_valid * win_bytes);
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const unsigned long long src = __shfl_sync(FULL, pc.src, gi * G + g);
+                        if (lane == 0 && g < n_valid)
+                            bulk_g2s(sbuf + (size_t)g * win_bytes, reinterpret_cast<const void*>(src), win_bytes, &full_w[stage]);
+                    }
+                }
+                if (last) break;
+                const int tc = claim_use(tc_raw);                // asked for one tile ago
+                tc_raw = claim();
+                pc = pn;
+                pn = load_tile_id(tc);
+                ta = tb; tb = tc;
+            }
+        } else {
         TilePre pc = load_tile(0), pn = load_tile(1);
         if (lane == 0)
             for (int k = 0; k < RT - 1; ++k) issue_ring(k);
@@ -293,17 +372,27 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
             pc = pn;
             pn = load_tile(k + 2);
         }
+        }
     } else if (warp == kCoopConsumerWarps + 1) {
         // ------------------------------------------------------------------ store warp (one thread)
         if (lane == 0) {
             int q = 0;
-            for (int k = 0; tile_env0(k) < env_end; ++k) {
+            int64_t e0 = 0;                                                  // DYN: first env of the current tile
+            for (int k = 0; DYN || tile_env0(k) < env_end; ++k) {
+                bool stop = false;
                 for (int gi = 0; gi < GROUPS; ++gi, ++q) {
-                    const int n_valid = group_valid(k, gi);
-                    if (n_valid == 0) break;
                     const int ws = q % WS;
-                    mbar_wait(&ready_w[ws], (uint32_t)(q / WS) & 1u);        // every consumer warp has patched the group
-                    bulk_s2g(reinterpret_cast<char*>(obs) + group_env0(k, gi) * (int64_t)win_bytes,
+                    if (DYN && gi == 0) {                                    // the tile id rides on the first group's barrier
+                        mbar_wait(&ready_w[ws], (uint32_t)(q / WS) & 1u);
+                        const int t = *reinterpret_cast<volatile int*>(&tile_id_s[k & 3]);
+                        if (t < 0) { stop = true; break; }
+                        e0 = env0_of(t);
+                    }
+                    const int n_valid = DYN ? valid_from(e0 + gi * G) : group_valid(k, gi);
+                    if (n_valid == 0) break;
+                    if (!(DYN && gi == 0))
+                        mbar_wait(&ready_w[ws], (uint32_t)(q / WS) & 1u);    // every consumer warp has patched the group
+                    bulk_s2g(reinterpret_cast<char*>(obs) + (DYN ? e0 + gi * G : group_env0(k, gi)) * (int64_t)win_bytes,
                              wbase + (size_t)ws * wstage_bytes, (uint32_t)n_valid * win_bytes);
                     bulk_commit();
                     if (q > 0) {
@@ -311,6 +400,7 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
                         mbar_arrive(&empty_w[(q - 1) % WS]);
                     }
                 }
+                if (stop) break;
             }
             bulk_wait_read<0>();                                 // smem must outlive the last store's reads
         }
@@ -321,19 +411,33 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
         // meet: each one signals the store warp (and, after a tile's last group, the producer) on its own.
         const int g = tid % G, t = tid / G;
         int q = 0;
-        for (int k = 0; tile_env0(k) < env_end; ++k) {
+        int64_t e0 = 0;                                                      // DYN: first env of the current tile
+        for (int k = 0; DYN || tile_env0(k) < env_end; ++k) {
             const int rs = k % RT;
+            bool stop = false;
             for (int gi = 0; gi < GROUPS; ++gi, ++q) {
-                const int n_valid = group_valid(k, gi);
-                if (n_valid == 0) break;
                 const int ws = q % WS;
+                if (DYN && gi == 0) {                                        // the tile id rides on the first group's barrier
+                    mbar_wait(&full_w[ws], (uint32_t)(q / WS) & 1u);
+                    const int tid_k = *reinterpret_cast<volatile int*>(&tile_id_s[k & 3]);
+                    if (tid_k < 0) {                                         // no more tiles: pass the word on to the store warp
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&ready_w[ws]);
+                        stop = true;
+                        break;
+                    }
+                    e0 = env0_of(tid_k);
+                }
+                const int n_valid = DYN ? valid_from(e0 + gi * G) : group_valid(k, gi);
+                if (n_valid == 0) break;
                 unsigned char* sbuf = wbase + (size_t)ws * wstage_bytes;
-                mbar_wait(&full_w[ws], (uint32_t)(q / WS) & 1u);             // windows landed (acquire: first_live too)
+                if (!(DYN && gi == 0))
+                    mbar_wait(&full_w[ws], (uint32_t)(q / WS) & 1u);         // windows landed (acquire: first_live too)
                 if (ring) {
                     mbar_wait(&full_r[rs], (uint32_t)(k / RT) & 1u);         // the tile's ring block landed
                     if (g < n_valid) {
                         const int live0 = first_live[k & 1][gi * G + g];
-                        const int e = (int)(tile_env0(k) & 31) + gi * G + g;      // env lane within the 32-env ring block
+                        const int e = (int)((DYN ? e0 : tile_env0(k)) & 31) + gi * G + g;      // env lane within the 32-env ring block
                         float* fbuf = reinterpret_cast<float*>(sbuf + (size_t)g * win_bytes);
                         const unsigned char* rtile = rbase + (size_t)rs * rstride;
                         for (int s = t; s < sh.W; s += SPP) {
@@ -354,6 +458,19 @@ obs_tma_coop_kernel(const GteParams P, const GteData D, const GteState S, float*
                     if (ring && gi == GROUPS - 1) mbar_arrive(&empty_r[rs]);  // ... and its reads of the ring block are done
                 }
             }
+            if (stop) break;
+        }
+    }
+    if (DYN) {
+        // the last CTA to finish leaves both counters at zero for the next launch that is handed this slot
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(FS.sched + 1, 1u) == gridDim.x - 1) {
+                FS.sched[0] = 0u;
+                FS.sched[1] = 0u;
+                __threadfence();
+            }
         }
     }
 }
@@ -367,10 +484,20 @@ static size_t tma_smem_bytes(const ObsShape& sh, const TmaConfig& c) {
     return (size_t)c.group * c.wstages * sh.win_bytes + ring;
 }
 
-static ObsKernelFn tma_kernel(const TmaConfig& c, int unit = kTileEnvs, bool fused = false) {
-    // (window stages, ring-tile stages, envs per group) combinations compiled in; smaller work units and the fused
-    // step+gather form for the default shapes
+static ObsKernelFn tma_kernel(const TmaConfig& c, int unit = kTileEnvs, bool fused = false, bool dyn = false) {
+    // (window stages, ring-tile stages, envs per group) combinations compiled in; smaller work units, the fused
+    // step+gather form and the claimed-tiles form (large batches) for the default shapes
     const int key = c.wstages * 10000 + c.rtiles * 100 + c.group;
+    if (dyn) {
+        if (fused || unit != kTileEnvs) return nullptr;
+        switch (key) {
+            case 30201: return obs_tma_coop_kernel<3, 2, 1, 32, false, true>;
+            case 30202: return obs_tma_coop_kernel<3, 2, 2, 32, false, true>;
+            case 30204: return obs_tma_coop_kernel<3, 2, 4, 32, false, true>;
+            case 30208: return obs_tma_coop_kernel<3, 2, 8, 32, false, true>;
+            default: return nullptr;
+        }
+    }
     if (fused) {
         switch (unit * 100000 + key) {
             case 3230201: return obs_tma_coop_kernel<3, 2, 1, 32, true>;
@@ -456,9 +583,29 @@ struct TmaPlan {
     ObsKernelFn kern;
     int grid, unit, envs_per_cta;
     size_t smem;
+    unsigned int* sched;       // claimed-tiles form: this launch's pair of counters, else nullptr
 };
 
-static cudaError_t plan_tma(const ObsShape& sh, int n_envs, bool fused, TmaPlan* out) {
+// Counters of the claimed-tiles form: 64 slots of {next tile, CTAs finished} per device, handed out round-robin (launches
+// that overlap on different streams get different slots; the last CTA of a launch zeroes its slot again).  Allocated on
+// first use — never inside a stream capture (the caller then falls back to the static split).
+constexpr int kDynMinTilesPerCta = 8;
+static unsigned int* dyn_sched_slot(cudaStream_t stream) {
+    static unsigned int* pool[16] = {};
+    static unsigned int next[16] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    unsigned int*& p = pool[dev & 15];
+    if (p == nullptr) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
+        if (cudaMalloc(reinterpret_cast<void**>(&p), 64 * 32) != cudaSuccess) { p = nullptr; (void)cudaGetLastError(); return nullptr; }
+        if (cudaMemset(p, 0, 64 * 32) != cudaSuccess) { cudaFree(p); p = nullptr; (void)cudaGetLastError(); return nullptr; }
+    }
+    return p + 8 * (next[dev & 15]++ & 63u);
+}
+
+static cudaError_t plan_tma(const ObsShape& sh, int n_envs, bool fused, TmaPlan* out, cudaStream_t stream = nullptr) {
     const TmaConfig cfg = tma_config(sh);
     const size_t smem = tma_smem_bytes(sh, cfg);
     ObsKernelFn probe = tma_kernel(cfg, kTileEnvs, fused);
@@ -512,10 +659,23 @@ static cudaError_t plan_tma(const ObsShape& sh, int n_envs, bool fused, TmaPlan*
     const int64_t need = ((int64_t)n_envs + unit - 1) / unit;
     const int64_t waves = (need + cap - 1) / cap;
     out->grid = (int)((need + waves - 1) / waves);
+    static const int tiles_per_cta = [] { const char* e = getenv("GTE_TMA_TILES_PER_CTA"); return e ? atoi(e) : 0; }();   // tuning runs
+    if (tiles_per_cta > 0 && !fused && (need + tiles_per_cta - 1) / tiles_per_cta > out->grid)
+        out->grid = (int)((need + tiles_per_cta - 1) / tiles_per_cta);
     out->unit = unit;
     out->envs_per_cta = (int)(((need + out->grid - 1) / out->grid) * unit);
     out->smem = smem;
     out->kern = tma_kernel(cfg, unit, fused);
+    out->sched = nullptr;
+    // large batches: tiles are claimed from a counter instead of being split evenly over the CTAs (GTE_TMA_DYN=0: never,
+    // 2: whenever the kernel exists, for tests of the small-batch corners)
+    static const int dyn_mode = [] { const char* e = getenv("GTE_TMA_DYN"); return e ? atoi(e) : 1; }();
+    ObsKernelFn dk = tma_kernel(cfg, unit, fused, true);
+    if (dyn_mode > 0 && dk != nullptr && tiles_per_cta <= 0 &&
+        (dyn_mode >= 2 || (need + out->grid - 1) / out->grid >= kDynMinTilesPerCta)) {
+        unsigned int* slot = dyn_sched_slot(stream);
+        if (slot != nullptr) { out->kern = dk; out->sched = slot; }
+    }
     int unused = 0;
     return out->kern == probe ? cudaSuccess : configure(out->kern, &unused);
 }
@@ -553,7 +713,7 @@ cudaError_t launch_fused_step_obs(const GteParams& P, const GteData& D, const Gt
     cudaError_t e = fused_plan(P, D, variant, &plan, done);
     if (e != cudaSuccess || !*done) return e;
     FusedStep fs;
-    fs.actions = actions; fs.K = K; fs.O = O; fs.autoreset = autoreset;
+    fs.actions = actions; fs.K = K; fs.O = O; fs.autoreset = autoreset; fs.sched = nullptr;
     return launch_pdl(plan.kern, dim3(plan.grid), dim3(kCoopThreads), plan.smem, stream, P, D, S, obs, make_shape(P), 0,
                       P.n_envs, fs);
 }
@@ -593,10 +753,11 @@ cudaError_t launch_obs_range(const GteParams& P, const GteData& D, const GteStat
     if (variant == GTE_OBS_TMA) {
         if (!obs_tma_supported(P, D)) return cudaErrorInvalidValue;
         TmaPlan plan;
-        cudaError_t e = plan_tma(sh, n_envs, false, &plan);
+        cudaError_t e = plan_tma(sh, n_envs, false, &plan, stream);
         if (e != cudaSuccess) return e;
-        return launch_pdl(plan.kern, dim3(plan.grid), dim3(kCoopThreads), plan.smem, stream, P, D, S, obs, sh, env_begin, env_end,
-                          FusedStep{});
+        FusedStep fs{};
+        fs.sched = plan.sched;
+        return launch_pdl(plan.kern, dim3(plan.grid), dim3(kCoopThreads), plan.smem, stream, P, D, S, obs, sh, env_begin, env_end, fs);
     }
     return cudaErrorInvalidValue;
 }

@@ -566,3 +566,20 @@ def test_persistent_rollout_with_dataset_rotation_and_narrow_actions_equals_step
     assert torch.equal(a._metrics_total[:3], b._metrics_total[:3])
     torch.testing.assert_close(a._metrics_total, b._metrics_total, rtol=1e-12, atol=1e-12)
     assert set(a._dataset_idx.cpu().tolist()) == {0, 1, 2}
+
+
+def test_claimed_tiles_gather_passes_the_parity_suites_at_every_size():
+    """The gather's claimed-tiles form (tiles handed out from a device counter instead of an even split; taken from
+    ~150k envs on, so the full-size C4 / C5 tests above already run it) forced on for EVERY windowed batch
+    (GTE_TMA_DYN=2): the golden / oracle parity files and the edge cases — ragged last tiles, batches smaller than the grid,
+    CTAs whose second tile is already past the end, env ranges — must not notice."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GTE_TMA_DYN="2")
+    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider",
+           os.path.join(root, "tests", "test_cuda_parity.py"), os.path.join(root, "tests", "test_cuda_edge_cases.py")]
+    r = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout

@@ -1,0 +1,8 @@
+# tuning helper: tiles per CTA of the TMA gather (0 = persistent single-wave grid)
+WORKLOAD=${WORKLOAD:-c5}
+for cfg in "GTE_TMA_TILES_PER_CTA=0" "GTE_TMA_TILES_PER_CTA=32" "GTE_TMA_TILES_PER_CTA=16" "GTE_TMA_TILES_PER_CTA=8" "GTE_TMA_TILES_PER_CTA=4" "GTE_TMA_TILES_PER_CTA=2" "GTE_TMA_TILES_PER_CTA=1"; do
+  env $cfg python bench.py --workload $WORKLOAD --no-e2e --no-cpu --no-configs --steps ${STEPS:-100} --warmup 5 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
+print('$cfg', 'us/step=%.2f obs_us=%.2f frac=%.3f step_us=%.2f clocks=%s' % (1e3*d['ms_per_step'], 1e3*r['kernel_ms'], r['frac'], 1e3*r['step_kernel_ms'], d['clocks']['sm_mhz']))"
+done
