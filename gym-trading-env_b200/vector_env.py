@@ -898,7 +898,11 @@ class TradingVectorEnv(_VectorEnvBase):
         self._async = None                                 # wire sets are rebuilt (a sender's result blocks move to shared memory)
         with torch.cuda.device(self.device):
             self._relay = ResultRelay(self, group=group, plan=plan, verbose=verbose)
-        return self._relay.describe()
+        desc = self._relay.describe()
+        if not self._relay.plan:                           # nothing to balance (or the set-up failed somewhere): the plain path
+            self._relay.close()
+            self._relay = None
+        return desc
 
     def step_async(self, actions):
         """Enqueue one lockstep iteration for host actions and return at once (`output="hybrid"`): the action copy, the
