@@ -30,9 +30,10 @@ from . import _cabi
 
 QUANTUM = 1024                      # envs: relayed tails are a multiple of this
 MIN_RATIO = 1.2                     # pairs whose measured bandwidths differ by less are left alone
+MAX_FRACTION = 0.5                  # a sender never ships more than half of its rewards (the peer buffers are sized for it)
 
 
-def plan_relay(bandwidth, n_envs, min_ratio=MIN_RATIO, quantum=QUANTUM, max_fraction=0.5):
+def plan_relay(bandwidth, n_envs, min_ratio=MIN_RATIO, quantum=QUANTUM, max_fraction=MAX_FRACTION):
     """Who ships how many of its per-env result words to whom.
 
     ``bandwidth[r]``: device-to-host GB/s rank r gets while every rank copies.  Ranks are paired slowest-with-fastest;
@@ -133,7 +134,7 @@ def measure_d2h_together(torch, dist, device, nbytes_of_rank, reps=6, group=None
 class ResultRelay:
     """Per-env state of the relay: the plan, this rank's role(s), the shared result blocks and the opened peer buffers."""
 
-    def __init__(self, env, group=None, plan=None, calibrate_rounds=4, verbose=False):
+    def __init__(self, env, group=None, plan=None, calibrate_rounds=2, verbose=False):
         import torch
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()):
@@ -154,10 +155,13 @@ class ResultRelay:
         if plan is None and forced is not None:
             plan = parse_forced_plan(forced, N)
         if plan is None:
-            # round 1: everybody copies a full block — decides WHICH pairs relay; later rounds copy the planned split
-            # and move each pair's split half-way towards what the rates seen last ask for.  (Measured on the 8 x B200
-            # node: the even load overstates a slow link's rate — its copy runs alone once the fast links have finished —
-            # 12.2 GB/s against 9.9 GB/s when the fast links stay busy for as long, so the split settles above round 1's.)
+            # round 1: everybody copies a full block — decides WHICH pairs relay; round 2 copies the planned split and
+            # moves each pair's split half-way towards what the rates seen then ask for.  (Measured on the 8 x B200 node:
+            # the even load overstates a slow link's rate — its copy runs alone once the fast links have finished — 12.2
+            # GB/s against 9.9 GB/s when the fast links stay busy for as long.)  Back-to-back copies are not how the job
+            # will load the links, though, and more rounds drift towards the split that suits two iterations in flight (every
+            # link busy all the time: 34-37 % shipped, 1.26 ms pipelined / 1.32-1.35 ms one step at a time) and away from
+            # the one that suits one step at a time (27-30 %: 1.26 ms / 1.32 ms pipelined) — measured, profiles/r02_tuning.md §6.
             plan, sizes = {}, [self.sparse_bytes] * self.world
             for rnd in range(max(1, int(calibrate_rounds))):
                 bw = measure_d2h_together(torch, dist, env.device, sizes, group=group)
@@ -218,11 +222,10 @@ class ResultRelay:
                 mine["paths"] = [b.path for b in self.blocks]
             # a peer allocates, per sender and wire set, the device buffer the sender's copy engine writes into
             for s in self.senders:
-                x = self.plan[s][1]
                 self._own[s] = []
                 for k in range(2):
                     base, handle = C.c_void_p(), (C.c_ubyte * 64)()
-                    _cabi.check(lib.gte_relay_alloc(8 * x, C.byref(base), handle), "gte_relay_alloc")
+                    _cabi.check(lib.gte_relay_alloc(8 * self.plan[s][1], C.byref(base), handle), "gte_relay_alloc")
                     self._own[s].append(base.value)
                     mine["handles"][(s, k)] = bytes(handle)
         except Exception as e:  # noqa: BLE001
@@ -240,10 +243,9 @@ class ResultRelay:
                     _cabi.check(lib.gte_relay_open(h, C.byref(base)), "gte_relay_open")
                     self.peer_bufs[k] = base.value
             for lane, s in enumerate(self.senders):                # map each sender's result blocks
-                x = self.plan[s][1]
                 blks = [SharedPinnedBlock(lib, self.block_bytes + 64, path=p) for p in everyone[s]["paths"]]
-                self.serve[s] = {"lane": lane, "bytes": 8 * x, "blocks": blks, "own": self._own[s],
-                                 "dst": [b.ptr + 8 * (N - x) for b in blks], "seq": [b.ptr + self.block_bytes for b in blks]}
+                self.serve[s] = {"lane": lane, "blocks": blks, "own": self._own[s],
+                                 "seq": [b.ptr + self.block_bytes for b in blks]}
         except Exception as e:  # noqa: BLE001
             err = e
         ok = self._everyone_ok(dist, err)                          # (also: every mapping exists, the descriptors can go)
@@ -276,9 +278,9 @@ class ResultRelay:
         iteration and the two copies into its result block."""
         k, seq = self.count & 1, (self.count + 1) & 0xffffffff
         for s in self.senders:
-            e = self.serve[s]
-            rc = self.lib.gte_relay_serve(e["lane"], C.c_void_p(e["own"][k]), e["bytes"], seq, C.c_void_p(e["dst"][k]),
-                                          C.c_void_p(e["seq"][k]))
+            e, x = self.serve[s], self.plan[s][1]
+            rc = self.lib.gte_relay_serve(e["lane"], C.c_void_p(e["own"][k]), 8 * x, seq,
+                                          C.c_void_p(e["blocks"][k].ptr + 8 * (self.N - x)), C.c_void_p(e["seq"][k]))
             if rc:
                 _cabi.check(rc, "gte_relay_serve")
 

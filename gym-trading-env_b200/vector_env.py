@@ -879,10 +879,11 @@ class TradingVectorEnv(_VectorEnvBase):
             self._async = {"sets": sets, "pending": [], "n": 0}
         return self._async
 
-    def enable_result_relay(self, group=None, plan=None, verbose=False):
+    def enable_result_relay(self, group=None, plan=None, verbose=False, calibrate_rounds=2):
         """COLLECTIVE (every rank of the ``torch.distributed`` job, or of ``group``): balance the device-to-host result
         bytes of a multi-GPU host-policy job over the GPUs' PCIe links in proportion to the bandwidth each link gets while
-        all ranks copy (measured here in four short rounds: the even load, then the planned split, refined).  A rank on a slow link then ships
+        all ranks copy (measured here in ``calibrate_rounds`` short rounds: the even load, then the planned split; 2 suits a
+        caller that steps one iteration at a time, 4 one that keeps two in flight with step_async).  A rank on a slow link then ships
         the tail of its fp64 rewards over NVLink to a peer GPU whose copy engine writes them into this rank's (shared,
         pinned) result block — lossless, no kernel, no NCCL call per step (``relay.py``, ``gte_relay_*``).  Afterwards
         every ``step()`` / ``step_async()`` is a collective too: all ranks must make the same calls in the same order.
@@ -897,12 +898,16 @@ class TradingVectorEnv(_VectorEnvBase):
             self._relay.close()
         self._async = None                                 # wire sets are rebuilt (a sender's result blocks move to shared memory)
         with torch.cuda.device(self.device):
-            self._relay = ResultRelay(self, group=group, plan=plan, verbose=verbose)
+            self._relay = ResultRelay(self, group=group, plan=plan, verbose=verbose, calibrate_rounds=calibrate_rounds)
         desc = self._relay.describe()
         if not self._relay.plan:                           # nothing to balance (or the set-up failed somewhere): the plain path
             self._relay.close()
             self._relay = None
         return desc
+
+    def result_relay_state(self):
+        """The relay's current plan, the measurements behind it and the adjustments the running job has made (or None)."""
+        return self._relay.describe() if self._relay is not None else None
 
     def step_async(self, actions):
         """Enqueue one lockstep iteration for host actions and return at once (`output="hybrid"`): the action copy, the
@@ -941,6 +946,7 @@ class TradingVectorEnv(_VectorEnvBase):
         io.actions = a.ctypes.data
         red, relay = self._red_stream, self._relay
         if relay is not None:
+            io.reward_host_count = relay.own_count        # (the running job may have moved the split)
             relay.before_begin()                          # this rank's share of its senders' iteration, enqueued first
         if red is not None:
             if self._red_snapshot is not None:

@@ -228,3 +228,4 @@ def test_relay_shared_block_is_one_memory_seen_through_two_mappings():
     assert own.array[9] == 4
     own.close(); peer.close(); own.close()
     assert lib.calls == [("reg", 1 << 16), ("reg", 1 << 16), ("unreg",), ("unreg",)]
+

@@ -27,7 +27,7 @@ for name, body in zip(demangle, parts[1:]):
     counts = {op: sum(1 for ln in lines if re.search(r"\b" + re.escape(op) + r"\b", ln)) for op in ops}
     short = re.sub(r"\(.*", "", name).replace("gte::", "")
     out["kernels"][short] = {"sass_instructions": len(lines), **{k: v for k, v in counts.items() if v}}
-    if "obs_tma_coop_kernel<3, 2, 4, 32, false>" in short:
+    if "obs_tma_coop_kernel<3, 2, 4, 32, false, true>" in short:            # the claimed-tiles form: what C5 / C4 launch
         excerpt = [short] + [ln.strip() for ln in lines if re.search(r"UBLKCP|SYNCS|UTMALDG", ln)][:24]
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "profiles", f"{tag}_sass.json"), "w"), indent=1)
