@@ -568,6 +568,31 @@ def test_persistent_rollout_with_dataset_rotation_and_narrow_actions_equals_step
     assert set(a._dataset_idx.cpu().tolist()) == {0, 1, 2}
 
 
+def test_reward_host_count_stops_the_results_copy_where_the_relay_takes_over():
+    """GteHostIO.reward_host_count (the result relay's hook in the C-ABI): the call's own device-to-host copy delivers the
+    first `count` rewards and the header / list / flags; rewards [count, N) stay on the device (for the caller to route
+    through a peer GPU) — the host array keeps whatever it held there."""
+    import gym_trading_env_b200 as gte
+    N, count = 50_000, 20_480
+    series = gte.frame_to_arrays(gte.make_gbm_ohlcv(20_000, seed=2))
+    kw = dict(positions=[-1, 0, 0.5, 1], windows=8, max_episode_duration=12, num_envs=N, seed=3, verbose=0, output="hybrid",
+              host_io="copy", **FEES)
+    for sparse in (True, False):
+        a, b = gte.TradingVectorEnv(series, sparse_flags=sparse, **kw), gte.TradingVectorEnv(series, sparse_flags=sparse, **kw)
+        a.reset(); b.reset()
+        acts = np.random.default_rng(5).integers(0, 4, size=(14, N)).astype(np.int8)
+        a.step(acts[0]); b.step(acts[0])
+        a._io.reward_host_count = count
+        for k in range(1, 14):                                          # (iteration 11 ends every episode at once: dense flags)
+            a._host["reward"][count:] = -7.0
+            ra, rb = a.step(acts[k]), b.step(acts[k])
+            H.assert_bits(ra[1][:count], rb[1][:count], f"step {k}: the rewards this call's own copy delivers")
+            assert np.all(ra[1][count:] == -7.0), "rewards past reward_host_count must not be copied by this call"
+            H.assert_bits(a.reward_device.cpu().numpy(), rb[1], f"step {k}: all rewards are on the device")
+            assert np.array_equal(ra[2], rb[2]) and np.array_equal(ra[3], rb[3]), k
+        a.close(); b.close()
+
+
 def test_claimed_tiles_gather_passes_the_parity_suites_at_every_size():
     """The gather's claimed-tiles form (tiles handed out from a device counter instead of an even split; taken from
     ~150k envs on, so the full-size C4 / C5 tests above already run it) forced on for EVERY windowed batch
