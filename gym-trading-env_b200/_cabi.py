@@ -123,7 +123,7 @@ class GteInfo(C.Structure):
 
 EXPORTS = ["gte_version", "gte_last_error", "gte_build_id", "gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs",
            "gte_step_host", "gte_step_host_begin", "gte_step_host_end", "gte_serve_stop", "gte_relay_supported", "gte_relay_alloc", "gte_relay_open",
-           "gte_relay_release", "gte_relay_push", "gte_relay_serve", "gte_host_register", "gte_host_unregister", "gte_rollout", "gte_info", "gte_obs_variant_for", "gte_default_chunks", "gte_struct_size",
+           "gte_relay_release", "gte_relay_push", "gte_relay_serve", "gte_relay_unblock", "gte_host_register", "gte_host_unregister", "gte_rollout", "gte_info", "gte_obs_variant_for", "gte_default_chunks", "gte_struct_size",
            "gte_step_obs_launches"]
 
 
@@ -220,6 +220,8 @@ def load():
     lib.gte_relay_release.argtypes = [C.c_void_p, C.c_int]
     lib.gte_relay_push.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]
     lib.gte_relay_serve.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.gte_relay_unblock.argtypes = [C.c_void_p, C.c_uint32]
+    lib.gte_relay_unblock.restype = C.c_int
     lib.gte_host_register.argtypes = [C.c_void_p, C.c_int64]
     lib.gte_host_unregister.argtypes = [C.c_void_p]
     for name in ("gte_relay_supported", "gte_relay_alloc", "gte_relay_open", "gte_relay_release", "gte_relay_push",
@@ -228,7 +230,7 @@ def load():
     lib.gte_default_chunks.argtypes = [C.c_int]
     lib.gte_default_chunks.restype = C.c_int
     for name in ("gte_reset", "gte_step", "gte_gather_obs", "gte_step_obs", "gte_step_host", "gte_step_host_begin", "gte_step_host_end", "gte_serve_stop", "gte_relay_supported", "gte_relay_alloc", "gte_relay_open",
-           "gte_relay_release", "gte_relay_push", "gte_relay_serve", "gte_host_register", "gte_host_unregister", "gte_rollout", "gte_info",
+           "gte_relay_release", "gte_relay_push", "gte_relay_serve", "gte_relay_unblock", "gte_host_register", "gte_host_unregister", "gte_rollout", "gte_info",
                  "gte_obs_variant_for"):
         getattr(lib, name).restype = C.c_int
     lib.gte_struct_size.argtypes = [C.c_int]

@@ -192,6 +192,11 @@ int gte_relay_serve(int lane, void* own_base, int64_t bytes, uint32_t seq, void*
     return check_cuda("gte_relay_serve", gte::relay_serve(lane, own_base, bytes, seq, host_dst, host_seq));
 }
 
+int gte_relay_unblock(void* own_base, uint32_t seq) {
+    GTE_REQUIRE("gte_relay_unblock", own_base != nullptr);
+    return check_cuda("gte_relay_unblock", gte::relay_unblock(own_base, seq));
+}
+
 int gte_host_register(void* ptr, int64_t bytes) {
     GTE_REQUIRE("gte_host_register", ptr != nullptr && bytes > 0);
     return check_cuda("gte_host_register", cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));

@@ -60,6 +60,7 @@ cudaError_t relay_open(const void* ipc_handle, void** dev_base);
 cudaError_t relay_release(void* dev_base, bool opened);
 cudaError_t relay_push(void* peer_base, const void* src_dev, int64_t bytes, uint32_t seq, cudaEvent_t after, cudaEvent_t done);
 cudaError_t relay_serve(int lane, void* own_base, int64_t bytes, uint32_t seq, void* host_dst, void* host_seq);
+cudaError_t relay_unblock(void* own_base, uint32_t seq);
 int default_chunks(int n_envs);
 int host_io_mode(const GteParams& P, int mode);
 cudaError_t serve_quiesce();

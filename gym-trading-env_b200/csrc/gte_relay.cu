@@ -120,4 +120,16 @@ cudaError_t relay_serve(int lane, void* own_base, int64_t bytes, uint32_t seq, v
     return cudaMemcpyAsync(host_seq, base, sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
 }
 
+// Release a serve stream that is waiting for a sequence word which will never come (a failed set-up): write the word from
+// this side.
+cudaError_t relay_unblock(void* own_base, uint32_t seq) {
+    cudaStream_t s = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(own_base, &seq, sizeof(seq), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    return e;
+}
+
 }  // namespace gte

@@ -210,7 +210,7 @@ class ResultRelay:
 
     def _setup(self, torch, dist):
         lib, N, rank = self.lib, self.N, self.rank
-        self.errors, self._own, self.relay_words, self.expect = [], {}, None, [0, 0]
+        self.errors, self._own, self.relay_words, self.expect, self.seq_base = [], {}, None, [0, 0], 0
         if not self.plan:
             return
         mine, err = {"paths": None, "handles": {}}, None
@@ -255,6 +255,31 @@ class ResultRelay:
             return self._switch_off()
         if self.peer is not None:
             self.relay_words = [b.array[self.block_bytes:self.block_bytes + 4].view(np.uint32) for b in self.blocks]
+        # self-test: ONE round trip per pair (sequence number 1, wire set 0) before the job depends on the road — IPC mapping,
+        # peer access, the stream wait and the peer's write into the shared block all have to work; if any pair fails, every
+        # rank goes back to the plain path instead of waiting for a word that never comes in the middle of a run
+        err = None
+        try:
+            for s in self.senders:
+                e = self.serve[s]
+                _cabi.check(lib.gte_relay_serve(e["lane"], C.c_void_p(e["own"][0]), 16, 1,
+                                                C.c_void_p(e["blocks"][0].ptr + 8 * (N - self.plan[s][1])), C.c_void_p(e["seq"][0])),
+                            "gte_relay_serve")
+            if self.peer is not None:
+                _cabi.check(lib.gte_relay_push(C.c_void_p(self.peer_bufs[0]), C.c_void_p(self.env._result_block.data_ptr()), 16, 1,
+                                               None, None), "gte_relay_push")
+                t0 = time.monotonic()
+                while self.relay_words[0][0] != 1:
+                    if time.monotonic() - t0 > 5.0:
+                        raise RuntimeError(f"no answer from rank {self.peer[0]} within 5 s")
+        except Exception as e:  # noqa: BLE001
+            err = e
+        self.seq_base = 1                                          # the job's sequence numbers start behind the self-test's
+        if not self._everyone_ok(dist, err):
+            for e in self.serve.values():                          # a serve stream may still be waiting: let it go
+                lib.gte_relay_unblock(C.c_void_p(e["own"][0]), 1)
+            torch.cuda.synchronize()
+            return self._switch_off()
 
     def _switch_off(self):
         self._release()
@@ -276,7 +301,7 @@ class ResultRelay:
     def before_begin(self):
         """Called first thing in step_async: enqueue, for every sender this rank serves, the wait for its data of this
         iteration and the two copies into its result block."""
-        k, seq = self.count & 1, (self.count + 1) & 0xffffffff
+        k, seq = self.count & 1, (self.count + 1 + self.seq_base) & 0xffffffff
         for s in self.senders:
             e, x = self.serve[s], self.plan[s][1]
             rc = self.lib.gte_relay_serve(e["lane"], C.c_void_p(e["own"][k]), 8 * x, seq,
@@ -286,7 +311,7 @@ class ResultRelay:
 
     def after_begin(self, k_set, dev_block_ptr, step_done_event):
         """Called right behind gte_step_host_begin: ship this iteration's reward tail to the peer."""
-        seq = (self.count + 1) & 0xffffffff
+        seq = (self.count + 1 + self.seq_base) & 0xffffffff
         if self.peer is not None:
             x = self.peer[1]
             rc = self.lib.gte_relay_push(C.c_void_p(self.peer_bufs[k_set]), C.c_void_p(dev_block_ptr + 8 * (self.N - x)), 8 * x, seq,

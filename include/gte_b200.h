@@ -369,6 +369,8 @@ int gte_step_host_end(const GteHostIO* io);
  *                   own_base holds a sequence number >= seq, copy `bytes` of payload to host_dst, then the 4-byte
  *                   sequence word to host_seq.  Both host addresses must be pinned for this process (gte_host_register).
  *                   Returns at once; the sender's host learns of completion by polling *host_seq == seq.
+ * gte_relay_unblock: (peer) write `seq` into own_base's header from this side: releases a serve stream whose sender will
+ *                   never deliver (set-up self-test failed) so that the buffer can be freed.
  * gte_host_register / gte_host_unregister: page-lock a host range (e.g. a shared-memory mapping) for DMA. */
 #define GTE_RELAY_HEADER_BYTES 256
 int gte_relay_supported(void);
@@ -377,6 +379,7 @@ int gte_relay_open(const void* ipc_handle, void** dev_base);
 int gte_relay_release(void* dev_base, int opened);
 int gte_relay_push(void* peer_base, const void* src_dev, int64_t bytes, uint32_t seq, void* after_event, void* done_event);
 int gte_relay_serve(int lane, void* own_base, int64_t bytes, uint32_t seq, void* host_dst, void* host_seq);
+int gte_relay_unblock(void* own_base, uint32_t seq);
 int gte_host_register(void* ptr, int64_t bytes);
 int gte_host_unregister(void* ptr);
 
