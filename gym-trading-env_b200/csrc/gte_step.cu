@@ -519,7 +519,7 @@ struct HostIOStreams {
     GteParams sp; GteData sd; GteState ss; GteStepOut so; float* sobs = nullptr; int sauto = 0;
     // gte_step_host_begin / _end: completion events of the result copies in flight, keyed by the host result block
     struct Pending { const void* results = nullptr; cudaEvent_t ev = nullptr; cudaEvent_t ev_in = nullptr; cudaEvent_t ev_step = nullptr;
-                     int64_t n = 0; bool sparse = false; } pending[4];
+                     int64_t n = 0; bool sparse = false; bool open = false; } pending[4];     // open: begun, not yet ended
 };
 static HostIOStreams g_hio[16];
 
@@ -773,6 +773,7 @@ cudaError_t launch_step_host_begin(const GteParams& P, const GteData& D, const G
     HostIOStreams::Pending* slot = nullptr;
     for (auto& p : h->pending) if (p.results == io.results) slot = &p;
     if (slot == nullptr) for (auto& p : h->pending) if (p.results == nullptr) { slot = &p; break; }
+    if (slot == nullptr) for (auto& p : h->pending) if (!p.open) { slot = &p; break; }     // a block whose iteration has ended: its slot is free
     if (slot == nullptr) return cudaErrorInvalidValue;       // more than 4 result blocks in flight
     if (slot->ev == nullptr) {
         if ((e = cudaEventCreateWithFlags(&slot->ev, cudaEventDisableTiming)) != cudaSuccess) return e;
@@ -780,6 +781,7 @@ cudaError_t launch_step_host_begin(const GteParams& P, const GteData& D, const G
         if ((e = cudaEventCreateWithFlags(&slot->ev_step, cudaEventDisableTiming)) != cudaSuccess) return e;
     }
     slot->results = io.results;
+    slot->open = true;
     slot->n = N;
     slot->sparse = io.sparse_flags != 0;
     GteStepOut o = O;
@@ -809,6 +811,7 @@ cudaError_t launch_step_host_end(const GteHostIO& io) {
     for (auto& p : h->pending)
         if (p.results == io.results && p.ev != nullptr) {
             if ((e = cudaEventSynchronize(p.ev)) != cudaSuccess) return e;
+            p.open = false;
             // (a later iteration's copy may be queued behind on the same stream: the rare dense fetch waits for it too)
             return p.sparse ? fetch_dense_flags_if_needed(io, p.n, h->out) : cudaSuccess;
         }

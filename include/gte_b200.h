@@ -340,7 +340,8 @@ int gte_step_host(const GteParams* params, const GteData* data, const GteState* 
  * dev_actions each their own; out->reward / terminated / truncated are again ignored) may call _begin for iteration
  * k+1 before _end for iteration k — what gymnasium 0.x / stable-baselines3 vector envs call step_async / step_wait:
  * the device-to-host copy of iteration k then runs under the action copy, transition and gather of iteration k+1.
- * A set's buffers are free for the next _begin once its _end has returned; at most 4 result blocks per device. */
+ * A set's buffers are free for the next _begin once its _end has returned; at most 4 result blocks IN FLIGHT (begun, not
+ * yet ended) per device. */
 int gte_step_host_begin(const GteParams* params, const GteData* data, const GteState* state, const GteHostIO* io,
                         const GteStepOut* out, float* obs, int autoreset, int variant, void* stream);
 int gte_step_host_end(const GteHostIO* io);

@@ -568,6 +568,33 @@ def test_persistent_rollout_with_dataset_rotation_and_narrow_actions_equals_step
     assert set(a._dataset_idx.cpu().tolist()) == {0, 1, 2}
 
 
+def test_result_block_slots_are_recycled_once_their_iteration_has_ended():
+    """gte_step_host_begin keeps at most 4 result blocks IN FLIGHT per device; blocks whose iteration has ended give their
+    slot back, so any number of envs (or wire sets rebuilt by enable_result_relay) can take turns."""
+    import gym_trading_env_b200 as gte
+    series = gte.frame_to_arrays(gte.make_gbm_ohlcv(5_000, seed=2))
+    kw = dict(positions=[-1, 0, 1], windows=4, max_episode_duration=30, num_envs=2048, seed=3, verbose=0, output="hybrid",
+              host_io="copy", **FEES)
+    envs = [gte.TradingVectorEnv(series, **kw) for _ in range(4)]          # 4 envs x 2 wire sets = 8 result blocks
+    ref = gte.TradingVectorEnv(series, **kw)
+    acts = np.random.default_rng(1).integers(0, 3, size=(6, 2048)).astype(np.int8)
+    for e in envs + [ref]:
+        e.reset()
+    for k in range(6):
+        want = ref.step(acts[k])
+        for e in envs:
+            e.step_async(acts[k])
+            got = e.step_wait()
+            H.assert_bits(got[1], want[1], f"step {k} reward")
+    envs[0].step_async(acts[0]); envs[0].step_async(acts[1]); envs[1].step_async(acts[0]); envs[1].step_async(acts[1])
+    with pytest.raises(RuntimeError):                                      # a fifth block in flight is refused, loudly
+        envs[2].step_async(acts[0])
+    for e in (envs[0], envs[0], envs[1], envs[1]):
+        e.step_wait()
+    for e in envs + [ref]:
+        e.close()
+
+
 def test_reward_host_count_stops_the_results_copy_where_the_relay_takes_over():
     """GteHostIO.reward_host_count (the result relay's hook in the C-ABI): the call's own device-to-host copy delivers the
     first `count` rewards and the header / list / flags; rewards [count, N) stay on the device (for the caller to route
