@@ -57,10 +57,12 @@ def main():
 
     half = world // 2
     rows = []
-    for frac in (0.15, 0.20, 0.25, 0.30, 0.0, 0.10, 0.35):
+    for frac in (0.0, 0.10, 0.15, 0.20, 0.25, 0.30, 0.35):
         x = int(frac * N) // 1024 * 1024
         if x > 0:
             env.enable_result_relay(plan={s: (s + half, x) for s in range(half)})
+        else:
+            env.close_extras()                                         # fraction 0: leave the relay (collective)
         row = {"fraction": frac, "ms_one_step_at_a_time": round(timed(sync), 4), "ms_two_in_flight": round(timed(piped), 4)}
         rows.append(row)
         if rank == 0:
