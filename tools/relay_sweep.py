@@ -27,11 +27,12 @@ def main():
                                num_envs=N, env_id_offset=rank * N, seed=0, verbose=0, output="hybrid")
     env.reset()
     rng = np.random.default_rng(rank)
-    sets = []
+    sets, keep = [], []
     for _ in range(4):
-        a = env.pinned_actions().copy() if False else torch.empty(N, dtype=torch.int8, pin_memory=True).numpy()
-        a[...] = rng.integers(0, 7, size=N)
-        sets.append(a)
+        t = torch.empty(N, dtype=torch.int8, pin_memory=True)       # pinned: read by the GPU in place
+        t.numpy()[...] = rng.integers(0, 7, size=N)
+        keep.append(t)
+        sets.append(t.numpy())
 
     def timed(fn):
         fn(5)
@@ -56,7 +57,6 @@ def main():
             env.step_wait()
 
     half = world // 2
-    rows = []
     for frac in (0.0, 0.10, 0.15, 0.20, 0.25, 0.30, 0.35):
         x = int(frac * N) // 1024 * 1024
         if x > 0:
@@ -64,7 +64,6 @@ def main():
         else:
             env.close_extras()                                         # fraction 0: leave the relay (collective)
         row = {"fraction": frac, "ms_one_step_at_a_time": round(timed(sync), 4), "ms_two_in_flight": round(timed(piped), 4)}
-        rows.append(row)
         if rank == 0:
             print(json.dumps(row), flush=True)
     env.close()
